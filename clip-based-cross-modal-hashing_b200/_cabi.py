@@ -1,0 +1,154 @@
+"""ctypes binding of ``libcmh_b200.so`` (declared in ``include/cmh_b200.h``).
+
+This is the only place the Python host code touches the C ABI.  There is deliberately no fallback: when the
+library is missing or fails to load, every entry point raises - the oracle under ``oracle/`` is test
+infrastructure and is never imported from here.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+from typing import List, Optional
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
+LIB_PATH = os.path.join(_PKG_DIR, "libcmh_b200.so")
+INCLUDE_DIR = os.path.join(os.path.dirname(_PKG_DIR), "include")
+SOURCES = ("api.cu", "pack.cu", "dense.cu", "eval_tile.cu", "eval_warp.cu", "eval_host.cu")
+NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared")
+
+CMH_MAX_TOPN = 64
+CMH_MAX_BITS = 4096
+DTYPE_CODES = {"float32": 0, "float16": 1, "bfloat16": 2, "float64": 3, "int8": 4, "int32": 5, "int64": 6, "uint8": 7}
+
+# every symbol include/cmh_b200.h declares (tests check that the built library exports each of them)
+EXPORTS = (
+    "cmh_abi_version", "cmh_last_error", "cmh_device_info",
+    "cmh_pack_codes", "cmh_pack_labels", "cmh_synth_codes",
+    "cmh_hamming_dense", "cmh_neighbor_dense",
+    "cmh_eval_plan", "cmh_eval_plan_design", "cmh_eval_hist", "cmh_eval_rank",
+    "cmh_finalize_map", "cmh_finalize_topn", "cmh_finalize_pr_workspace_bytes", "cmh_finalize_pr",
+    "cmh_map_k_workspace_bytes", "cmh_map_k",
+    "cmh_topk", "cmh_topk_merge",
+)
+
+
+class CodeSet(ctypes.Structure):
+    """``cmh_codeset``"""
+    _fields_ = [("sign", ctypes.c_void_p), ("valid", ctypes.c_void_p), ("labels", ctypes.c_void_p),
+                ("n", ctypes.c_int64)]
+
+
+class Plan(ctypes.Structure):
+    """``cmh_plan``"""
+    _fields_ = [("bits", ctypes.c_int32), ("words", ctypes.c_int32), ("nlab", ctypes.c_int32),
+                ("lwords", ctypes.c_int32), ("ternary", ctypes.c_int32), ("max_topn", ctypes.c_int32),
+                ("nb", ctypes.c_int32), ("design", ctypes.c_int32), ("q_tile", ctypes.c_int32),
+                ("n_qtiles", ctypes.c_int32), ("chunk_rows", ctypes.c_int32), ("n_chunks", ctypes.c_int32),
+                ("nq", ctypes.c_int64), ("nd", ctypes.c_int64), ("nq_pad", ctypes.c_int64),
+                ("workspace_bytes", ctypes.c_uint64)]
+
+
+def sources() -> List[str]:
+    return [os.path.join(CSRC_DIR, s) for s in SOURCES]
+
+
+def _stale() -> bool:
+    if not os.path.isfile(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    deps = sources() + [os.path.join(CSRC_DIR, h) for h in os.listdir(CSRC_DIR) if h.endswith((".cuh", ".h"))]
+    deps.append(os.path.join(INCLUDE_DIR, "cmh_b200.h"))
+    return any(os.path.getmtime(d) > built for d in deps if os.path.isfile(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile ``csrc/*.cu`` for sm_100a into ``libcmh_b200.so`` next to this file (nvcc cross-compiles without a
+    GPU).  Skips the compile when the library is newer than every source."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, *sources()]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded library.  Raises RuntimeError when it has not been built - there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.isfile(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(cmh_b200 has no CPU fallback)")
+            L = ctypes.CDLL(LIB_PATH)
+            _declare(L)
+            if L.cmh_abi_version() != 1:
+                raise RuntimeError("libcmh_b200.so ABI version mismatch")
+            _lib = L
+    return _lib
+
+
+def _declare(L: ctypes.CDLL) -> None:
+    vp, i32, i64, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64
+    pcs, ppl = ctypes.POINTER(CodeSet), ctypes.POINTER(Plan)
+    L.cmh_abi_version.restype = i32
+    L.cmh_last_error.restype = ctypes.c_char_p
+    L.cmh_device_info.argtypes = [ctypes.POINTER(i32)] * 3 + [ctypes.POINTER(u64)]
+    L.cmh_pack_codes.argtypes = [vp, i32, i64, i32, i64, vp, vp, vp, vp]
+    L.cmh_pack_labels.argtypes = [vp, i32, i64, i32, i64, vp, vp, vp]
+    L.cmh_synth_codes.argtypes = [u64, i64, i64, i32, vp, vp]
+    L.cmh_hamming_dense.argtypes = [pcs, pcs, i32, vp, i64, vp]
+    L.cmh_neighbor_dense.argtypes = [vp, i64, vp, i64, i32, vp, i64, vp]
+    L.cmh_eval_plan.argtypes = [i64, i64, i32, i32, i32, i32, ppl]
+    L.cmh_eval_plan_design.argtypes = [i64, i64, i32, i32, i32, i32, i32, ppl]
+    L.cmh_eval_hist.argtypes = [ppl, pcs, pcs, vp, vp, vp, vp]
+    L.cmh_eval_rank.argtypes = [ppl, pcs, pcs, i64, vp, vp, vp, vp, ctypes.POINTER(i64), i32, vp, vp, vp, vp, vp]
+    L.cmh_finalize_map.argtypes = [vp, vp, i64, i64, vp, vp, vp]
+    L.cmh_finalize_topn.argtypes = [vp, vp, i64, ctypes.POINTER(i64), i32, i64, vp, vp]
+    L.cmh_finalize_pr_workspace_bytes.argtypes = [i64, i32]
+    L.cmh_finalize_pr_workspace_bytes.restype = u64
+    L.cmh_finalize_pr.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp]
+    L.cmh_map_k_workspace_bytes.argtypes = [i64, i64, i32, i32, i32]
+    L.cmh_map_k_workspace_bytes.restype = u64
+    L.cmh_map_k.argtypes = [pcs, pcs, i32, i32, i64, vp, vp, vp, u64, vp]
+    L.cmh_topk.argtypes = [ppl, pcs, pcs, i32, i64, vp, vp, vp]
+    L.cmh_topk_merge.argtypes = [vp, i32, i64, i32, vp, vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("cmh_last_error", "cmh_finalize_pr_workspace_bytes", "cmh_map_k_workspace_bytes"):
+            fn.restype = i32
+
+
+def last_error() -> str:
+    msg = lib().cmh_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int, what: str = "") -> None:
+    """0 -> ok; negative -> ValueError (argument / shape errors); positive -> RuntimeError (CUDA error code)."""
+    if rc == 0:
+        return
+    msg = f"{what}: {last_error()} (code {rc})" if what else f"{last_error()} (code {rc})"
+    if rc < 0:
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+def i64_array(values) -> Optional[ctypes.Array]:
+    values = [int(v) for v in values]
+    return (ctypes.c_int64 * len(values))(*values) if values else None

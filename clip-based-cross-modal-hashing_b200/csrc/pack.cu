@@ -1,0 +1,264 @@
+// K1 - sign + bit-pack.  Replaces the float32 code buffers that train/base.py:141-146 fills with torch.sign
+// output (and the float multi-hot labels of dataset/base.py:89-94) by packed 64-bit words:
+//   sign plane  bit = (x > 0)      valid plane  bit = (x != 0)      label mask  bit = (L != 0)
+// HBM-bound: 4*n*bits bytes in, n*ceil(bits/64)*8 (x2 with the valid plane) out.
+#include <algorithm>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace cmh {
+
+template <typename T>
+struct Cls {
+    __device__ static __forceinline__ void get(T v, bool& pos, bool& zero, bool& unit) {
+        float f = (float)v;
+        pos = f > 0.f; zero = f == 0.f; unit = fabsf(f) == 1.f;
+    }
+};
+template <>
+struct Cls<double> {
+    __device__ static __forceinline__ void get(double v, bool& pos, bool& zero, bool& unit) {
+        pos = v > 0.0; zero = v == 0.0; unit = fabs(v) == 1.0;
+    }
+};
+template <>
+struct Cls<long long> {
+    __device__ static __forceinline__ void get(long long v, bool& pos, bool& zero, bool& unit) {
+        pos = v > 0; zero = v == 0; unit = (v == 1 || v == -1);
+    }
+};
+template <>
+struct Cls<__half> {
+    __device__ static __forceinline__ void get(__half v, bool& pos, bool& zero, bool& unit) {
+        Cls<float>::get(__half2float(v), pos, zero, unit);
+    }
+};
+template <>
+struct Cls<__nv_bfloat16> {
+    __device__ static __forceinline__ void get(__nv_bfloat16 v, bool& pos, bool& zero, bool& unit) {
+        Cls<float>::get(__bfloat162float(v), pos, zero, unit);
+    }
+};
+
+__device__ __forceinline__ void warp_count_flush(unsigned long long a, unsigned long long b,
+                                                 unsigned long long* counters) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if ((threadIdx.x & 31) == 0 && counters != nullptr) {
+        if (a) atomicAdd(&counters[0], a);
+        if (b) atomicAdd(&counters[1], b);
+    }
+}
+
+// ---- fast path: float32, contiguous rows, bits % 32 == 0 -------------------------------------------------------
+// The matrix is a flat stream of float4; 8 consecutive lanes own one 32-bit output word.  Each thread keeps
+// UNROLL independent 16-byte loads in flight (Guideline 7/13: vectorised, coalesced, MLP before use).
+constexpr int PACK_UNROLL = 4;
+
+__global__ void __launch_bounds__(256) pack_codes_f32_fast(const float4* __restrict__ x, int64_t n_vec,
+                                                           int w32_per_row_in,   // bits / 32
+                                                           int w32_per_row_out,  // words * 2
+                                                           uint32_t* __restrict__ sign32,
+                                                           uint32_t* __restrict__ valid32,
+                                                           unsigned long long* counters) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    unsigned long long n_zero = 0, n_odd = 0;
+    for (int64_t f0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f0 - lane < n_vec; f0 += stride * PACK_UNROLL) {
+        float4 v[PACK_UNROLL];
+#pragma unroll
+        for (int u = 0; u < PACK_UNROLL; ++u) {
+            const int64_t f = f0 + u * stride;
+            v[u] = f < n_vec ? __ldcs(x + f) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+#pragma unroll
+        for (int u = 0; u < PACK_UNROLL; ++u) {
+            const int64_t f = f0 + u * stride;
+            const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            uint32_t s = 0, nz = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                s |= (e[c] > 0.f ? 1u : 0u) << c;
+                nz |= (e[c] != 0.f ? 1u : 0u) << c;
+                n_zero += e[c] == 0.f;
+                n_odd += (e[c] != 0.f) && (fabsf(e[c]) != 1.f);
+            }
+            // nibble -> byte -> half -> word across 8 lanes
+            uint32_t sv = s | (nz << 16);
+            sv |= (__shfl_down_sync(0xffffffffu, sv, 1) & 0x000f000fu) << 4;
+            sv |= (__shfl_down_sync(0xffffffffu, sv, 2) & 0x00ff00ffu) << 8;
+            // after two steps lanes %4==0 hold 16 bits of each plane in [0,16) and [16,32)
+            const uint32_t hi = __shfl_down_sync(0xffffffffu, sv, 4);
+            if ((lane & 7) == 0 && f < n_vec) {
+                const uint32_t sw = (sv & 0xffffu) | ((hi & 0xffffu) << 16);
+                const uint32_t vw = (sv >> 16) | (hi & 0xffff0000u);
+                const int64_t w_flat = f >> 3;
+                const int64_t row = w_flat / w32_per_row_in;
+                const int w = (int)(w_flat - row * w32_per_row_in);
+                const int64_t o = row * w32_per_row_out + w;
+                sign32[o] = sw;
+                if (valid32) valid32[o] = vw;
+                if (w == w32_per_row_in - 1 && (w32_per_row_in & 1)) {  // clear the unused high half-word
+                    sign32[o + 1] = 0u;
+                    if (valid32) valid32[o + 1] = 0u;
+                }
+            }
+        }
+    }
+    warp_count_flush(n_zero, n_odd, counters);
+}
+
+// ---- generic path: any dtype / leading dimension / width; one warp per row, lane = column, ballot packs --------
+constexpr int PACK_ROWS = 4;  // rows in flight per warp
+
+template <typename T, bool LABELS>
+__global__ void __launch_bounds__(256) pack_rows_generic(const T* __restrict__ x, int64_t n, int ncols, int64_t ld,
+                                                         int w32_out, uint32_t* __restrict__ sign32,
+                                                         uint32_t* __restrict__ valid32,
+                                                         unsigned long long* counters) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int n_seg = (ncols + 31) >> 5;
+    unsigned long long c0 = 0, c1 = 0;
+    for (int64_t r0 = warp * PACK_ROWS; r0 < n; r0 += n_warps * PACK_ROWS) {
+        for (int seg = 0; seg < w32_out; ++seg) {
+            const int col = seg * 32 + lane;
+            T v[PACK_ROWS];
+#pragma unroll
+            for (int u = 0; u < PACK_ROWS; ++u) {
+                const int64_t r = r0 + u;
+                v[u] = (seg < n_seg && col < ncols && r < n) ? x[r * ld + col] : T(0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < PACK_ROWS; ++u) {
+                const int64_t r = r0 + u;
+                bool pos, zero, unit;
+                Cls<T>::get(v[u], pos, zero, unit);
+                const bool live = seg < n_seg && col < ncols && r < n;
+                uint32_t sw, vw;
+                if (LABELS) {
+                    sw = __ballot_sync(0xffffffffu, live && !zero);
+                    vw = 0;
+                    c0 += live && !pos && !zero;  // negative label entry
+                } else {
+                    sw = __ballot_sync(0xffffffffu, live && pos);
+                    vw = __ballot_sync(0xffffffffu, live && !zero);
+                    c0 += live && zero;
+                    c1 += live && !zero && !unit;
+                }
+                if (lane == 0 && r < n) {
+                    sign32[r * w32_out + seg] = sw;
+                    if (!LABELS && valid32) valid32[r * w32_out + seg] = vw;
+                }
+            }
+        }
+    }
+    warp_count_flush(c0, c1, counters);
+}
+
+__device__ __forceinline__ uint64_t splitmix64_dev(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256) synth_codes_kernel(uint64_t base, int64_t row0, int64_t n, int words,
+                                                          uint64_t tail_mask, uint64_t* __restrict__ out) {
+    const int64_t total = n * words;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / words;
+        const int w = (int)(i - r * words);
+        uint64_t v = splitmix64_dev(base + (uint64_t)((row0 + r) * words + w));
+        if (w == words - 1) v &= tail_mask;
+        out[i] = v;
+    }
+}
+
+template <bool LABELS>
+static int launch_generic(const void* x, int dtype, int64_t n, int ncols, int64_t ld, int w32_out, uint32_t* s32,
+                          uint32_t* v32, unsigned long long* counters, cudaStream_t st) {
+    const int block = 256;
+    const int64_t warps_needed = ceil_div(n, PACK_ROWS);
+    int grid = (int)std::min<int64_t>(ceil_div(warps_needed * 32, block), (int64_t)sm_count() * 16);
+    if (grid < 1) grid = 1;
+#define CMH_PACK_CASE(DT, T)                                                                                     \
+    case DT:                                                                                                     \
+        pack_rows_generic<T, LABELS><<<grid, block, 0, st>>>((const T*)x, n, ncols, ld, w32_out, s32, v32, counters); \
+        break;
+    switch (dtype) {
+        CMH_PACK_CASE(CMH_F32, float)
+        CMH_PACK_CASE(CMH_F16, __half)
+        CMH_PACK_CASE(CMH_BF16, __nv_bfloat16)
+        CMH_PACK_CASE(CMH_F64, double)
+        CMH_PACK_CASE(CMH_I8, signed char)
+        CMH_PACK_CASE(CMH_I32, int)
+        CMH_PACK_CASE(CMH_I64, long long)
+        CMH_PACK_CASE(CMH_U8, unsigned char)
+        default:
+            set_error("unsupported dtype %d", dtype);
+            return CMH_ERR_UNSUPPORTED;
+    }
+#undef CMH_PACK_CASE
+    CMH_LAUNCH_CHECK("pack_rows_generic");
+    return CMH_OK;
+}
+
+}  // namespace cmh
+
+using namespace cmh;
+
+extern "C" int cmh_pack_codes(const void* x, int dtype, int64_t n, int bits, int64_t ld, uint64_t* sign_out,
+                              uint64_t* valid_out, unsigned long long* counters, void* stream) {
+    CMH_REQUIRE(n >= 0 && bits > 0 && ld >= bits, CMH_ERR_ARG, "cmh_pack_codes: bad shape n=%lld bits=%d ld=%lld",
+                (long long)n, bits, (long long)ld);
+    CMH_REQUIRE(bits <= CMH_MAX_BITS, CMH_ERR_UNSUPPORTED, "cmh_pack_codes: bits=%d > %d", bits, CMH_MAX_BITS);
+    if (n == 0) return CMH_OK;
+    CMH_REQUIRE(x && sign_out, CMH_ERR_ARG, "cmh_pack_codes: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int words = (bits + 63) / 64;
+    const bool fast = dtype == CMH_F32 && ld == bits && (bits % 32) == 0 && (((uintptr_t)x) & 15) == 0;
+    if (fast) {
+        const int64_t n_vec = n * bits / 4;
+        const int block = 256;
+        int grid = (int)std::min<int64_t>(ceil_div(n_vec, (int64_t)block * PACK_UNROLL), (int64_t)sm_count() * 8);
+        if (grid < 1) grid = 1;
+        pack_codes_f32_fast<<<grid, block, 0, st>>>((const float4*)x, n_vec, bits / 32, words * 2,
+                                                    (uint32_t*)sign_out, (uint32_t*)valid_out, counters);
+        CMH_LAUNCH_CHECK("pack_codes_f32_fast");
+        return CMH_OK;
+    }
+    return launch_generic<false>(x, dtype, n, bits, ld, words * 2, (uint32_t*)sign_out, (uint32_t*)valid_out,
+                                 counters, st);
+}
+
+extern "C" int cmh_pack_labels(const void* L, int dtype, int64_t n, int nlab, int64_t ld, uint64_t* out,
+                               unsigned long long* neg_counter, void* stream) {
+    CMH_REQUIRE(n >= 0 && nlab > 0 && ld >= nlab, CMH_ERR_ARG, "cmh_pack_labels: bad shape n=%lld nlab=%d ld=%lld",
+                (long long)n, nlab, (long long)ld);
+    if (n == 0) return CMH_OK;
+    CMH_REQUIRE(L && out, CMH_ERR_ARG, "cmh_pack_labels: NULL pointer");
+    const int lwords = (nlab + 63) / 64;
+    return launch_generic<true>(L, dtype, n, nlab, ld, lwords * 2, (uint32_t*)out, nullptr, neg_counter,
+                                (cudaStream_t)stream);
+}
+
+extern "C" int cmh_synth_codes(uint64_t seed, int64_t row0, int64_t n, int bits, uint64_t* out, void* stream) {
+    CMH_REQUIRE(n >= 0 && bits > 0 && row0 >= 0, CMH_ERR_ARG, "cmh_synth_codes: bad arguments");
+    if (n == 0) return CMH_OK;
+    CMH_REQUIRE(out, CMH_ERR_ARG, "cmh_synth_codes: NULL pointer");
+    const int words = (bits + 63) / 64;
+    const int tail = bits - 64 * (words - 1);
+    const uint64_t tail_mask = tail >= 64 ? ~0ull : ((1ull << tail) - 1ull);
+    const int block = 256;
+    int grid = (int)std::min<int64_t>(ceil_div(n * words, block), (int64_t)sm_count() * 16);
+    synth_codes_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(seed * 0x100000001B3ull, row0, n, words, tail_mask, out);
+    CMH_LAUNCH_CHECK("synth_codes_kernel");
+    return CMH_OK;
+}

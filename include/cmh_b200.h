@@ -1,0 +1,166 @@
+/* cmh_b200 - C ABI of the B200-native retrieval-evaluation path (libcmh_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of QinLab-WFU/CLIP-based-Cross-Modal-Hashing: the retrieval evaluation in
+ * utils/calc_utils.py that train/base.py:259-262,299-302 and train/TwDH/hash_train.py:221-224 run on the
+ * sign()-binarised image / text hash codes.  The reference is pure Python on torch CPU ops and has no FFI of
+ * its own; the entry points below are what a ctypes binding of that path binds (INTEGRATION.md shows the stub),
+ * one group per reference function:
+ *
+ *   reference site (file:line)                                   entry points
+ *   ------------------------------------------------------------ -------------------------------------------
+ *   torch.sign + float buffers, train/base.py:141-146            cmh_pack_codes
+ *   float multi-hot labels, dataset/base.py:89-94                cmh_pack_labels
+ *   calc_hammingDist, utils/calc_utils.py:8-13                   cmh_hamming_dense
+ *   calc_neighbor, utils/calc_utils.py:4-5,42-45                 cmh_neighbor_dense
+ *   calc_map_k_matrix, utils/calc_utils.py:16-39                 cmh_eval_plan / cmh_eval_hist / cmh_eval_rank /
+ *     gnd :26-27, sort+gather :31-33, AP :34-38                  cmh_finalize_map  (one call each: cmh_map_k)
+ *   p_topK / pr_curve (north star; not in the reference)         cmh_eval_rank (topn hits) + cmh_finalize_topn,
+ *                                                                cmh_finalize_pr
+ *   stable top-K ranking (north star config 4)                   cmh_topk, cmh_topk_merge
+ *
+ * Conventions
+ *   - every pointer marked "device" is a CUDA device pointer on the current device, 16-byte aligned;
+ *     `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls only enqueue work;
+ *     nothing synchronises unless stated.
+ *   - every function returns 0 on success, a negative CMH_ERR_* for argument errors, or a positive
+ *     cudaError_t.  cmh_last_error() returns a thread-local message for the last non-zero return.
+ *   - packed codes: uint64 [n][words], words = ceil(bits/64); bit (c % 64) of word (c / 64) is column c;
+ *     padding bits are 0.  "sign" plane: x > 0.  "valid" plane: x != 0 (NULL = every entry is +-1).
+ *   - packed labels: uint64 [n][lwords], lwords = ceil(nlab/64), bit = (L != 0).
+ *   - buckets: with both valid planes NULL (binary mode) bucket b = Hamming distance, nb = bits + 1; otherwise
+ *     (ternary mode) bucket b = 2 * dist = bits - <q, r>, nb = 2 * bits + 1.   top-K keys always carry 2*dist.
+ *   - in ternary mode the ranking entry points need BOTH valid planes (cmh_pack_codes always can write one).
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef CMH_B200_H
+#define CMH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMH_ABI_VERSION 1
+
+#define CMH_OK 0
+#define CMH_ERR_ARG (-1)         /* NULL / negative size / inconsistent arguments            */
+#define CMH_ERR_UNSUPPORTED (-2) /* bits > CMH_MAX_BITS, unknown dtype ...                    */
+#define CMH_ERR_WORKSPACE (-3)   /* workspace too small for the plan                          */
+#define CMH_ERR_DEVICE (-4)      /* not an sm_100 device / no device                          */
+
+#define CMH_MAX_BITS 4096
+#define CMH_MAX_TOPN 64
+
+enum cmh_dtype { CMH_F32 = 0, CMH_F16 = 1, CMH_BF16 = 2, CMH_F64 = 3, CMH_I8 = 4, CMH_I32 = 5, CMH_I64 = 6, CMH_U8 = 7 };
+
+/* One side of a comparison (queries or database shard), all device pointers. */
+typedef struct cmh_codeset {
+    const uint64_t* sign;   /* [n][words]                                  */
+    const uint64_t* valid;  /* [n][words] or NULL (all entries are +-1)    */
+    const uint64_t* labels; /* [n][lwords] or NULL (no relevance needed)   */
+    int64_t n;
+} cmh_codeset;
+
+/* Launch geometry chosen by cmh_eval_plan; pass the same plan to hist and rank. */
+typedef struct cmh_plan {
+    int32_t bits, words, nlab, lwords, ternary;
+    int32_t max_topn;      /* precision@N cutoffs the workspace has room for                       */
+    int32_t nb;            /* buckets (bits+1 or 2*bits+1)                                         */
+    int32_t design;        /* 0 = thread-per-query tile kernels, 1 = warp-per-query generic kernels */
+    int32_t q_tile;        /* queries per CTA                                                      */
+    int32_t n_qtiles;
+    int32_t chunk_rows;    /* database rows per CTA column (multiple of 16, <= 65520)              */
+    int32_t n_chunks;
+    int64_t nq, nd, nq_pad;
+    uint64_t workspace_bytes;
+} cmh_plan;
+
+int cmh_abi_version(void);
+const char* cmh_last_error(void);
+/* sm count / compute capability / total memory of the current device */
+int cmh_device_info(int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem);
+
+/* ---- K1: sign + bit-pack ---------------------------------------------------------------------------------- */
+/* x: device [n][ld] of `dtype` (first `bits` columns used).  sign_out / valid_out: device [n][words]
+ * (valid_out may be NULL).  counters: device uint64[2], INCREMENTED by (#entries == 0, #entries not in
+ * {-1, 0, +1}); may be NULL. */
+int cmh_pack_codes(const void* x, int dtype, int64_t n, int bits, int64_t ld,
+                   uint64_t* sign_out, uint64_t* valid_out, unsigned long long* counters, void* stream);
+/* L: device [n][ld] multi-hot (non-negative).  out: device [n][lwords].  neg_counter: device uint64[1],
+ * incremented by #entries < 0 (the reference's `dot > 0` predicate is only a set intersection for L >= 0). */
+int cmh_pack_labels(const void* L, int dtype, int64_t n, int nlab, int64_t ld,
+                    uint64_t* out, unsigned long long* neg_counter, void* stream);
+/* counter-based synthetic packed codes (bench / tests): word w of global row r =
+ * splitmix64(seed * 0x100000001B3 + r * words + w), tail bits cleared.  out: device [n][words]. */
+int cmh_synth_codes(uint64_t seed, int64_t row0, int64_t n, int bits, uint64_t* out, void* stream);
+
+/* ---- a2 / a4: dense blocks -------------------------------------------------------------------------------- */
+/* out[i][j] = 0.5 * (bits - <q_i, d_j>)  float32, device [q->n][ld_out] */
+int cmh_hamming_dense(const cmh_codeset* q, const cmh_codeset* d, int bits, float* out, int64_t ld_out, void* stream);
+/* out[i][j] = 1.0f if label rows i, j intersect else 0.0f */
+int cmh_neighbor_dense(const uint64_t* la, int64_t na, const uint64_t* lb, int64_t nb_rows, int lwords,
+                       float* out, int64_t ld_out, void* stream);
+
+/* ---- a3 / a5 / a6: ranking by counting --------------------------------------------------------------------- */
+/* Fills *plan (host struct) for nq queries against an nd-row database shard on the current device.
+ * nlab: number of labels (0 = no relevance, e.g. top-K); ternary: 1 when either side has a valid plane;
+ * max_topn: largest ntopn a later cmh_eval_rank may pass.  plan->workspace_bytes is the device scratch needed. */
+int cmh_eval_plan(int64_t nq, int64_t nd, int bits, int nlab, int ternary, int max_topn, cmh_plan* plan);
+/* Same with the kernel design forced (0 tile, 1 warp, -1 automatic) - used by the tests to cover both designs
+ * on small inputs. */
+int cmh_eval_plan_design(int64_t nq, int64_t nd, int bits, int nlab, int ternary, int max_topn, int design,
+                         cmh_plan* plan);
+
+/* Pass 1.  Per-(query, chunk) bucket histograms into `workspace` and their sum over this shard into
+ * hist_all / hist_rel: device uint32 [nq][nb] (hist_rel may be NULL when q->labels is NULL). */
+int cmh_eval_hist(const cmh_plan* plan, const cmh_codeset* q, const cmh_codeset* d,
+                  uint32_t* hist_all, uint32_t* hist_rel, void* workspace, void* stream);
+
+/* Pass 2.  Must follow cmh_eval_hist with the same plan / inputs / workspace.
+ *   k            reference `k` (<0 = None = all)                                 calc_utils.py:23-24,34
+ *   lower_*      device uint32 [nq][nb]: rows of LOWER-indexed shards per bucket, NULL on one GPU
+ *   global_*     device uint32 [nq][nb]: rows of ALL shards per bucket,          NULL on one GPU
+ *   topn/ntopn   HOST int64 list for precision@N (ntopn <= CMH_MAX_TOPN), hits: device uint32 [nq][ntopn]
+ *   ap_sum       device double [nq]: sum over this shard's relevant rows with relrank <= min(k, n_rel) of
+ *                relrank / rank   (AP = ap_sum / min(k, n_rel) once summed over shards)
+ *   n_rel        device int64 [nq]: relevant rows over all shards                 calc_utils.py:27 */
+int cmh_eval_rank(const cmh_plan* plan, const cmh_codeset* q, const cmh_codeset* d, int64_t k,
+                  const uint32_t* lower_all, const uint32_t* lower_rel,
+                  const uint32_t* global_all, const uint32_t* global_rel,
+                  const int64_t* topn, int ntopn, uint32_t* hits,
+                  double* ap_sum, int64_t* n_rel, void* workspace, void* stream);
+
+/* ap[q] = ap_sum[q] / min(k, n_rel[q]) (0 when n_rel == 0), *map = float(sum_q ap[q] / nq).
+ * ap (device double [nq]) may be NULL; map: device float[1].                    calc_utils.py:37-38 */
+int cmh_finalize_map(const double* ap_sum, const int64_t* n_rel, int64_t nq, int64_t k,
+                     double* ap, float* map, void* stream);
+/* prec[i] = (1/nq) * sum over queries with n_rel > 0 of hits[q][i] / min(topn[i], nd_total).  prec: device float [ntopn] */
+int cmh_finalize_topn(const uint32_t* hits, const int64_t* n_rel, int64_t nq, const int64_t* topn, int ntopn,
+                      int64_t nd_total, float* prec, void* stream);
+/* Hamming-radius PR curve from (global) bucket histograms.  P, R: device float [bits+1];
+ * workspace: device scratch of cmh_finalize_pr_workspace_bytes(nq, bits). */
+uint64_t cmh_finalize_pr_workspace_bytes(int64_t nq, int bits);
+int cmh_finalize_pr(const uint32_t* hist_all, const uint32_t* hist_rel, int64_t nq, int bits, int ternary,
+                    float* P, float* R, void* workspace, void* stream);
+
+/* One-call single-GPU calc_map_k_matrix (plan + hist + rank + finalize).
+ * workspace >= cmh_map_k_workspace_bytes(...). */
+uint64_t cmh_map_k_workspace_bytes(int64_t nq, int64_t nd, int bits, int nlab, int ternary);
+int cmh_map_k(const cmh_codeset* q, const cmh_codeset* d, int bits, int nlab, int64_t k,
+              double* ap /* device [nq] or NULL */, float* map /* device [1] */,
+              void* workspace, uint64_t workspace_bytes, void* stream);
+
+/* ---- top-K retrieval ---------------------------------------------------------------------------------------- */
+/* keys: device uint64 [nq][K], ascending (2*dist << 32) | (index_base + row); padded with UINT64_MAX when
+ * nd < K.  Uses the same plan / workspace as the eval passes (lwords = 0). */
+int cmh_topk(const cmh_plan* plan, const cmh_codeset* q, const cmh_codeset* d, int K, int64_t index_base,
+             uint64_t* keys, void* workspace, void* stream);
+/* keys_in: device uint64 [n_lists][nq][K] (each row ascending) -> keys_out: device [nq][K] smallest. */
+int cmh_topk_merge(const uint64_t* keys_in, int n_lists, int64_t nq, int K, uint64_t* keys_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMH_B200_H */
