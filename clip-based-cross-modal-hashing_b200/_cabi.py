@@ -16,7 +16,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "libcmh_b200.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(_PKG_DIR), "include")
-SOURCES = ("api.cu", "pack.cu", "dense.cu", "eval_tile.cu", "eval_warp.cu", "eval_host.cu")
+SOURCES = ("api.cu", "pack.cu", "dense.cu", "eval_tile.cu", "eval_warp.cu", "eval_host.cu", "peaks.cu")
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared")
 
@@ -26,7 +26,7 @@ DTYPE_CODES = {"float32": 0, "float16": 1, "bfloat16": 2, "float64": 3, "int8": 
 
 # every symbol include/cmh_b200.h declares (tests check that the built library exports each of them)
 EXPORTS = (
-    "cmh_abi_version", "cmh_last_error", "cmh_device_info",
+    "cmh_abi_version", "cmh_last_error", "cmh_device_info", "cmh_launch_count", "cmh_measure_popc_peak",
     "cmh_pack_codes", "cmh_pack_labels", "cmh_synth_codes",
     "cmh_hamming_dense", "cmh_neighbor_dense",
     "cmh_eval_plan", "cmh_eval_plan_design", "cmh_eval_hist", "cmh_eval_rank",
@@ -109,6 +109,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cmh_abi_version.restype = i32
     L.cmh_last_error.restype = ctypes.c_char_p
     L.cmh_device_info.argtypes = [ctypes.POINTER(i32)] * 3 + [ctypes.POINTER(u64)]
+    L.cmh_launch_count.restype = ctypes.c_ulonglong
+    L.cmh_measure_popc_peak.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double), vp]
     L.cmh_pack_codes.argtypes = [vp, i32, i64, i32, i64, vp, vp, vp, vp]
     L.cmh_pack_labels.argtypes = [vp, i32, i64, i32, i64, vp, vp, vp]
     L.cmh_synth_codes.argtypes = [u64, i64, i64, i32, vp, vp]
@@ -130,7 +132,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cmh_topk_merge.argtypes = [vp, i32, i64, i32, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("cmh_last_error", "cmh_finalize_pr_workspace_bytes", "cmh_map_k_workspace_bytes"):
+        if name not in ("cmh_last_error", "cmh_finalize_pr_workspace_bytes", "cmh_map_k_workspace_bytes",
+                        "cmh_launch_count"):
             fn.restype = i32
 
 

@@ -1,4 +1,5 @@
 // Library-wide plumbing: thread-local error message, device queries.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -14,6 +15,10 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+unsigned long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
@@ -35,7 +40,9 @@ int sm_count() {
 
 }  // namespace cmh
 
+namespace cmh { unsigned long long launches(); }
 extern "C" int cmh_abi_version(void) { return CMH_ABI_VERSION; }
+extern "C" unsigned long long cmh_launch_count(void) { return cmh::launches(); }
 extern "C" const char* cmh_last_error(void) { return cmh::g_err; }
 
 extern "C" int cmh_device_info(int* sm, int* cc_major, int* cc_minor, uint64_t* total_mem) {

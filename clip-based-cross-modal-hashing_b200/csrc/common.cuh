@@ -27,7 +27,14 @@ int cuda_fail(cudaError_t e, const char* what);
         }                                  \
     } while (0)
 
-#define CMH_LAUNCH_CHECK(name) CMH_CUDA(cudaPeekAtLastError())
+// every kernel launch of the library is followed by exactly one CMH_LAUNCH_CHECK: it counts the launch
+// (cmh_launch_count, bench.py's "gpu_launches") and surfaces launch-configuration errors
+void count_launch();
+#define CMH_LAUNCH_CHECK(name)              \
+    do {                                    \
+        ::cmh::count_launch();              \
+        CMH_CUDA(cudaPeekAtLastError());    \
+    } while (0)
 
 int sm_count();  // of the current device (cached per device)
 

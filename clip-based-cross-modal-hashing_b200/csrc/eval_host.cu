@@ -450,7 +450,9 @@ extern "C" int cmh_eval_hist(const cmh_plan* plan, const cmh_codeset* q, const c
             reduce_hist_kernel<true><<<g, 256, 0, st>>>(s, w.chunk_hist + q0 * a.nb, w.shard_all + q0 * a.nb,
                                                         w.shard_rel + q0 * a.nb, hist_all ? hist_all + q0 * a.nb : nullptr,
                                                         hist_rel ? hist_rel + q0 * a.nb : nullptr);
+            CMH_LAUNCH_CHECK("reduce_hist_kernel");
         }
+        return CMH_OK;
     }
     CMH_LAUNCH_CHECK("reduce_hist_kernel");
     return CMH_OK;
@@ -493,7 +495,7 @@ extern "C" int cmh_eval_rank(const cmh_plan* plan, const cmh_codeset* q, const c
     } else if ((rc = fill_args(*plan, q, d, true, &a))) {
         return rc;
     }
-    TopnList tl, tl_unsorted;
+    TopnList tl;
     int order[CMH_MAX_TOPN];
     for (int i = 0; i < ntopn; ++i) {
         CMH_REQUIRE(topn[i] >= 1, CMH_ERR_ARG, "cmh_eval_rank: topn[%d]=%lld must be >= 1", i, (long long)topn[i]);
@@ -503,7 +505,6 @@ extern "C" int cmh_eval_rank(const cmh_plan* plan, const cmh_codeset* q, const c
     for (int i = 0; i < CMH_MAX_TOPN; ++i) {
         tl.n[i] = i < ntopn ? (uint32_t)std::min<int64_t>(topn[order[i]], 0xfffffffell) : 0xffffffffu;
         tl.perm[i] = i < ntopn ? order[i] : 0;
-        tl_unsorted.n[i] = 0; tl_unsorted.perm[i] = 0;
     }
     a.ntopn = ntopn;
     a.nmax = ntopn ? tl.n[ntopn - 1] : 0u;
@@ -637,6 +638,7 @@ extern "C" int cmh_topk_merge(const uint64_t* keys_in, int n_lists, int64_t nq, 
     cudaStream_t st = (cudaStream_t)stream;
     fill_u64_kernel<<<(unsigned)std::min<int64_t>(ceil_div(nq * (int64_t)K, 256), (int64_t)sm_count() * 16), 256, 0, st>>>(
         keys_out, nq * (int64_t)K, ~0ull);
+    CMH_LAUNCH_CHECK("fill_u64_kernel");
     CMH_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     topk_merge_kernel<<<(unsigned)nq, 256, smem, st>>>(keys_in, n_lists, nq, K, keys_out);
     CMH_LAUNCH_CHECK("topk_merge_kernel");

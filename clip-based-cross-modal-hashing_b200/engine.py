@@ -1,0 +1,330 @@
+"""Device-side objects of the retrieval-evaluation path: packed code sets and the thin wrappers that enqueue the
+kernels of ``libcmh_b200.so`` on torch's current CUDA stream.
+
+PyTorch is plumbing here (device memory, streams); every computation is a hand-written sm_100a kernel reached
+through the C ABI of ``include/cmh_b200.h``.  Nothing in this module has a CPU path: tensors must live on a CUDA
+device, and a missing library raises (`_cabi.lib`).
+
+Packed words are stored in ``torch.int64`` tensors (torch has no arithmetic on uint64; the bit patterns are what
+matter).  Reference sites: `utils/calc_utils.py:8-39`, `train/base.py:130-148`.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import CodeSet, Plan, check
+
+_TORCH_DTYPE = {
+    torch.float32: 0, torch.float16: 1, torch.bfloat16: 2, torch.float64: 3,
+    torch.int8: 4, torch.int32: 5, torch.int64: 6, torch.uint8: 7, torch.bool: 7,
+}
+
+
+def _stream(device: torch.device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[ctypes.c_void_p]:
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must be a CUDA tensor (cmh_b200 has no CPU path)")
+
+
+@dataclass
+class PackedSet:
+    """One side of a comparison in packed form (``cmh_codeset``).
+
+    sign / valid : int64 [n, words]   bit c%64 of word c//64 = column c; valid is None when every entry is +-1
+    labels       : int64 [n, lwords]  or None
+    n_zero       : number of exact-zero code entries seen while packing (``torch.sign(0) == 0``)
+    """
+    sign: torch.Tensor
+    valid: Optional[torch.Tensor]
+    labels: Optional[torch.Tensor]
+    n: int
+    bits: int
+    nlab: int = 0
+    n_zero: int = 0
+
+    @property
+    def device(self) -> torch.device:
+        return self.sign.device
+
+    @property
+    def words(self) -> int:
+        return (self.bits + 63) // 64
+
+    @property
+    def lwords(self) -> int:
+        return (self.nlab + 63) // 64
+
+    def with_labels(self, labels: Optional[torch.Tensor], nlab: int) -> "PackedSet":
+        return PackedSet(self.sign, self.valid, labels, self.n, self.bits, nlab if labels is not None else 0,
+                         self.n_zero)
+
+    def rows(self, lo: int, hi: int) -> "PackedSet":
+        """Contiguous row range (a view) - how a database is split into shards."""
+        return PackedSet(self.sign[lo:hi], None if self.valid is None else self.valid[lo:hi],
+                         None if self.labels is None else self.labels[lo:hi], hi - lo, self.bits, self.nlab,
+                         self.n_zero)
+
+    def struct(self, use_valid: bool = True, use_labels: bool = True) -> CodeSet:
+        cs = CodeSet()
+        cs.sign = self.sign.data_ptr() if self.n else None
+        cs.valid = self.valid.data_ptr() if (use_valid and self.valid is not None and self.n) else None
+        cs.labels = self.labels.data_ptr() if (use_labels and self.labels is not None and self.n) else None
+        cs.n = self.n
+        return cs
+
+
+def _as_2d(x: torch.Tensor, what: str) -> torch.Tensor:
+    if x.dim() == 1:
+        x = x.unsqueeze(0)
+    if x.dim() != 2:
+        raise ValueError(f"{what} must be 1-D or 2-D, got shape {tuple(x.shape)}")
+    return x
+
+
+def _row_major(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype not in _TORCH_DTYPE:
+        raise ValueError(f"unsupported dtype {x.dtype}")
+    if x.dtype == torch.bool:
+        x = x.view(torch.uint8)
+    if x.stride(-1) != 1 or (x.shape[0] > 1 and x.stride(0) < x.shape[1]):
+        x = x.contiguous()
+    return x
+
+
+def pack_codes_device(x: torch.Tensor, counters: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Enqueue K1 on float / integer codes ``[n, bits]`` (CUDA).  Returns (sign, valid) int64 [n, words];
+    ``counters`` (int64 [2], CUDA) is incremented by (#zeros, #entries outside {-1, 0, +1})."""
+    _require_cuda(x, "codes")
+    x = _row_major(_as_2d(x, "codes"))
+    n, bits = x.shape
+    if bits < 1 or bits > _cabi.CMH_MAX_BITS:
+        raise ValueError(f"code length {bits} outside [1, {_cabi.CMH_MAX_BITS}]")
+    words = (bits + 63) // 64
+    sign = torch.empty((n, words), dtype=torch.int64, device=x.device)
+    valid = torch.empty((n, words), dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_cabi.lib().cmh_pack_codes(_ptr(x), _TORCH_DTYPE[x.dtype], n, bits, x.stride(0) if n > 1 else bits,
+                                         _ptr(sign), _ptr(valid), _ptr(counters), _stream(x.device)),
+              "cmh_pack_codes")
+    return sign, valid
+
+
+def pack_labels_device(L: torch.Tensor, neg_counter: torch.Tensor) -> torch.Tensor:
+    """Enqueue the label packer on multi-hot labels ``[n, nlab]`` (CUDA) -> int64 [n, lwords]."""
+    _require_cuda(L, "labels")
+    L = _row_major(_as_2d(L, "labels"))
+    n, nlab = L.shape
+    if nlab < 1:
+        raise ValueError("labels need at least one column")
+    lwords = (nlab + 63) // 64
+    out = torch.empty((n, lwords), dtype=torch.int64, device=L.device)
+    with torch.cuda.device(L.device):
+        check(_cabi.lib().cmh_pack_labels(_ptr(L), _TORCH_DTYPE[L.dtype], n, nlab, L.stride(0) if n > 1 else nlab,
+                                          _ptr(out), _ptr(neg_counter), _stream(L.device)), "cmh_pack_labels")
+    return out
+
+
+def synth_codes(seed: int, row0: int, n: int, bits: int, device: torch.device) -> PackedSet:
+    """Counter-based packed codes generated on the device (`cmh_synth_codes`; CPU twin: `synth.splitmix_rows`)."""
+    words = (bits + 63) // 64
+    out = torch.empty((n, words), dtype=torch.int64, device=device)
+    with torch.cuda.device(device):
+        check(_cabi.lib().cmh_synth_codes(ctypes.c_uint64(seed), row0, n, bits, _ptr(out), _stream(device)),
+              "cmh_synth_codes")
+    return PackedSet(out, None, None, n, bits)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dense blocks (a2 / a4)
+# ---------------------------------------------------------------------------------------------------------------
+_DENSE_MAX_ROWS = 65535 * 8
+
+
+def hamming_dense(q: PackedSet, d: PackedSet) -> torch.Tensor:
+    """float32 [q.n, d.n] = 0.5 * (bits - <q_i, d_j>)   (`calc_hammingDist`, utils/calc_utils.py:8-13)."""
+    if q.bits != d.bits:
+        raise ValueError(f"code lengths differ: {q.bits} vs {d.bits}")
+    out = torch.empty((q.n, d.n), dtype=torch.float32, device=q.device)
+    if q.n == 0 or d.n == 0:
+        return out
+    L = _cabi.lib()
+    with torch.cuda.device(q.device):
+        for lo in range(0, q.n, _DENSE_MAX_ROWS):
+            hi = min(q.n, lo + _DENSE_MAX_ROWS)
+            qs, ds = q.rows(lo, hi).struct(), d.struct()
+            check(L.cmh_hamming_dense(ctypes.byref(qs), ctypes.byref(ds), q.bits, _ptr(out[lo:hi]), out.stride(0),
+                                      _stream(q.device)), "cmh_hamming_dense")
+    return out
+
+
+def neighbor_dense(a: torch.Tensor, b: torch.Tensor, nlab: int) -> torch.Tensor:
+    """float32 [na, nb] of {0, 1} from packed label masks (`calc_neighbor`, utils/calc_utils.py:42-45)."""
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    if a.shape[0] == 0 or b.shape[0] == 0:
+        return out
+    L = _cabi.lib()
+    with torch.cuda.device(a.device):
+        for lo in range(0, a.shape[0], _DENSE_MAX_ROWS):
+            hi = min(a.shape[0], lo + _DENSE_MAX_ROWS)
+            check(L.cmh_neighbor_dense(_ptr(a[lo:hi]), hi - lo, _ptr(b), b.shape[0], (nlab + 63) // 64,
+                                       _ptr(out[lo:hi]), out.stride(0), _stream(a.device)), "cmh_neighbor_dense")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ranking by counting (a3 / a5 / a6, p_topK, pr_curve, top-K)
+# ---------------------------------------------------------------------------------------------------------------
+class RankPass:
+    """One (queries, database shard) pair walked through the two counting passes.
+
+    Single GPU:  ``hist()`` -> ``rank(k, topn)`` -> finalisers.
+    Sharded   :  ``hist()`` on every shard, exchange the shard histograms (`sharded.py`), then
+                 ``rank(k, topn, lower=..., glob=...)``.
+    """
+
+    def __init__(self, q: PackedSet, d: PackedSet, *, need_labels: bool = True, max_topn: int = 0,
+                 design: int = -1, ternary: Optional[bool] = None):
+        if q.bits != d.bits:
+            raise ValueError(f"code lengths differ: {q.bits} vs {d.bits}")
+        if need_labels:
+            if q.labels is None or d.labels is None:
+                raise ValueError("relevance needs labels on both sides")
+            if q.nlab != d.nlab:
+                raise ValueError(f"label widths differ: {q.nlab} vs {d.nlab}")
+        if q.device != d.device:
+            raise ValueError("queries and database must be on the same device")
+        self.q, self.d = q, d
+        self.device = q.device
+        self.need_labels = need_labels
+        # sharded callers pass `ternary` so that every rank uses the same bucket layout even when only some
+        # shards contain exact zeros
+        self.ternary = (q.valid is not None or d.valid is not None) if ternary is None else bool(ternary)
+        if not self.ternary and (q.valid is not None or d.valid is not None):
+            raise ValueError("ternary=False but a valid plane is present")
+        if self.ternary:
+            # the ranking kernels need both planes; an all-ones plane stands in for a +-1 side
+            if q.valid is None:
+                q = PackedSet(q.sign, _full_valid(q), q.labels, q.n, q.bits, q.nlab)
+            if d.valid is None:
+                d = PackedSet(d.sign, _full_valid(d), d.labels, d.n, d.bits, d.nlab)
+            self.q, self.d = q, d
+        self.plan = Plan()
+        with torch.cuda.device(self.device):
+            check(_cabi.lib().cmh_eval_plan_design(q.n, d.n, q.bits, q.nlab if need_labels else 0,
+                                                   1 if self.ternary else 0, max_topn, design,
+                                                   ctypes.byref(self.plan)), "cmh_eval_plan")
+        self.nb = self.plan.nb
+        self.workspace = torch.empty(max(1, self.plan.workspace_bytes), dtype=torch.uint8, device=self.device)
+        self._qs = self.q.struct(use_labels=need_labels)
+        self._ds = self.d.struct(use_labels=need_labels)
+        self.hist_all: Optional[torch.Tensor] = None
+        self.hist_rel: Optional[torch.Tensor] = None
+
+    # pass 1
+    def hist(self) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """uint32-valued int32 tensors [nq, nb]: rows of this shard per (query, bucket), all / relevant."""
+        nq = self.q.n
+        self.hist_all = torch.empty((nq, self.nb), dtype=torch.int32, device=self.device)
+        self.hist_rel = torch.empty((nq, self.nb), dtype=torch.int32, device=self.device) if self.need_labels else None
+        with torch.cuda.device(self.device):
+            check(_cabi.lib().cmh_eval_hist(ctypes.byref(self.plan), ctypes.byref(self._qs), ctypes.byref(self._ds),
+                                            _ptr(self.hist_all), _ptr(self.hist_rel), _ptr(self.workspace),
+                                            _stream(self.device)), "cmh_eval_hist")
+        return self.hist_all, self.hist_rel
+
+    # pass 2
+    def rank(self, k: Optional[int], topn: Sequence[int] = (), lower=None, glob=None):
+        """Returns (ap_sum float64 [nq], n_rel int64 [nq], hits int32 [nq, len(topn)] or None)."""
+        if not self.need_labels:
+            raise ValueError("rank() needs labels")
+        nq = self.q.n
+        ap_sum = torch.zeros(nq, dtype=torch.float64, device=self.device)
+        n_rel = torch.zeros(nq, dtype=torch.int64, device=self.device)
+        topn = [int(t) for t in topn]
+        hits = torch.zeros((nq, len(topn)), dtype=torch.int32, device=self.device) if topn else None
+        la = lr = ga = gr = None
+        if lower is not None:
+            la, lr = lower
+        if glob is not None:
+            ga, gr = glob
+        with torch.cuda.device(self.device):
+            check(_cabi.lib().cmh_eval_rank(ctypes.byref(self.plan), ctypes.byref(self._qs), ctypes.byref(self._ds),
+                                            -1 if k is None else int(k), _ptr(la), _ptr(lr), _ptr(ga), _ptr(gr),
+                                            _cabi.i64_array(topn), len(topn), _ptr(hits), _ptr(ap_sum), _ptr(n_rel),
+                                            _ptr(self.workspace), _stream(self.device)), "cmh_eval_rank")
+        return ap_sum, n_rel, hits
+
+    def topk(self, K: int, index_base: int = 0) -> torch.Tensor:
+        """int64 [nq, K] ascending keys ``(2*dist << 32) | (index_base + row)``; -1 (= UINT64_MAX) pads."""
+        keys = torch.empty((self.q.n, int(K)), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(_cabi.lib().cmh_topk(ctypes.byref(self.plan), ctypes.byref(self._qs), ctypes.byref(self._ds), int(K),
+                                       int(index_base), _ptr(keys), _ptr(self.workspace), _stream(self.device)),
+                  "cmh_topk")
+        return keys
+
+
+def _full_valid(p: PackedSet) -> torch.Tensor:
+    """All-ones valid plane over the real bit positions (padding bits stay 0)."""
+    v = torch.full((p.n, p.words), -1, dtype=torch.int64, device=p.device)
+    tail = p.bits - 64 * (p.words - 1)
+    if tail < 64:
+        v[:, p.words - 1] = (1 << tail) - 1
+    return v
+
+
+def finalize_map(ap_sum: torch.Tensor, n_rel: torch.Tensor, k: Optional[int]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(ap float64 [nq], mAP float32 [1]) on the device   (utils/calc_utils.py:37-38)."""
+    nq = ap_sum.shape[0]
+    ap = torch.empty(nq, dtype=torch.float64, device=ap_sum.device)
+    out = torch.zeros(1, dtype=torch.float32, device=ap_sum.device)
+    with torch.cuda.device(ap_sum.device):
+        check(_cabi.lib().cmh_finalize_map(_ptr(ap_sum), _ptr(n_rel), nq, -1 if k is None else int(k), _ptr(ap),
+                                           _ptr(out), _stream(ap_sum.device)), "cmh_finalize_map")
+    return ap, out
+
+
+def finalize_topn(hits: torch.Tensor, n_rel: torch.Tensor, topn: Sequence[int], nd_total: int) -> torch.Tensor:
+    out = torch.zeros(len(topn), dtype=torch.float32, device=hits.device)
+    with torch.cuda.device(hits.device):
+        check(_cabi.lib().cmh_finalize_topn(_ptr(hits), _ptr(n_rel), hits.shape[0], _cabi.i64_array(topn), len(topn),
+                                            int(nd_total), _ptr(out), _stream(hits.device)), "cmh_finalize_topn")
+    return out
+
+
+def finalize_pr(hist_all: torch.Tensor, hist_rel: torch.Tensor, bits: int, ternary: bool):
+    nq = hist_all.shape[0]
+    dev = hist_all.device
+    P = torch.zeros(bits + 1, dtype=torch.float32, device=dev)
+    R = torch.zeros(bits + 1, dtype=torch.float32, device=dev)
+    L = _cabi.lib()
+    ws = torch.empty(max(1, L.cmh_finalize_pr_workspace_bytes(nq, bits)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(L.cmh_finalize_pr(_ptr(hist_all), _ptr(hist_rel), nq, bits, 1 if ternary else 0, _ptr(P), _ptr(R),
+                                _ptr(ws), _stream(dev)), "cmh_finalize_pr")
+    return P, R
+
+
+def topk_merge(keys_in: torch.Tensor, K: int) -> torch.Tensor:
+    """keys_in int64 [n_lists, nq, K] (rows ascending) -> int64 [nq, K] smallest."""
+    n_lists, nq, kk = keys_in.shape
+    if kk != K:
+        raise ValueError("keys_in last dimension must equal K")
+    keys_in = keys_in.contiguous()
+    out = torch.empty((nq, K), dtype=torch.int64, device=keys_in.device)
+    with torch.cuda.device(keys_in.device):
+        check(_cabi.lib().cmh_topk_merge(_ptr(keys_in), n_lists, nq, K, _ptr(out), _stream(keys_in.device)),
+              "cmh_topk_merge")
+    return out

@@ -1,0 +1,64 @@
+"""Resident database for large-scale top-K Hamming retrieval (BASELINE.json config 4: 64-bit codes, top-1000,
+1M queries x 100M database rows sharded over the GPUs of one box).
+
+The reference only ever ranks inside `calc_map_k_matrix` (`utils/calc_utils.py:30-31`: distance row + full sort per
+query); this class is that ranking, truncated to the first K entries, for databases far beyond what a per-query
+sort can touch.  The database stays packed in HBM (8 B per 64-bit row: 100M rows = 800 MB); queries stream
+through in chunks; each chunk is two counting passes over the shard (histogram -> threshold -> ordered select)
+and, when sharded, one all-gather + merge.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import calc_utils as _cu
+from . import engine as _e
+from . import sharded as _sh
+from .engine import PackedSet
+
+
+class HammingIndex:
+    """Database shard resident on one GPU.
+
+    ``index_base`` is the global row index of the shard's first row; with ``group`` (a `torch.distributed`
+    process group, one rank per GPU) `search` returns the global top-K on every rank."""
+
+    def __init__(self, db: PackedSet, index_base: int = 0, group=None):
+        if db.labels is not None:
+            db = db.with_labels(None, 0)
+        self.db = db
+        self.index_base = int(index_base)
+        self.group = group
+
+    @classmethod
+    def from_codes(cls, rB, device=None, index_base: int = 0, group=None) -> "HammingIndex":
+        """Pack float codes ``[D, bits]`` (entries in {-1, 0, +1}) once and keep them on the device."""
+        return cls(_cu.pack_codes(rB, device), index_base, group)
+
+    @classmethod
+    def from_packed(cls, words: torch.Tensor, bits: int, index_base: int = 0, group=None) -> "HammingIndex":
+        """Adopt already packed +-1 codes: int64 / uint64-bit-pattern tensor ``[D, ceil(bits/64)]`` on a GPU,
+        padding bits zero."""
+        if words.dim() != 2 or words.shape[1] != (bits + 63) // 64:
+            raise ValueError(f"packed words must be [D, {(bits + 63) // 64}]")
+        if not words.is_cuda:
+            raise RuntimeError("packed database must be on a CUDA device")
+        return cls(PackedSet(words.contiguous().view(torch.int64), None, None, words.shape[0], bits), index_base, group)
+
+    def search_packed(self, q: PackedSet, K: int) -> torch.Tensor:
+        """int64 [Q, K] ascending keys ``(2*dist << 32) | global_row`` (-1 pads rows beyond the database)."""
+        ternary = None
+        return _sh.topk_sharded(q, self.db, int(K), self.index_base, self.group, ternary=ternary)
+
+    def search(self, qB, K: int):
+        """Float query codes in -> (dist float32 [Q, K], index int64 [Q, K]) on the device; pads have index -1."""
+        q = _cu.pack_codes(qB, self.db.device)
+        if q.bits != self.db.bits:
+            raise RuntimeError(f"code lengths differ: queries {q.bits}, database {self.db.bits}")
+        keys = self.search_packed(q, K)
+        pad = keys < 0
+        dist = (keys >> 32).to(torch.float32) * 0.5
+        idx = keys & 0xFFFFFFFF
+        return dist.masked_fill(pad, float("inf")), idx.masked_fill(pad, -1)

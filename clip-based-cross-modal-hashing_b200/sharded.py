@@ -1,0 +1,100 @@
+"""Database sharding across the GPUs of one box: one process per GPU (`torch.distributed`, NCCL over NVLink),
+queries replicated, database rows split into contiguous index ranges so that "ascending global index" - the tie
+order of the stable ranking (`utils/calc_utils.py:31` forced stable) - is (shard, local row).
+
+The path has exactly one exchange step per metric, and nothing else crosses GPUs:
+
+  mAP / precision@N / PR   all-gather of the per-shard bucket histograms ``[Q, nb]`` (all, relevant) after pass 1;
+                           every rank derives the global bucket totals and the rows contributed by lower shards,
+                           ranks its own rows exactly in pass 2, then one all-reduce(sum) of ``Q`` partial AP sums
+                           (+ the precision@N hit counts).  Ranks are integers, so N shards == 1 shard bit for bit;
+                           only the order of the final float64 sum differs.
+  top-K                    every rank selects its local top-K keys ``(2*dist << 32) | global_row`` (already globally
+                           comparable), all-gather, K-way merge kernel.
+
+The reference has no distributed code at all; this is the north star's multi-GPU requirement.
+``eng`` is the module providing the device passes (`cmh_b200.engine`); the gloo tests substitute a CPU stand-in to
+exercise the exchange logic without a GPU.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import engine as _engine
+
+
+def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced row range of ``rank``: the first ``n_rows % world`` shards get one extra row."""
+    base, extra = divmod(int(n_rows), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _world(group) -> Tuple[int, int]:
+    if not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def _all_gather_stack(x: torch.Tensor, world: int, group) -> torch.Tensor:
+    """[world, *x.shape] from every rank's ``x`` (concatenation along dim 0 - the layout both NCCL and gloo accept)."""
+    x = x.contiguous()
+    flat = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(flat, x, group=group)
+    return flat.view((world,) + tuple(x.shape))
+
+
+def exchange_histograms(h_all: torch.Tensor, h_rel: Optional[torch.Tensor], group=None):
+    """All-gather the shard histograms and reduce them to what pass 2 needs.
+
+    Returns ((lower_all, lower_rel), (global_all, global_rel)) as int32 tensors with uint32 bit patterns
+    (sums are taken in int64 and truncated, i.e. modulo 2^32 like the kernels' own counters)."""
+    rank, world = _world(group)
+    both = torch.stack([h_all, h_rel if h_rel is not None else torch.zeros_like(h_all)])  # [2, Q, nb]
+    if world == 1:
+        zero = torch.zeros_like(both)
+        return (zero[0], zero[1]), (both[0], both[1])
+    gathered = _all_gather_stack(both, world, group)
+    wide = gathered.to(torch.int64) & 0xFFFFFFFF
+    lower = wide[:rank].sum(0).to(torch.int32) if rank > 0 else torch.zeros_like(both)
+    glob = wide.sum(0).to(torch.int32)
+    return (lower[0].contiguous(), lower[1].contiguous()), (glob[0].contiguous(), glob[1].contiguous())
+
+
+def map_k_sharded(q, d_shard, k: Optional[int], nd_total: int, topn: Sequence[int] = (), group=None,
+                  eng=_engine, want_pr: bool = False, ternary: Optional[bool] = None):
+    """One direction of `calc_map_k_matrix` with the database sharded over the ranks of ``group``.
+
+    q        packed queries (replicated on every rank, labels attached)
+    d_shard  this rank's contiguous database rows (labels attached)
+    ternary  must be the same on every rank: True when ANY shard (or the queries) holds exact-zero entries
+    Returns dict(map float32 [1], ap float64 [Q], n_rel int64 [Q], prec float32 [len(topn)] | None,
+                 pr (P, R) | None) - identical on every rank."""
+    rp = eng.RankPass(q, d_shard, need_labels=True, max_topn=len(topn), ternary=ternary)
+    h_all, h_rel = rp.hist()
+    lower, glob = exchange_histograms(h_all, h_rel, group)
+    ap_sum, n_rel, hits = rp.rank(k, topn, lower=lower, glob=glob)
+    _, world = _world(group)
+    if world > 1:
+        dist.all_reduce(ap_sum, op=dist.ReduceOp.SUM, group=group)
+        if hits is not None:
+            dist.all_reduce(hits, op=dist.ReduceOp.SUM, group=group)
+    ap, m = eng.finalize_map(ap_sum, n_rel, k)
+    prec = eng.finalize_topn(hits, n_rel, topn, nd_total) if len(topn) else None
+    pr = eng.finalize_pr(glob[0], glob[1], q.bits, rp.ternary) if want_pr else None
+    return {"map": m, "ap": ap, "n_rel": n_rel, "prec": prec, "pr": pr}
+
+
+def topk_sharded(q, d_shard, K: int, index_base: int, group=None, eng=_engine,
+                 ternary: Optional[bool] = None) -> torch.Tensor:
+    """Global top-``K`` keys int64 [Q, K] (ascending, ``-1`` pads) - identical on every rank.
+    ``index_base`` is the global index of this shard's first row."""
+    rp = eng.RankPass(q, d_shard, need_labels=False, ternary=ternary)
+    local = rp.topk(K, index_base)
+    _, world = _world(group)
+    if world == 1:
+        return local
+    return eng.topk_merge(_all_gather_stack(local, world, group), K)

@@ -81,6 +81,12 @@ int cmh_abi_version(void);
 const char* cmh_last_error(void);
 /* sm count / compute capability / total memory of the current device */
 int cmh_device_info(int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem);
+/* kernels launched by this library in this process so far (bench.py reports the delta as "gpu_launches") */
+unsigned long long cmh_launch_count(void);
+/* Integer-pipe roofline of the XOR+POPC compare, measured live: a register-only kernel with the compare's
+ * instruction mix (one LOP3 + one POPC + one IADD per 32-bit word).  Best of `reps` launches of `iters`
+ * iterations, in 32-bit compares per second.  Synchronises `stream`. */
+int cmh_measure_popc_peak(int iters, int reps, double* popc32_per_s, void* stream);
 
 /* ---- K1: sign + bit-pack ---------------------------------------------------------------------------------- */
 /* x: device [n][ld] of `dtype` (first `bits` columns used).  sign_out / valid_out: device [n][words]

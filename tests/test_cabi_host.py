@@ -1,0 +1,110 @@
+"""CPU-side checks of the boundary: the built library loads and exports every symbol `include/cmh_b200.h`
+declares, the ctypes structs mirror the header, argument errors are reported through the C ABI's error
+convention, and the Python product refuses to run without a CUDA device (no CPU fallback).  No compute calls."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from cmh_b200 import _cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "cmh_b200.h")
+
+
+def _header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cmh_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(cuda_lib):
+    declared = _header_functions()
+    assert sorted(_cabi.EXPORTS) == declared, "the _cabi.EXPORTS list and include/cmh_b200.h disagree"
+    raw = ctypes.CDLL(_cabi.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} is declared in the header but not exported by libcmh_b200.so"
+    assert cuda_lib.cmh_abi_version() == 1
+
+
+def test_structs_mirror_header():
+    assert ctypes.sizeof(_cabi.CodeSet) == 32            # 3 pointers + int64
+    assert ctypes.sizeof(_cabi.Plan) == 12 * 4 + 3 * 8 + 8
+    src = open(HEADER).read()
+    fields = re.search(r"typedef struct cmh_plan \{(.*?)\} cmh_plan;", src, re.S).group(1)
+    fields = re.sub(r"/\*.*?\*/", "", fields, flags=re.S)
+    names = [n.strip() for decl in fields.split(";") if decl.strip() for n in decl.strip().split(None, 1)[1].split(",")]
+    assert names == [f[0] for f in _cabi.Plan._fields_]
+
+
+def test_argument_errors_use_the_error_convention(cuda_lib):
+    """Planning is host-only arithmetic: it must reject bad arguments with a negative code and a message, without
+    touching a device."""
+    plan = _cabi.Plan()
+    rc = cuda_lib.cmh_eval_plan(10, 100, 0, 24, 0, 0, ctypes.byref(plan))
+    assert rc == -2 and "bits" in _cabi.last_error()
+    rc = cuda_lib.cmh_eval_plan(10, 100, 64, 24, 0, 999, ctypes.byref(plan))
+    assert rc == -1
+    with pytest.raises(ValueError):
+        _cabi.check(rc, "cmh_eval_plan")
+    rc = cuda_lib.cmh_eval_plan(-1, 100, 64, 24, 0, 0, ctypes.byref(plan))
+    assert rc == -1
+    assert cuda_lib.cmh_pack_codes(None, 0, 5, 64, 64, None, None, None, None) == -1      # NULL pointers
+    assert cuda_lib.cmh_pack_codes(None, 0, 5, 64, 32, None, None, None, None) == -1      # ld < bits
+    assert cuda_lib.cmh_topk_merge(None, 0, 1, 1, None, None) == -1
+
+
+def test_plan_geometry(cuda_lib):
+    """The plan is the launch geometry both passes share: chunks cover the database, counters fit 16 bits, and
+    the long-code / ternary cases fall back to the warp-per-query design."""
+    for nq, nd, bits, nlab, tern in [(2000, 18015, 64, 24, 0), (2100, 193734, 16, 21, 0), (5000, 117218, 128, 80, 0),
+                                      (8192, 100_000_000, 64, 0, 0), (7, 700, 2048, 24, 0), (32, 2000, 64, 24, 1),
+                                      (1, 1, 1, 1, 0), (0, 0, 64, 24, 0)]:
+        plan = _cabi.Plan()
+        assert cuda_lib.cmh_eval_plan(nq, nd, bits, nlab, tern, 11, ctypes.byref(plan)) == 0, _cabi.last_error()
+        assert plan.nb == (2 * bits + 1 if tern else bits + 1)
+        assert plan.chunk_rows % 16 == 0 and plan.chunk_rows <= 65520
+        assert plan.n_chunks * plan.chunk_rows >= nd
+        assert plan.nq_pad % plan.q_tile == 0 and plan.nq_pad >= nq
+        assert plan.design == (0 if plan.nb <= 200 else 1)
+        assert plan.workspace_bytes > 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour of a box WITHOUT a GPU")
+def test_product_refuses_to_run_without_cuda():
+    from cmh_b200 import calc_utils as cu
+    q = torch.ones(2, 16); r = torch.ones(5, 16); l = torch.ones(2, 3); rl = torch.ones(5, 3)
+    for call in (lambda: cu.calc_map_k_matrix(q, r, l, rl), lambda: cu.calc_hammingDist(q, r),
+                 lambda: cu.calc_neighbor(l, rl), lambda: cu.p_topK(q, r, l, rl, [1]), lambda: cu.pr_curve(q, r, l, rl)):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
+
+
+def test_product_never_imports_the_oracle():
+    """A product path that routes through the oracle voids every parity claim: no module of the package may
+    mention it."""
+    pkg = os.path.join(ROOT, "clip-based-cross-modal-hashing_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+                assert "cmh_oracle" not in src.replace("oracle/cmh_oracle", ""), f"{f} references the oracle"
+
+
+def test_pack_cache_is_keyed_on_live_tensor_objects():
+    from cmh_b200.calc_utils import _PackCache
+    c = _PackCache(limit=4)
+    t = torch.zeros(4, 8)
+    dev = torch.device("cpu")
+    c.put(t, "codes", dev, "packed-1")
+    assert c.get(t, "codes", dev) == "packed-1"
+    t.add_(1)                                   # in-place update bumps the version -> stale entry must miss
+    assert c.get(t, "codes", dev) is None
+    c.put(t, "codes", dev, "packed-2")
+    u = t.clone()
+    assert c.get(u, "codes", dev) is None       # a different object never hits, whatever its address
+    del t
+    assert len(c._entries) == 0                 # entry dies with the tensor

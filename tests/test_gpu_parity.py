@@ -1,0 +1,388 @@
+"""Parity tests proper: the CUDA path, called through the drop-in Python API (which reaches the kernels only
+through the C ABI of include/cmh_b200.h), against
+  * the committed golden vectors generated from the reference's own code (tests/golden/*.npz),
+  * the CPU oracle on the same seeded inputs (small sizes: torch restatement; full BASELINE.json sizes: C
+    restatement, pinned on the same goldens by tests/test_oracle_golden.py),
+  * size-independent properties at sizes the oracle cannot reach.
+Bars: rankings / counts / packed words bit-exact; mAP, AP, precision, PR within 1e-6 (BASELINE.json north star).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from golden_cases import BY_NAME, CASES, SMALL, k_tag, load_golden
+from oracle import c_oracle, cmh_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6          # north-star tolerance for mAP / precision (float); everything integer is compared exactly
+
+
+@pytest.fixture(scope="module")
+def dev(cuda_lib):
+    assert torch.cuda.is_available()
+    sm, major, minor, mem = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_uint64()
+    rc = cuda_lib.cmh_device_info(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor), ctypes.byref(mem))
+    assert rc == 0 and major.value == 10, "libcmh_b200 is sm_100a-only"
+    return torch.device("cuda", 0)
+
+
+def _cu():
+    from cmh_b200 import calc_utils
+    return calc_utils
+
+
+def _T(case, n=None):
+    t = case.tensors()
+    n = case.n_golden if n is None else n
+    return {k: torch.from_numpy(v[:n] if k in ("qB", "qL") else v) for k, v in t.items()}
+
+
+def _keys_from_golden(g):
+    d2 = np.rint(g["topk_dist"].astype(np.float64) * 2).astype(np.uint64)
+    return (d2 << np.uint64(32)) | g["topk_idx"].astype(np.uint64)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K1: sign + bit-pack
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bits", [1, 16, 20, 32, 48, 64, 96, 128, 200, 256, 2048])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16, torch.float64, torch.int8, torch.int64])
+def test_pack_codes_bit_exact(dev, bits, dtype):
+    from cmh_b200 import engine
+    rng = np.random.default_rng(bits * 7 + 1)
+    n = 1037
+    x = rng.integers(-1, 2, size=(n, bits)).astype(np.float32)          # ternary content
+    xt = torch.from_numpy(x).to(dtype).to(dev)
+    counters = torch.zeros(2, dtype=torch.int64, device=dev)
+    sign, valid = engine.pack_codes_device(xt, counters)
+    ws, wv, nz, nodd = orc.pack_codes(x)
+    assert np.array_equal(sign.cpu().numpy().view(np.uint64), ws)
+    assert np.array_equal(valid.cpu().numpy().view(np.uint64), wv)
+    assert counters.tolist() == [nz, 0]
+
+
+def test_pack_codes_strided_and_odd_values(dev):
+    from cmh_b200 import engine
+    rng = np.random.default_rng(3)
+    big = torch.from_numpy(rng.standard_normal((300, 100)).astype(np.float32)).to(dev)
+    view = big[:, 10:74]                                                 # ld = 100, 64 columns, unaligned start
+    counters = torch.zeros(2, dtype=torch.int64, device=dev)
+    sign, valid = engine.pack_codes_device(view, counters)
+    ws, wv, nz, nodd = orc.pack_codes(view.cpu().numpy())
+    assert np.array_equal(sign.cpu().numpy().view(np.uint64), ws)
+    assert np.array_equal(valid.cpu().numpy().view(np.uint64), wv)
+    assert counters.tolist() == [nz, nodd] and nodd > 0
+    with pytest.raises(ValueError, match="outside"):
+        _cu().pack_codes(big)                                            # raw activations are rejected loudly
+
+
+@pytest.mark.parametrize("nlab", [1, 21, 24, 64, 80, 291])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.int64, torch.uint8])
+def test_pack_labels_bit_exact(dev, nlab, dtype):
+    from cmh_b200 import engine
+    rng = np.random.default_rng(nlab)
+    L = (rng.random((777, nlab)) < 0.1).astype(np.float32) * rng.integers(1, 3, size=(777, nlab))   # non-0/1 positives
+    neg = torch.zeros(1, dtype=torch.int64, device=dev)
+    masks = engine.pack_labels_device(torch.from_numpy(L).to(dtype).to(dev), neg)
+    assert np.array_equal(masks.cpu().numpy().view(np.uint64), orc.pack_labels(L))
+    assert int(neg.item()) == 0
+    if dtype != torch.uint8:
+        bad = torch.from_numpy(L).to(dtype)
+        bad[3, 0] = -1
+        with pytest.raises(ValueError, match="non-negative"):
+            _cu().pack_labels(bad.to(dev))
+
+
+def test_synth_codes_match_cpu_twin(dev):
+    from cmh_b200 import engine
+    from cmh_b200.synth import splitmix_rows
+    for bits, row0, n in [(64, 0, 1000), (64, 99_999_000, 1000), (40, 5, 333), (128, 7, 100)]:
+        got = engine.synth_codes(4000, row0, n, bits, dev).sign.cpu().numpy().view(np.uint64)
+        assert np.array_equal(got, splitmix_rows(4000, row0, n, (bits + 63) // 64, bits))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# golden vectors from the reference
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("design", [-1, 1])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
+def test_map_k_matches_reference_goldens(dev, case, design):
+    if design == 1 and case.slow:
+        pytest.skip("generic design is covered on the small cases")
+    g, T = load_golden(case), _T(case)
+    cu = _cu()
+    for k in case.ks:
+        res = cu.map_k_detail(T["qB"].to(dev), T["rB"].to(dev), T["qL"], T["rL"], k, 0, design=design)
+        assert np.array_equal(res["n_rel"].cpu().numpy(), g["n_rel"])
+        np.testing.assert_allclose(res["ap"].cpu().numpy(), g[f"ap_{k_tag(k)}"], rtol=0, atol=TOL)
+        assert abs(float(res["map"].cpu()[0]) - float(g[f"map_{k_tag(k)}"])) < TOL
+    # the public call, host inputs (the reference's labels are host tensors, train/base.py:81-82)
+    out = cu.calc_map_k_matrix(T["qB"], T["rB"], T["qL"], T["rL"], case.ks[0], 0)
+    assert isinstance(out, torch.Tensor) and out.dim() == 0 and out.dtype == torch.float32 and not out.is_cuda
+    assert abs(float(out) - float(g[f"map_{k_tag(case.ks[0])}"])) < TOL
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
+def test_topk_ranking_bit_exact_vs_reference_goldens(dev, case):
+    g, T = load_golden(case), _T(case)
+    dist, idx = _cu().topk_hamming(T["qB"].to(dev), T["rB"].to(dev), case.topk)
+    assert np.array_equal(idx.cpu().numpy().astype(np.int32), g["topk_idx"])
+    assert np.array_equal(dist.cpu().numpy(), g["topk_dist"])
+
+
+@pytest.mark.parametrize("case", SMALL, ids=lambda c: c.name)
+def test_dense_blocks_match_reference_goldens(dev, case):
+    g, T = load_golden(case), _T(case)
+    cu = _cu()
+    m = g["dense_dist"].shape[0]
+    got = cu.calc_hammingDist(T["qB"][:m].to(dev), T["rB"][:256].to(dev))
+    assert got.is_cuda and got.dtype == torch.float32
+    assert np.array_equal(got.cpu().numpy(), g["dense_dist"])
+    assert np.array_equal(cu.calc_neighbor(T["qL"][:m], T["rL"][:256]).numpy(), g["dense_neighbor"])
+    one = cu.calc_hammingDist(T["qB"][0], T["rB"][:256])                 # 1-D B1 -> [1, n]  (calc_utils.py:10-11)
+    assert tuple(one.shape) == (1, 256) and np.array_equal(one.numpy()[0], g["dense_dist"][0])
+    full = cu.calc_hammingDist(T["qB"], T["rB"])
+    assert torch.equal(full, orc.hamming_dist(T["qB"], T["rB"]))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# precision@N and PR curve (definitions frozen in the oracle; not in the reference)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["small_b64_l24", "small_b16_l21", "small_b64_ternary", "small_b128_l80", "small_b256_long",
+                                  "small_b64_ragged"])
+def test_precision_topn_and_pr_curve(dev, name):
+    case = BY_NAME[name]
+    T = _T(case, 24)
+    cu = _cu()
+    topn = [1, 2, 10, 100, 1000, 1029, 10 ** 7, 50]                      # unsorted, duplicates of D, beyond D
+    got = cu.p_topK(T["qB"], T["rB"], T["qL"], T["rL"], topn)
+    want = orc.p_topk_sorted(T["qB"], T["rB"], T["qL"], T["rL"], topn)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=TOL)
+    P, R = cu.pr_curve(T["qB"], T["rB"], T["qL"], T["rL"])
+    wP, wR = orc.pr_curve_dense(T["qB"], T["rB"], T["qL"], T["rL"])
+    np.testing.assert_allclose(P.numpy(), wP.numpy(), rtol=0, atol=TOL)
+    np.testing.assert_allclose(R.numpy(), wR.numpy(), rtol=0, atol=TOL)
+
+
+def test_more_than_64_cutoffs(dev):
+    T = _T(BY_NAME["small_b32_l21"], 16)
+    topn = list(range(1, 140, 2))
+    got = _cu().p_topK(T["qB"], T["rB"], T["qL"], T["rL"], topn)
+    want = orc.p_topk_sorted(T["qB"], T["rB"], T["qL"], T["rL"], topn)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=TOL)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs at full size, against the C oracle
+# ---------------------------------------------------------------------------------------------------------------
+def _full_config(dev, name, direction, k, topn=(), pr=False):
+    from cmh_b200.synth import CONFIGS, make_case
+    shape = CONFIGS[name]
+    t = make_case(shape, clustered=True, zero_query_frac=0.01)
+    qk, rk = ("q_img", "r_txt") if direction == "i2t" else ("q_txt", "r_img")
+    cu = _cu()
+    qB, rB = torch.from_numpy(t[qk]).to(dev), torch.from_numpy(t[rk]).to(dev)
+    qL, rL = torch.from_numpy(t["q_lab"]), torch.from_numpy(t["r_lab"])
+    res = cu.map_k_detail(qB, rB, qL, rL, k, 0, topn=topn)
+    want_map, want_ap, want_nrel, want_prec = c_oracle.map_k(t[qk], t[rk], t["q_lab"], t["r_lab"], k, topn)
+    assert np.array_equal(res["n_rel"].cpu().numpy(), want_nrel)
+    err = np.max(np.abs(res["ap"].cpu().numpy() - want_ap))
+    assert err < TOL, f"per-query AP off by {err}"
+    assert abs(float(res["map"].cpu()[0]) - want_map) < TOL
+    assert 0.05 < want_map < 0.999, "degenerate synthetic case"
+    if topn:
+        np.testing.assert_allclose(res["prec"].cpu().numpy(), want_prec, rtol=0, atol=TOL)
+    if pr:
+        P, R = cu.pr_curve(qB, rB, qL, rL)
+        h_all, h_rel = c_oracle.hist_packed(*(orc.pack_codes(t[qk])[:2]), orc.pack_labels(t["q_lab"]),
+                                            *(orc.pack_codes(t[rk])[:2]), orc.pack_labels(t["r_lab"]), shape.bits)
+        assert np.array_equal(res["hist_all"].cpu().numpy().astype(np.int64), h_all[:, 0::2])
+        assert np.array_equal(res["hist_rel"].cpu().numpy().astype(np.int64), h_rel[:, 0::2])
+        wP, wR = _pr_from_hist(h_all, h_rel, shape.bits)
+        np.testing.assert_allclose(P.numpy(), wP, rtol=0, atol=TOL)
+        np.testing.assert_allclose(R.numpy(), wR, rtol=0, atol=TOL)
+    # the public entry point on the same tensors (second call: served from the pack cache)
+    assert abs(float(cu.calc_map_k_matrix(qB, rB, qL, rL, k, 0)) - want_map) < TOL
+
+
+def _pr_from_hist(h_all, h_rel, bits):
+    ca = np.cumsum(h_all, 1)[:, 0::2][:, :bits + 1].astype(np.float64)
+    cr = np.cumsum(h_rel, 1)[:, 0::2][:, :bits + 1].astype(np.float64)
+    nr = h_rel.sum(1).astype(np.float64); live = nr > 0
+    P = np.where(live[:, None], cr / np.maximum(ca, 0.1), 0.0)
+    R = np.where(live[:, None], cr / np.maximum(nr, 1.0)[:, None], 0.0)
+    sup = (P > 0).sum(0).astype(np.float64); sup[sup == 0] = 0.1
+    return P.sum(0) / sup, R.sum(0) / sup
+
+
+def test_config1_mirflickr_full(dev):
+    _full_config(dev, "c1", "i2t", None)
+    _full_config(dev, "c1", "t2i", None)
+
+
+@pytest.mark.parametrize("name", ["c2-16", "c2-32", "c2-64"])
+@pytest.mark.parametrize("direction", ["i2t", "t2i"])
+def test_config2_nuswide_full(dev, name, direction):
+    from cmh_b200.synth import CONFIGS
+    _full_config(dev, name, direction, None, topn=CONFIGS[name].topn)
+
+
+def test_config3_coco_full(dev):
+    _full_config(dev, "c3", "i2t", 5000, pr=True)
+
+
+def test_config4_slice_topk(dev):
+    """Config 4 (64-bit, top-1000) on a 2M-row slice of the counter-based database, 48 queries, bit-exact keys;
+    plus the two-shard merge of the same slice."""
+    from cmh_b200 import engine
+    from cmh_b200.index import HammingIndex
+    from cmh_b200.synth import splitmix_rows
+    D, Q, K, seed = 2_000_000, 48, 1000, 4000
+    db = engine.synth_codes(seed, 0, D, 64, dev)
+    q = engine.synth_codes(seed + 1, 0, Q, 64, dev)
+    keys = HammingIndex(db).search_packed(q, K).cpu().numpy().view(np.uint64)
+    ds = splitmix_rows(seed, 0, D, 1, 64); qs = splitmix_rows(seed + 1, 0, Q, 1, 64)
+    ones = np.full_like(ds, np.uint64((1 << 64) - 1)); qones = np.full_like(qs, np.uint64((1 << 64) - 1))
+    want = c_oracle.topk_packed(qs, qones, ds, ones, 64, K)
+    assert np.array_equal(keys, want)
+    half = D // 2 + 12345
+    parts = torch.stack([HammingIndex(db.rows(0, half), 0).search_packed(q, K),
+                         HammingIndex(db.rows(half, D), half).search_packed(q, K)])
+    assert np.array_equal(engine.topk_merge(parts, K).cpu().numpy().view(np.uint64), want)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# size-independent properties (sizes beyond what the oracle is asked to do)
+# ---------------------------------------------------------------------------------------------------------------
+def test_properties_large(dev):
+    from cmh_b200 import engine
+    D, Q, K = 20_000_000, 512, 1000
+    db = engine.synth_codes(11, 0, D, 64, dev)
+    # plant every query's own code in the database at a known row -> it must rank first among its ties
+    q = db.rows(1_000_000, 1_000_000 + Q)
+    rp = engine.RankPass(q, db, need_labels=False)
+    h_all, _ = rp.hist()
+    assert torch.all(h_all.to(torch.int64).sum(1) == D)                          # every row lands in exactly one bucket
+    keys = rp.topk(K).cpu().numpy().view(np.uint64)
+    assert np.all(np.diff(keys.astype(np.int64), axis=1) > 0)                    # strictly ascending, unique keys
+    assert np.all((keys[:, 0] >> np.uint64(32)) == 0)                            # distance 0 first ...
+    d0 = (keys >> np.uint64(32)) == 0
+    rows0 = np.where(d0, keys & np.uint64(0xFFFFFFFF), np.uint64(0xFFFFFFFF))
+    planted = np.arange(1_000_000, 1_000_000 + Q, dtype=np.uint64)
+    assert np.all((rows0 == planted[:, None]).any(axis=1))                       # ... and the planted row is among them
+    # the K-th key's bucket equals the histogram's threshold bucket (checksum of the select against pass 1)
+    cum = torch.cumsum(h_all.to(torch.int64), 1)
+    thr = (cum < K).sum(1).cpu().numpy()
+    assert np.array_equal((keys[:, -1] >> np.uint64(33)).astype(np.int64), thr)
+    # shard + merge == single pass  (4 uneven shards)
+    cuts = [0, 3_000_001, 9_999_999, 15_000_016, D]
+    parts = torch.stack([engine.RankPass(q, db.rows(cuts[i], cuts[i + 1]), need_labels=False).topk(K, cuts[i])
+                         for i in range(4)])
+    assert np.array_equal(engine.topk_merge(parts, K).cpu().numpy().view(np.uint64), keys)
+
+
+def test_all_relevant_and_identical_codes(dev):
+    cu = _cu()
+    q = torch.ones(5, 64); r = torch.ones(3000, 64)
+    qL = torch.ones(5, 24); rL = torch.ones(3000, 24)
+    assert abs(float(cu.calc_map_k_matrix(q, r, qL, rL)) - 1.0) < TOL            # every row relevant -> AP = 1
+    dist, idx = cu.topk_hamming(q, r, 100)
+    assert torch.equal(idx.cpu(), torch.arange(100).expand(5, 100))              # all ties -> index order
+    rL2 = torch.zeros(3000, 24); rL2[7, 0] = 1
+    assert abs(float(cu.calc_map_k_matrix(q, r, qL, rL2)) - 1.0 / 8) < TOL        # single relevant row at rank 8
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------------------------
+def test_edge_cases(dev):
+    cu = _cu()
+    rng = np.random.default_rng(5)
+    r = torch.from_numpy((rng.integers(0, 2, (50, 32)) * 2 - 1).astype(np.float32))
+    rL = torch.from_numpy((rng.random((50, 5)) < 0.3).astype(np.float32))
+    q = r[:4].clone(); qL = rL[:4].clone()
+    # no query at all -> python 0.0 like the reference's untouched accumulator (utils/calc_utils.py:22,38)
+    assert cu.calc_map_k_matrix(q[:0], r, qL[:0], rL) == 0.0
+    # every query label-free -> 0
+    assert float(cu.calc_map_k_matrix(q, r, torch.zeros(4, 5), rL)) == 0.0
+    # K beyond the database: K' = D, and a 1-row database
+    dist, idx = cu.topk_hamming(q, r, 1000)
+    ref_d, ref_i = orc.topk_sorted(q, r, 1000)
+    assert torch.equal(idx.cpu(), ref_i) and torch.equal(dist.cpu(), ref_d)
+    assert abs(float(cu.calc_map_k_matrix(q, r[:1], qL, rL[:1])) - float(orc.map_k_sorted(q, r[:1], qL, rL[:1]))) < TOL
+    # k larger than D and k = 1
+    for k in (1, 3, 10 ** 9):
+        assert abs(float(cu.calc_map_k_matrix(q, r, qL, rL, k)) - float(orc.map_k_sorted(q, r, qL, rL, k))) < TOL
+    # integer labels and codes (the reference accepts int64 labels)
+    got = cu.calc_map_k_matrix(q.to(torch.int8), r.to(torch.int64), qL.to(torch.int64), rL.to(torch.uint8))
+    assert abs(float(got) - float(orc.map_k_sorted(q, r, qL, rL))) < TOL
+    # mismatched code lengths raise like torch.mm would
+    with pytest.raises(RuntimeError):
+        cu.calc_map_k_matrix(q[:, :16], r, qL, rL)
+    with pytest.raises(RuntimeError):
+        cu.calc_hammingDist(q[:, :16], r)
+
+
+def test_duplicate_api_aliases(dev):
+    """`utils/utils.py: calc_map_k` applies torch.sign itself (:77-78); `calcHammingDist` takes numpy (:105-118)."""
+    from cmh_b200 import utils as u
+    case = BY_NAME["small_b64_l24"]
+    T = _T(case, 16)
+    raw_q = T["qB"] * torch.rand_like(T["qB"]).add(0.1)                          # real-valued, same signs
+    raw_r = T["rB"] * torch.rand_like(T["rB"]).add(0.1)
+    got = u.calc_map_k(raw_q.to(dev), raw_r.to(dev), T["qL"].to(dev), T["rL"].to(dev), None, 0)
+    assert got.is_cuda and abs(float(got) - float(orc.map_k_sorted(T["qB"], T["rB"], T["qL"], T["rL"]))) < TOL
+    d = u.calcHammingDist(T["qB"][:3].numpy(), T["rB"][:40].numpy())
+    assert isinstance(d, np.ndarray) and np.array_equal(d, orc.hamming_dist(T["qB"][:3], T["rB"][:40]).numpy())
+
+
+def test_four_direction_valid_pattern(dev):
+    """`TrainBase.valid` (train/base.py:259-262): four calls on the same four device buffers and host labels."""
+    from cmh_b200.synth import EvalShape, make_case
+    t = make_case(EvalShape("v", 150, 4000, 64, 24, 0.15, None, (), 99), clustered=True)
+    cu = _cu()
+    bufs = {k: torch.from_numpy(t[k]).to(dev) for k in ("q_img", "q_txt", "r_img", "r_txt")}
+    qL, rL = torch.from_numpy(t["q_lab"]), torch.from_numpy(t["r_lab"])
+    for a, b in (("q_img", "r_txt"), ("q_txt", "r_img"), ("q_img", "r_img"), ("q_txt", "r_txt")):
+        got = cu.calc_map_k(bufs[a], bufs[b], qL, rL, None, 0)
+        want = c_oracle.map_k(t[a], t[b], t["q_lab"], t["r_lab"], None)[0]
+        assert abs(float(got) - want) < TOL
+    # in-place change of a buffer (next epoch's codes) must not be served from the cache
+    bufs["q_img"].mul_(-1)
+    got = cu.calc_map_k(bufs["q_img"], bufs["r_txt"], qL, rL, None, 0)
+    want = c_oracle.map_k(-t["q_img"], t["r_txt"], t["q_lab"], t["r_lab"], None)[0]
+    assert abs(float(got) - want) < TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# sharded path, emulated on one GPU (the ranks' kernels run one after another; the exchange is done by hand)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,n_shards", [("small_b64_l24", 3), ("small_b64_ternary", 2), ("small_b256_long", 4)])
+def test_sharded_rank_equals_single(dev, name, n_shards):
+    from cmh_b200 import engine
+    from cmh_b200.sharded import shard_bounds
+    case = BY_NAME[name]
+    g, T = load_golden(case), _T(case)
+    cu = _cu()
+    q, d = cu._prepare(T["qB"].to(dev), T["rB"].to(dev), T["qL"], T["rL"], 0)
+    tern = q.valid is not None or d.valid is not None
+    topn = (1, 10, 100)
+    passes = [engine.RankPass(q, d.rows(*shard_bounds(d.n, n_shards, r)), need_labels=True, max_topn=3, ternary=tern)
+              for r in range(n_shards)]
+    hists = [p.hist() for p in passes]
+    wide_a = torch.stack([h[0].to(torch.int64) for h in hists]); wide_r = torch.stack([h[1].to(torch.int64) for h in hists])
+    glob = (wide_a.sum(0).to(torch.int32), wide_r.sum(0).to(torch.int32))
+    k = case.ks[-1]
+    ap_sum = torch.zeros(q.n, dtype=torch.float64, device=dev); hits = torch.zeros((q.n, 3), dtype=torch.int32, device=dev)
+    for r, p in enumerate(passes):
+        lower = (wide_a[:r].sum(0).to(torch.int32), wide_r[:r].sum(0).to(torch.int32))
+        s, n_rel, h = p.rank(k, topn, lower=lower, glob=glob)
+        ap_sum += s; hits += h
+    ap, m = engine.finalize_map(ap_sum, n_rel, k)
+    assert np.array_equal(n_rel.cpu().numpy(), g["n_rel"])
+    np.testing.assert_allclose(ap.cpu().numpy(), g[f"ap_{k_tag(k)}"], rtol=0, atol=TOL)
+    single = cu.map_k_detail(T["qB"].to(dev), T["rB"].to(dev), T["qL"], T["rL"], k, 0, topn=topn)
+    assert torch.equal(hits, single["hits"])                                       # integer hit counts: exact
+    assert abs(float(m.cpu()[0]) - float(single["map"].cpu()[0])) < 1e-7

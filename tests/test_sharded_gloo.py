@@ -1,0 +1,90 @@
+"""world_size-2 (and 3) `gloo` runs of the multi-GPU exchange logic in `cmh_b200.sharded`, on CPU, with the numpy
+test double of the device passes (`tests/cpu_engine.py`).  Checks N shards == 1 shard: per-query AP, n_rel,
+precision@N, PR curve and the merged top-K keys."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _packed_sets(ternary_frac):
+    from cmh_b200.engine import PackedSet
+    from cmh_b200.synth import EvalShape, make_case
+    from oracle import cmh_oracle as orc
+    shape = EvalShape("gloo", 9, 301, 20, 24, 0.15, None, (), 77)
+    t = make_case(shape, clustered=True, zero_query_frac=0.15, ternary_frac=ternary_frac)
+
+    def mk(codes, labels):
+        s, v, nz, _ = orc.pack_codes(codes)
+        return PackedSet(torch.from_numpy(s.view(np.int64)), torch.from_numpy(v.view(np.int64)) if ternary_frac else None,
+                         torch.from_numpy(orc.pack_labels(labels).view(np.int64)), codes.shape[0], codes.shape[1], labels.shape[1], nz)
+    return mk(t["q_img"], t["q_lab"]), mk(t["r_txt"], t["r_lab"]), t
+
+
+def _worker(rank, world, port, ternary_frac, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import cpu_engine
+        from cmh_b200 import sharded
+        q, d, _ = _packed_sets(ternary_frac)
+        lo, hi = sharded.shard_bounds(d.n, world, rank)
+        topn = (1, 7, 50, 10_000)
+        res = sharded.map_k_sharded(q, d.rows(lo, hi), 40, d.n, topn, eng=cpu_engine, want_pr=True,
+                                    ternary=bool(ternary_frac))
+        keys = sharded.topk_sharded(q.with_labels(None, 0), d.rows(lo, hi).with_labels(None, 0), 25, lo,
+                                    eng=cpu_engine, ternary=bool(ternary_frac))
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), ap=res["ap"].numpy(), n_rel=res["n_rel"].numpy(),
+                 map=res["map"].numpy(), prec=res["prec"].numpy(), P=res["pr"][0].numpy(), R=res["pr"][1].numpy(),
+                 keys=keys.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,ternary_frac", [(2, 0.0), (2, 0.1), (3, 0.0)])
+def test_sharded_equals_single(tmp_path, world, ternary_frac):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, ternary_frac, str(tmp_path)), nprocs=world, join=True)
+    from oracle import c_oracle, cmh_oracle as orc
+    _, _, t = _packed_sets(ternary_frac)
+    topn = (1, 7, 50, 10_000)
+    want_map, want_ap, want_nrel, want_prec = c_oracle.map_k(t["q_img"], t["r_txt"], t["q_lab"], t["r_lab"], 40, topn)
+    wP, wR = orc.pr_curve_counting(t["q_img"], t["r_txt"], t["q_lab"], t["r_lab"])
+    want_keys = orc.topk_counting(t["q_img"], t["r_txt"], 25)
+    for r in range(world):
+        z = np.load(os.path.join(str(tmp_path), f"r{r}.npz"))
+        assert np.array_equal(z["n_rel"], want_nrel)
+        np.testing.assert_allclose(z["ap"], want_ap, rtol=0, atol=1e-12)
+        assert abs(float(z["map"][0]) - want_map) < 1e-6
+        np.testing.assert_allclose(z["prec"], want_prec, rtol=0, atol=1e-6)
+        np.testing.assert_allclose(z["P"], wP, rtol=0, atol=1e-6)
+        np.testing.assert_allclose(z["R"], wR, rtol=0, atol=1e-6)
+        assert np.array_equal(z["keys"].view(np.uint64), want_keys)       # bit-exact merged ranking
+
+
+def test_shard_bounds_cover_rows():
+    from cmh_b200.sharded import shard_bounds
+    for n in (0, 1, 7, 100, 100_000_000):
+        for w in (1, 2, 3, 8):
+            b = [shard_bounds(n, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
