@@ -44,6 +44,7 @@ struct EvalArgs {
     int cw, lw;                     // 32-bit words that can be non-zero
     int bits, nb;
     int chunk_rows, n_chunks;
+    int bulk_ok;                    // database planes are 16-byte aligned: stages may use the bulk-copy engine
     // pass 2
     int64_t index_base;
     int ntopn, K;

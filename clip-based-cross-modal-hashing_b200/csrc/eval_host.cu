@@ -79,6 +79,8 @@ static int fill_args(const cmh_plan& p, const cmh_codeset* q, const cmh_codeset*
     if (!(q->labels && d->labels)) { a.lw = 0; a.lw_stride = 0; a.ql = a.dl = nullptr; }
     a.nq = p.nq; a.nd = p.nd; a.nq_pad = p.nq_pad;
     a.chunk_rows = p.chunk_rows; a.n_chunks = p.n_chunks;
+    const uintptr_t align = (uintptr_t)a.ds | (uintptr_t)a.dv | (uintptr_t)a.dl;
+    a.bulk_ok = (align & 15) == 0;
     *out = a;
     return CMH_OK;
 }

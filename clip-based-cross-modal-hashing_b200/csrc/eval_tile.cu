@@ -51,13 +51,14 @@ __device__ __forceinline__ TileSmem carve_tile_smem(unsigned char* raw, const Ev
 }
 
 // Fill one stage with database rows [row0, row0 + rows).  Full stages go through the bulk-copy engine; the ragged
-// last stage of a chunk is copied by the CTA (row counts that are not a multiple of 16 bytes cannot be bulk-copied).
+// last stage of a chunk is copied by the CTA (row counts that are not a multiple of 16 bytes cannot be bulk-copied),
+// and so is every stage of a shard whose planes are not 16-byte aligned (a row-range view starting at an odd row).
 // Must be called by all threads of the CTA.
 template <bool TERN>
 __device__ __forceinline__ void load_stage(const EvalArgs& a, const TileSmem& s, int st, int64_t row0, int rows) {
     const uint32_t code_b = (uint32_t)rows * a.cw_stride * 4;
     const uint32_t lab_b = (uint32_t)rows * a.lw_stride * 4;
-    if (rows == TILE_ROWS) {
+    if (rows == TILE_ROWS && a.bulk_ok) {
         if (threadIdx.x == 0) {
             mbar_expect_tx(&s.bar[st], code_b * (TERN ? 2u : 1u) + lab_b);
             bulk_g2s(s.codes[st], a.ds + row0 * a.cw_stride, code_b, &s.bar[st]);

@@ -238,6 +238,8 @@ class RankPass:
         nq = self.q.n
         self.hist_all = torch.empty((nq, self.nb), dtype=torch.int32, device=self.device)
         self.hist_rel = torch.empty((nq, self.nb), dtype=torch.int32, device=self.device) if self.need_labels else None
+        if nq == 0:
+            return self.hist_all, self.hist_rel
         with torch.cuda.device(self.device):
             check(_cabi.lib().cmh_eval_hist(ctypes.byref(self.plan), ctypes.byref(self._qs), ctypes.byref(self._ds),
                                             _ptr(self.hist_all), _ptr(self.hist_rel), _ptr(self.workspace),
@@ -254,6 +256,8 @@ class RankPass:
         n_rel = torch.zeros(nq, dtype=torch.int64, device=self.device)
         topn = [int(t) for t in topn]
         hits = torch.zeros((nq, len(topn)), dtype=torch.int32, device=self.device) if topn else None
+        if nq == 0:
+            return ap_sum, n_rel, hits
         la = lr = ga = gr = None
         if lower is not None:
             la, lr = lower
@@ -269,6 +273,8 @@ class RankPass:
     def topk(self, K: int, index_base: int = 0) -> torch.Tensor:
         """int64 [nq, K] ascending keys ``(2*dist << 32) | (index_base + row)``; -1 (= UINT64_MAX) pads."""
         keys = torch.empty((self.q.n, int(K)), dtype=torch.int64, device=self.device)
+        if self.q.n == 0:
+            return keys
         with torch.cuda.device(self.device):
             check(_cabi.lib().cmh_topk(ctypes.byref(self.plan), ctypes.byref(self._qs), ctypes.byref(self._ds), int(K),
                                        int(index_base), _ptr(keys), _ptr(self.workspace), _stream(self.device)),

@@ -19,7 +19,8 @@
  *   stable top-K ranking (north star config 4)                   cmh_topk, cmh_topk_merge
  *
  * Conventions
- *   - every pointer marked "device" is a CUDA device pointer on the current device, 16-byte aligned;
+ *   - every pointer marked "device" is a CUDA device pointer on the current device, 8-byte aligned (16-byte aligned
+ *     database planes let the ranking kernels stage rows with the bulk-copy engine; others take a slower path);
  *     `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls only enqueue work;
  *     nothing synchronises unless stated.
  *   - every function returns 0 on success, a negative CMH_ERR_* for argument errors, or a positive
