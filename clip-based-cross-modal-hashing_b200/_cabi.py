@@ -16,7 +16,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "libcmh_b200.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(_PKG_DIR), "include")
-SOURCES = ("api.cu", "pack.cu", "dense.cu", "eval_tile.cu", "eval_warp.cu", "eval_host.cu", "peaks.cu")
+SOURCES = ("api.cu", "pack.cu", "dense.cu", "eval_tile.cu", "eval_warp.cu", "eval_host.cu", "peaks.cu", "tc_collect.cu")
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared")
 
@@ -33,6 +33,7 @@ EXPORTS = (
     "cmh_finalize_map", "cmh_finalize_topn", "cmh_finalize_pr_workspace_bytes", "cmh_finalize_pr",
     "cmh_map_k_workspace_bytes", "cmh_map_k",
     "cmh_topk", "cmh_topk_merge",
+    "cmh_tc_supported", "cmh_tc_collect", "cmh_topk_threshold", "cmh_topk_finalize",
 )
 
 
@@ -130,6 +131,10 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cmh_map_k.argtypes = [pcs, pcs, i32, i32, i64, vp, vp, vp, u64, vp]
     L.cmh_topk.argtypes = [ppl, pcs, pcs, i32, i64, vp, vp, vp]
     L.cmh_topk_merge.argtypes = [vp, i32, i64, i32, vp, vp]
+    L.cmh_tc_supported.argtypes = [i32, i32]
+    L.cmh_tc_collect.argtypes = [vp, i64, vp, i64, i32, i64, vp, i32, vp, vp, vp]
+    L.cmh_topk_threshold.argtypes = [vp, i64, i32, i64, i64, i32, vp, vp]
+    L.cmh_topk_finalize.argtypes = [vp, vp, i64, i32, i32, i64, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("cmh_last_error", "cmh_finalize_pr_workspace_bytes", "cmh_map_k_workspace_bytes",

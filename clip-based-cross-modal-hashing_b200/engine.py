@@ -334,3 +334,58 @@ def topk_merge(keys_in: torch.Tensor, K: int) -> torch.Tensor:
         check(_cabi.lib().cmh_topk_merge(_ptr(keys_in), n_lists, nq, K, _ptr(out), _stream(keys_in.device)),
               "cmh_topk_merge")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# top-K on the tensor cores (tcgen05 / TMEM): sample histogram -> thresholds -> fused GEMM + candidate filter ->
+# per-query sort; queries whose candidate list came out short or overflowed are redone by the exact two-pass path
+# ---------------------------------------------------------------------------------------------------------------
+TC_DEFAULT_CAP = 16384
+
+
+def tc_supported(q: PackedSet, d: PackedSet) -> bool:
+    return (q.valid is None and d.valid is None and q.bits == d.bits
+            and bool(_cabi.lib().cmh_tc_supported(q.bits, 0)))
+
+
+def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Optional[PackedSet] = None,
+            cap: int = TC_DEFAULT_CAP, stats: Optional[dict] = None) -> torch.Tensor:
+    """int64 [nq, K] ascending keys, identical to ``RankPass(q, d).topk(K, index_base)``.
+
+    ``sample``: a subset of the rows of ``d`` (any rows, contiguous in memory) used only to guess the per-query
+    thresholds; None = use ``d`` itself (exact thresholds, an extra popc pass)."""
+    if not tc_supported(q, d):
+        raise ValueError("tensor-core top-K needs +-1 codes of 64 or 128 bits")
+    K = int(K)
+    dev = q.device
+    nq = q.n
+    keys = torch.empty((nq, K), dtype=torch.int64, device=dev)
+    if nq == 0:
+        return keys
+    if d.n == 0:
+        return keys.fill_(-1)
+    L = _cabi.lib()
+    smp = d if sample is None else sample
+    h_all, _ = RankPass(q.with_labels(None, 0), smp.with_labels(None, 0), need_labels=False).hist()
+    thr = torch.empty(nq, dtype=torch.int32, device=dev)
+    cand = torch.empty((nq, cap), dtype=torch.int64, device=dev)
+    cnt = torch.empty(nq, dtype=torch.int32, device=dev)
+    fail_flags = torch.empty(nq, dtype=torch.int32, device=dev)
+    fail_count = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        check(L.cmh_topk_threshold(_ptr(h_all), nq, q.bits + 1, smp.n, d.n, K, _ptr(thr), st), "cmh_topk_threshold")
+        check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign), d.n, q.bits, int(index_base), _ptr(thr), cap,
+                               _ptr(cand), _ptr(cnt), st), "cmh_tc_collect")
+        check(L.cmh_topk_finalize(_ptr(cand), _ptr(cnt), nq, cap, K, d.n, _ptr(keys), _ptr(fail_flags),
+                                  _ptr(fail_count), st), "cmh_topk_finalize")
+    n_fail = int(fail_count.item())
+    if stats is not None:
+        stats["n_fail"] = n_fail
+        stats["candidates"] = cnt
+        stats["thr"] = thr
+    if n_fail:
+        rows = torch.nonzero(fail_flags, as_tuple=False).squeeze(1)
+        sub = PackedSet(q.sign.index_select(0, rows).contiguous(), None, None, int(rows.numel()), q.bits)
+        keys.index_copy_(0, rows, RankPass(sub, d.with_labels(None, 0), need_labels=False).topk(K, index_base))
+    return keys

@@ -254,6 +254,48 @@ def test_config4_slice_topk(dev):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) top-K path against the popc path / oracle
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bits,nq,nd,K", [(64, 48, 5000, 100), (64, 700, 100_003, 1000), (128, 130, 40_000, 50),
+                                          (64, 5, 255, 1000), (64, 513, 300_000, 10), (128, 1025, 70_001, 1000)])
+def test_tc_topk_matches_popc_path(dev, bits, nq, nd, K):
+    from cmh_b200 import engine
+    db = engine.synth_codes(100 + bits, 0, nd, bits, dev)
+    q = engine.synth_codes(200 + bits, 0, nq, bits, dev)
+    want = engine.RankPass(q, db, need_labels=False).topk(K, 77)
+    stats = {}
+    got = engine.topk_tc(q, db, K, 77, stats=stats)
+    assert stats["n_fail"] == 0
+    assert torch.equal(got, want)
+
+
+def test_tc_topk_against_oracle_and_fallback(dev):
+    from cmh_b200 import engine
+    from cmh_b200.synth import splitmix_rows
+    D, Q, K, seed = 1_000_000, 64, 1000, 4000
+    db = engine.synth_codes(seed, 0, D, 64, dev)
+    q = engine.synth_codes(seed + 1, 0, Q, 64, dev)
+    ds = splitmix_rows(seed, 0, D, 1, 64); qs = splitmix_rows(seed + 1, 0, Q, 1, 64)
+    ones = np.full_like(ds, np.uint64((1 << 64) - 1)); qones = np.full_like(qs, np.uint64((1 << 64) - 1))
+    want = c_oracle.topk_packed(qs, qones, ds, ones, 64, K)
+    # thresholds from a 1/64 strided sample (statistical; exactness must not depend on it)
+    sample = engine.PackedSet(db.sign[::64].contiguous(), None, None, (D + 63) // 64, 64)
+    stats = {}
+    got = engine.topk_tc(q, db, K, 0, sample=sample, stats=stats)
+    assert np.array_equal(got.cpu().numpy().view(np.uint64), want)
+    # a candidate buffer that is far too small forces every query through the exact fallback
+    stats = {}
+    got = engine.topk_tc(q, db, K, 0, cap=512, stats=stats)
+    assert stats["n_fail"] == Q
+    assert np.array_equal(got.cpu().numpy().view(np.uint64), want)
+    # massive ties (identical codes): candidate lists overflow -> fallback -> index order
+    same = engine.PackedSet(torch.zeros((50_000, 1), dtype=torch.int64, device=dev), None, None, 50_000, 64)
+    qz = engine.PackedSet(torch.zeros((3, 1), dtype=torch.int64, device=dev), None, None, 3, 64)
+    got = engine.topk_tc(qz, same, 100, 0)
+    assert torch.equal(got.cpu(), torch.arange(100).expand(3, 100))
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # size-independent properties (sizes beyond what the oracle is asked to do)
 # ---------------------------------------------------------------------------------------------------------------
 def test_properties_large(dev):
