@@ -132,9 +132,9 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cmh_topk.argtypes = [ppl, pcs, pcs, i32, i64, vp, vp, vp]
     L.cmh_topk_merge.argtypes = [vp, i32, i64, i32, vp, vp]
     L.cmh_tc_supported.argtypes = [i32, i32]
-    L.cmh_tc_collect.argtypes = [vp, i64, vp, i64, i32, i64, vp, i32, vp, vp, vp]
+    L.cmh_tc_collect.argtypes = [vp, i64, vp, i64, i32, i64, vp, i32, i32, vp, vp, vp, vp]
     L.cmh_topk_threshold.argtypes = [vp, i64, i32, i64, i64, i32, vp, vp]
-    L.cmh_topk_finalize.argtypes = [vp, vp, i64, i32, i32, i64, vp, vp, vp, vp]
+    L.cmh_topk_finalize.argtypes = [vp, vp, vp, i64, i32, i32, i64, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("cmh_last_error", "cmh_finalize_pr_workspace_bytes", "cmh_map_k_workspace_bytes",

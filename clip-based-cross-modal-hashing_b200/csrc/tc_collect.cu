@@ -99,18 +99,50 @@ __device__ __forceinline__ uint4 expand16(uint32_t bits16, const uint32_t* __res
     return o;
 }
 
+constexpr int TC_SLOTS = 8;        // staged hits per epilogue LANE (private slots: the hit path has no atomics)
+constexpr int TC_FLUSH_AT = 4;     // a warp flushes once any of its lanes holds this many staged hits
+constexpr int TC_REFRESH = 128;    // tile iterations between threshold refreshes
+
+// per-query bookkeeping shared by every CTA working on the query (global memory, zeroed by cmh_tc_collect)
+struct TcAux {
+    uint32_t cum_le[4];   // candidates found so far with dist <= thr0 - j   (j = 0..3)
+    uint32_t force_fail;  // a staging buffer overflowed: a candidate may have been dropped
+    uint32_t pad[3];
+};
+
 struct TcArgs {
     const uint64_t* q;      // [nq][words]
     const uint64_t* d;      // [nd][words]
-    const int32_t* thr;     // [nq] threshold bucket (Hamming distance): rows with dist <= thr are candidates
+    const int32_t* thr;     // [nq] initial threshold bucket thr0 (Hamming distance): rows with dist <= thr qualify
     uint64_t* cand;         // [nq][cap]
     uint32_t* cnt;          // [nq] candidates found (may exceed cap)
+    TcAux* aux;             // [nq]
     int64_t nq, nd, index_base;
     int chunk_rows;         // database rows per CTA (multiple of TC_N)
     int cap, bits;
+    int K;                  // > 0: tighten thresholds while scanning (once K rows at dist <= thr0 - j are known)
 };
 
-// smem: [A: T tiles][B: STAGES tiles][lut 64 B][barriers][tmem slot]
+__device__ __forceinline__ int max8(const int* v) {
+    int m = __vimax3_s32(v[0], v[1], v[2]);
+    int n = __vimax3_s32(v[3], v[4], v[5]);
+    return __vimax3_s32(m, n, max(v[6], v[7]));
+}
+
+// Out of line on purpose: one copy of the append code keeps the epilogue's instruction footprint small (an inlined,
+// fully unrolled hit path was ~160 KB of SASS and every rare hit paid a chain of instruction-cache misses).
+__device__ __noinline__ int tc_stage_hit(uint64_t* my_key, unsigned char* my_t, int n_staged, uint64_t key, int t,
+                                         uint32_t* force_fail) {
+    if (n_staged < TC_SLOTS) {
+        my_key[n_staged * 32] = key;
+        my_t[n_staged * 32] = (unsigned char)t;
+        return n_staged + 1;
+    }
+    *force_fail = 1u;
+    return n_staged;
+}
+
+// smem: [A: T tiles][B: STAGES tiles][lut 64 B][barriers][tmem slot][staging][thresholds]
 template <int WORDS, int T, int TC_STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs a) {
     constexpr int KBYTES = WORDS * 64;           // int8 elements (= bytes) per row
@@ -128,6 +160,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
     uint64_t* t_full = bars + 2 * TC_STAGES;     // [2] MMA -> epilogue
     uint64_t* t_empty = bars + 2 * TC_STAGES + 2;  // [2] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+    // staged hits: [EPI_WARPS][SLOTS][32 lanes] (slot-major, lane fastest: conflict-free), 8-byte aligned
+    uint64_t* stg_key = reinterpret_cast<uint64_t*>(tmem_slot + 2);
+    unsigned char* stg_t = reinterpret_cast<unsigned char*>(stg_key + TC_EPI_WARPS * TC_SLOTS * 32);
+    int* s_thr = reinterpret_cast<int*>(stg_t + TC_EPI_WARPS * TC_SLOTS * 32);    // [T][128] current dot thresholds
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t q0 = (int64_t)blockIdx.x * (T * TC_M);
@@ -240,52 +276,100 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
         const int quarter = warp & 3;                     // TMEM lanes this warp may touch: 32 * (warp % 4)
         const int col_half = ew >> 2;                     // columns [0,128) or [128,256)
         const int qrow = quarter * 32 + lane;             // query row inside the 128-row tile
-        int thr_dot[T];
-#pragma unroll
+        uint64_t* my_key = stg_key + ew * (TC_SLOTS * 32) + lane;      // slot s at my_key[s * 32]
+        unsigned char* my_t = stg_t + ew * (TC_SLOTS * 32) + lane;
+        int n_staged = 0;                                              // this lane's staged hits
+        // dist <= thr  <=>  dot = bits - 2 dist >= bits - 2 thr ; padding queries never fire.  Both column halves
+        // own the same (t, qrow) entries and write identical values.
         for (int t = 0; t < T; ++t) {
             const int64_t q = q0 + t * TC_M + qrow;
-            // dist <= thr  <=>  dot = bits - 2 dist >= bits - 2 thr ; padding queries never fire
-            thr_dot[t] = q < a.nq ? a.bits - 2 * a.thr[q] : 0x7fffffff;
+            s_thr[t * TC_M + qrow] = q < a.nq ? a.bits - 2 * a.thr[q] : 0x7fffffff;
         }
+        __syncwarp();
+        // staged hits -> global candidate lists.  Every lane drains its own slots, so the 32 returning atomics of a
+        // trip are in flight together and their latency is paid once per flush instead of once per hit.
+        auto flush = [&](int at_least) {
+            if (__any_sync(0xffffffffu, n_staged >= at_least)) {
+                for (int e = 0; e < n_staged; ++e) {
+                    const uint64_t key = my_key[e * 32];
+                    const int64_t q = q0 + (int)my_t[e * 32] * TC_M + qrow;
+                    const uint32_t pos = atomicAdd(&a.cnt[q], 1u);
+                    if (pos < (uint32_t)a.cap) a.cand[q * a.cap + pos] = key;
+                    if (a.K > 0) {
+                        const int slack = a.thr[q] - (int)((uint32_t)(key >> 32) >> 1);   // thr0 - dist >= 0
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (slack >= j) atomicAdd(&a.aux[q].cum_le[j], 1u);
+                    }
+                }
+                n_staged = 0;
+            }
+        };
+        // 32 dot products of this lane's query: block maxima (ILP 4), one compare; the hit path is rare
+        auto scan32 = [&](const int (&x)[32], int thr, int t, int64_t row0) {
+            int mb[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) mb[b] = max8(x + 8 * b);
+            const int m = __vimax3_s32(mb[0], mb[1], max(mb[2], mb[3]));
+            if (m >= thr) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (mb[b] >= thr) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int val = x[8 * b + j];
+                            const int64_t row = row0 + 8 * b + j;
+                            if (val >= thr && row < c_end)
+                                n_staged = tc_stage_hit(my_key, my_t, n_staged,
+                                                        ((uint64_t)(uint32_t)(a.bits - val) << 32) |
+                                                            (uint64_t)(a.index_base + row),
+                                                        t, &a.aux[q0 + t * TC_M + qrow].force_fail);
+                        }
+                    }
+                }
+            }
+        };
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + col_half * 128;
         int it = 0;
         for (int i = 0; i < n_tiles; ++i) {
             const int64_t tile_row0 = c_begin + (int64_t)i * TC_N + col_half * 128;
-#pragma unroll
+#pragma unroll 1
             for (int t = 0; t < T; ++t, ++it) {
                 const int buf = it & 1;
                 mbar_wait(&t_full[buf], (it >> 1) & 1);
                 tc_fence_after();
-                const int thr = thr_dot[t];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    int v[32];
-                    tmem_ld32(lane_addr + buf * TC_N + g * 32, v);
+                const int thr = s_thr[t * TC_M + qrow];
+                const uint32_t taddr = lane_addr + buf * TC_N;
+                int v0[32], v1[32];
+                tmem_ld32(taddr, v0);
+#pragma unroll 1
+                for (int gp = 0; gp < 2; ++gp) {      // rolled: two static scan sites in the whole epilogue
                     tmem_ld_wait();
-                    int m = v[0];
-#pragma unroll
-                    for (int j = 1; j + 1 < 32; j += 2) m = __vimax3_s32(m, v[j], v[j + 1]);
-                    m = max(m, v[31]);
-                    if (m >= thr) {
-                        const int64_t q = q0 + t * TC_M + qrow;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (v[j] >= thr) {
-                                const int64_t row = tile_row0 + g * 32 + j;
-                                if (row < c_end) {
-                                    const uint32_t pos = atomicAdd(&a.cnt[q], 1u);
-                                    if (pos < (uint32_t)a.cap)
-                                        a.cand[q * a.cap + pos] =
-                                            ((uint64_t)(uint32_t)(a.bits - v[j]) << 32) | (uint64_t)(a.index_base + row);
-                                }
-                            }
-                        }
-                    }
+                    tmem_ld32(taddr + (2 * gp + 1) * 32, v1);          // in flight while v0 is scanned
+                    scan32(v0, thr, t, tile_row0 + (2 * gp) * 32);
+                    tmem_ld_wait();
+                    if (gp == 0) tmem_ld32(taddr + 64, v0);
+                    scan32(v1, thr, t, tile_row0 + (2 * gp + 1) * 32);
                 }
                 tc_fence_before();
                 mbar_arrive(&t_empty[buf]);
+                flush(TC_FLUSH_AT);
+                if (a.K > 0 && (it & (TC_REFRESH - 1)) == TC_REFRESH - 1) {
+                    // tighten: once K rows at dist <= thr0 - j are known, nothing beyond that bucket can be in the top K
+                    for (int u = 0; u < T; ++u) {
+                        const int64_t q = q0 + u * TC_M + qrow;
+                        if (q < a.nq) {
+                            const uint4 c = __ldcg(reinterpret_cast<const uint4*>(a.aux[q].cum_le));
+                            const uint32_t K = (uint32_t)a.K;
+                            const int j = c.w >= K ? 3 : (c.z >= K ? 2 : (c.y >= K ? 1 : 0));
+                            s_thr[u * TC_M + qrow] = a.bits - 2 * (a.thr[q] - j);
+                        }
+                    }
+                    __syncwarp();
+                }
             }
         }
+        flush(1);
     }
     // ---- teardown -----------------------------------------------------------------------------------------------
     tc_fence_before();
@@ -311,18 +395,46 @@ __global__ void __launch_bounds__(256) topk_threshold_kernel(const uint32_t* __r
     thr[q] = t;
 }
 
-// ---- finalize: sort the candidates of one query by key, emit the K smallest --------------------------------------------
-// One CTA per query; bitonic sort in shared memory over the next power of two >= min(cnt, cap).
+// ---- finalize: exact K-th bucket from the candidates' own histogram, compact, sort, emit -------------------------------
+// One CTA per query.  Every database row at or below the query's final threshold was collected, and that threshold
+// is an upper bound of the K-th distance, so the smallest bucket T whose cumulative candidate count reaches K is the
+// true K-th distance; only candidates with dist <= T (between K and a few K of them) are sorted - by key, i.e. by
+// (distance, global index), which is the stable ranking.
+constexpr int FIN_MAX = 4096;
+constexpr int FIN_BINS = 129;   // bits <= 128 on the tensor path
+
 __global__ void __launch_bounds__(512) topk_finalize_kernel(const uint64_t* __restrict__ cand,
-                                                            const uint32_t* __restrict__ cnt, int cap, int K,
-                                                            int64_t nd, uint64_t* __restrict__ keys,
+                                                            const uint32_t* __restrict__ cnt,
+                                                            const TcAux* __restrict__ aux, int cap, int K, int64_t nd,
+                                                            uint64_t* __restrict__ keys,
                                                             uint32_t* __restrict__ fail_flags,
                                                             uint32_t* __restrict__ fail_count) {
-    extern __shared__ uint64_t sk[];
+    __shared__ uint64_t sk[FIN_MAX];
+    __shared__ uint32_t hist[FIN_BINS];
+    __shared__ int s_T, s_keep;
+    __shared__ uint32_t s_n;
     const int64_t q = blockIdx.x;
     const uint32_t n_found = cnt[q];
     const int64_t need = nd < (int64_t)K ? nd : (int64_t)K;
-    const bool fail = n_found > (uint32_t)cap || (int64_t)n_found < need;
+    bool fail = n_found > (uint32_t)cap || (int64_t)n_found < need || aux[q].force_fail != 0u;
+    const int n = (int)n_found;
+    const uint64_t* __restrict__ mine = cand + q * cap;
+    if (!fail) {
+        for (int i = threadIdx.x; i < FIN_BINS; i += blockDim.x) hist[i] = 0u;
+        if (threadIdx.x == 0) s_n = 0u;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[(uint32_t)(mine[i] >> 33)], 1u);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int64_t cum = 0;
+            int T = -1;
+            for (int b = 0; b < FIN_BINS && cum < need; ++b) { cum += hist[b]; T = b; }
+            s_T = T;
+            s_keep = cum > FIN_MAX ? -1 : (int)cum;
+        }
+        __syncthreads();
+        fail = s_keep < 0;
+    }
     if (threadIdx.x == 0) {
         fail_flags[q] = fail ? 1u : 0u;
         if (fail) atomicAdd(fail_count, 1u);
@@ -331,10 +443,15 @@ __global__ void __launch_bounds__(512) topk_finalize_kernel(const uint64_t* __re
         for (int i = threadIdx.x; i < K; i += blockDim.x) keys[q * K + i] = ~0ull;
         return;
     }
-    const int n = (int)n_found;
+    const int T = s_T, keep = s_keep;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t key = mine[i];
+        if ((int)(uint32_t)(key >> 33) <= T) sk[atomicAdd(&s_n, 1u)] = key;
+    }
     int p2 = 1;
-    while (p2 < n) p2 <<= 1;
-    for (int i = threadIdx.x; i < p2; i += blockDim.x) sk[i] = i < n ? cand[q * cap + i] : ~0ull;
+    while (p2 < keep) p2 <<= 1;
+    __syncthreads();
+    for (int i = keep + threadIdx.x; i < p2; i += blockDim.x) sk[i] = ~0ull;
     __syncthreads();
     for (int k = 2; k <= p2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -349,7 +466,7 @@ __global__ void __launch_bounds__(512) topk_finalize_kernel(const uint64_t* __re
             __syncthreads();
         }
     }
-    for (int i = threadIdx.x; i < K; i += blockDim.x) keys[q * K + i] = i < n ? sk[i] : ~0ull;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) keys[q * K + i] = i < keep ? sk[i] : ~0ull;
 }
 
 }  // namespace cmh
@@ -361,7 +478,8 @@ using namespace cmh;
 static int tc_stages(int words) { return words == 1 ? 6 : 4; }
 static size_t tc_smem_bytes(int words, int T) {
     const int st = tc_stages(words);
-    return (size_t)T * TC_M * words * 64 + (size_t)st * TC_N * words * 64 + 64 + (2 * st + 4) * 8 + 16;
+    return (size_t)T * TC_M * words * 64 + (size_t)st * TC_N * words * 64 + 64 + (2 * st + 4) * 8 + 8 +
+           (size_t)TC_EPI_WARPS * TC_SLOTS * 32 * 9 + (size_t)T * TC_M * 4 + 16;
 }
 
 extern "C" int cmh_tc_supported(int bits, int ternary) {
@@ -369,15 +487,17 @@ extern "C" int cmh_tc_supported(int bits, int ternary) {
 }
 
 extern "C" int cmh_tc_collect(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits,
-                              int64_t index_base, const int32_t* thr, int cap, uint64_t* cand, uint32_t* cnt,
-                              void* stream) {
+                              int64_t index_base, const int32_t* thr, int K, int cap, uint64_t* cand, uint32_t* cnt,
+                              uint32_t* aux, void* stream) {
     CMH_REQUIRE(cmh_tc_supported(bits, 0), CMH_ERR_UNSUPPORTED, "cmh_tc_collect: bits=%d (64 or 128, +-1 codes only)", bits);
-    CMH_REQUIRE(nq >= 0 && nd >= 0 && cap >= 1 && index_base >= 0 && index_base + nd <= (1ll << 32), CMH_ERR_ARG,
+    CMH_REQUIRE(nq >= 0 && nd >= 0 && cap >= 1 && K >= 0 && index_base >= 0 && index_base + nd <= (1ll << 32), CMH_ERR_ARG,
                 "cmh_tc_collect: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
     if (nq == 0) return CMH_OK;
-    CMH_REQUIRE(q_sign && thr && cand && cnt, CMH_ERR_ARG, "cmh_tc_collect: NULL pointer");
+    CMH_REQUIRE(q_sign && thr && cand && cnt && aux, CMH_ERR_ARG, "cmh_tc_collect: NULL pointer");
+    static_assert(sizeof(TcAux) == 32, "cmh_tc_collect: aux is uint32 [nq][8]");
     CMH_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, st));
+    CMH_CUDA(cudaMemsetAsync(aux, 0, (size_t)nq * sizeof(TcAux), st));
     if (nd == 0) return CMH_OK;
     CMH_REQUIRE(d_sign, CMH_ERR_ARG, "cmh_tc_collect: NULL database");
     const int words = bits / 64;
@@ -391,8 +511,9 @@ extern "C" int cmh_tc_collect(const uint64_t* q_sign, int64_t nq, const uint64_t
     CMH_REQUIRE(n_chunks <= 65535 && n_qgroups <= 0x7fffffffll && chunk_rows <= 0x7fffffff, CMH_ERR_UNSUPPORTED,
                 "cmh_tc_collect: launch geometry out of range");
     TcArgs a;
-    a.q = q_sign; a.d = d_sign; a.thr = thr; a.cand = cand; a.cnt = cnt;
+    a.q = q_sign; a.d = d_sign; a.thr = thr; a.cand = cand; a.cnt = cnt; a.aux = reinterpret_cast<TcAux*>(aux);
     a.nq = nq; a.nd = nd; a.index_base = index_base; a.chunk_rows = (int)chunk_rows; a.cap = cap; a.bits = bits;
+    a.K = K;
     const size_t smem = tc_smem_bytes(words, T);
     const dim3 grid((unsigned)n_qgroups, (unsigned)n_chunks);
     if (words == 1) {
@@ -423,20 +544,18 @@ extern "C" int cmh_topk_threshold(const uint32_t* hist, int64_t nq, int nb, int6
     return CMH_OK;
 }
 
-extern "C" int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, int64_t nq, int cap, int K, int64_t nd,
-                                 uint64_t* keys, uint32_t* fail_flags, uint32_t* fail_count, void* stream) {
+extern "C" int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, const uint32_t* aux, int64_t nq, int cap,
+                                 int K, int64_t nd, uint64_t* keys, uint32_t* fail_flags, uint32_t* fail_count,
+                                 void* stream) {
     CMH_REQUIRE(nq >= 0 && cap >= 1 && K >= 1 && nd >= 0, CMH_ERR_ARG, "cmh_topk_finalize: bad sizes");
+    CMH_REQUIRE(K <= FIN_MAX, CMH_ERR_UNSUPPORTED, "cmh_topk_finalize: K=%d > %d", K, FIN_MAX);
     if (nq == 0) return CMH_OK;
-    CMH_REQUIRE(cand && cnt && keys && fail_flags && fail_count, CMH_ERR_ARG, "cmh_topk_finalize: NULL pointer");
-    int p2 = 1;
-    while (p2 < cap) p2 <<= 1;
-    const size_t smem = (size_t)p2 * 8;
-    CMH_REQUIRE(smem <= 227 * 1024, CMH_ERR_UNSUPPORTED, "cmh_topk_finalize: cap=%d does not fit shared memory", cap);
+    CMH_REQUIRE(cand && cnt && aux && keys && fail_flags && fail_count, CMH_ERR_ARG, "cmh_topk_finalize: NULL pointer");
     CMH_REQUIRE(nq <= 0x7fffffffll, CMH_ERR_UNSUPPORTED, "cmh_topk_finalize: too many queries per call");
     cudaStream_t st = (cudaStream_t)stream;
     CMH_CUDA(cudaMemsetAsync(fail_count, 0, 4, st));
-    CMH_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_finalize_kernel<<<(unsigned)nq, 512, smem, st>>>(cand, cnt, cap, K, nd, keys, fail_flags, fail_count);
+    topk_finalize_kernel<<<(unsigned)nq, 512, 0, st>>>(cand, cnt, reinterpret_cast<const TcAux*>(aux), cap, K, nd, keys,
+                                                       fail_flags, fail_count);
     CMH_LAUNCH_CHECK("topk_finalize_kernel");
     return CMH_OK;
 }

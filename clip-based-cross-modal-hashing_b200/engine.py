@@ -340,22 +340,23 @@ def topk_merge(keys_in: torch.Tensor, K: int) -> torch.Tensor:
 # top-K on the tensor cores (tcgen05 / TMEM): sample histogram -> thresholds -> fused GEMM + candidate filter ->
 # per-query sort; queries whose candidate list came out short or overflowed are redone by the exact two-pass path
 # ---------------------------------------------------------------------------------------------------------------
-TC_DEFAULT_CAP = 16384
+TC_DEFAULT_CAP = 8192
+TC_MAX_K = 4096
 
 
-def tc_supported(q: PackedSet, d: PackedSet) -> bool:
-    return (q.valid is None and d.valid is None and q.bits == d.bits
+def tc_supported(q: PackedSet, d: PackedSet, K: int = 1) -> bool:
+    return (q.valid is None and d.valid is None and q.bits == d.bits and 1 <= int(K) <= TC_MAX_K
             and bool(_cabi.lib().cmh_tc_supported(q.bits, 0)))
 
 
 def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Optional[PackedSet] = None,
-            cap: int = TC_DEFAULT_CAP, stats: Optional[dict] = None) -> torch.Tensor:
+            cap: int = TC_DEFAULT_CAP, stats: Optional[dict] = None, tighten: bool = True) -> torch.Tensor:
     """int64 [nq, K] ascending keys, identical to ``RankPass(q, d).topk(K, index_base)``.
 
     ``sample``: a subset of the rows of ``d`` (any rows, contiguous in memory) used only to guess the per-query
     thresholds; None = use ``d`` itself (exact thresholds, an extra popc pass)."""
-    if not tc_supported(q, d):
-        raise ValueError("tensor-core top-K needs +-1 codes of 64 or 128 bits")
+    if not tc_supported(q, d, K):
+        raise ValueError("tensor-core top-K needs +-1 codes of 64 or 128 bits and K <= 4096")
     K = int(K)
     dev = q.device
     nq = q.n
@@ -370,14 +371,15 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     thr = torch.empty(nq, dtype=torch.int32, device=dev)
     cand = torch.empty((nq, cap), dtype=torch.int64, device=dev)
     cnt = torch.empty(nq, dtype=torch.int32, device=dev)
+    aux = torch.empty((nq, 8), dtype=torch.int32, device=dev)
     fail_flags = torch.empty(nq, dtype=torch.int32, device=dev)
     fail_count = torch.zeros(1, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         st = _stream(dev)
         check(L.cmh_topk_threshold(_ptr(h_all), nq, q.bits + 1, smp.n, d.n, K, _ptr(thr), st), "cmh_topk_threshold")
-        check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign), d.n, q.bits, int(index_base), _ptr(thr), cap,
-                               _ptr(cand), _ptr(cnt), st), "cmh_tc_collect")
-        check(L.cmh_topk_finalize(_ptr(cand), _ptr(cnt), nq, cap, K, d.n, _ptr(keys), _ptr(fail_flags),
+        check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign), d.n, q.bits, int(index_base), _ptr(thr),
+                               K if tighten else 0, cap, _ptr(cand), _ptr(cnt), _ptr(aux), st), "cmh_tc_collect")
+        check(L.cmh_topk_finalize(_ptr(cand), _ptr(cnt), _ptr(aux), nq, cap, K, d.n, _ptr(keys), _ptr(fail_flags),
                                   _ptr(fail_count), st), "cmh_topk_finalize")
     n_fail = int(fail_count.item())
     if stats is not None:

@@ -172,20 +172,24 @@ int cmh_topk_merge(const uint64_t* keys_in, int n_lists, int64_t nq, int K, uint
  * candidate filter fused as the epilogue.  Supported: +-1 codes (no valid plane) of 64 or 128 bits. */
 int cmh_tc_supported(int bits, int ternary);
 /* thr: device int32 [nq] - per-query upper bound of the K-th Hamming distance; every database row with
- * dist <= thr[q] is appended (in no particular order) to cand[q][0..cap) as key (2*dist << 32) | (index_base + row),
- * cnt[q] (device uint32 [nq], zeroed by the call) counts them and may exceed cap. */
+ * dist <= thr[q] (or <= a tighter bound derived while scanning when K > 0: once K rows at dist <= thr[q] - j are
+ * known, j <= 3) is appended, in no particular order, to cand[q][0..cap) as key (2*dist << 32) | (index_base + row).
+ * cnt[q] (device uint32 [nq]) counts them and may exceed cap; aux: device uint32 [nq][8] bookkeeping; both are
+ * zeroed by the call.  K = 0 keeps the thresholds fixed. */
 int cmh_tc_collect(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits,
-                   int64_t index_base, const int32_t* thr, int cap, uint64_t* cand, uint32_t* cnt, void* stream);
+                   int64_t index_base, const int32_t* thr, int K, int cap, uint64_t* cand, uint32_t* cnt,
+                   uint32_t* aux, void* stream);
 /* thr[q] from a histogram (cmh_eval_hist, binary mode, nb = bits + 1) over a SAMPLE of n_sample rows of an nd-row
  * shard: smallest bucket whose cumulative sample count reaches K*f + 6*sqrt(K*f) + 8 (f = n_sample / nd), exactly
  * min(K, nd) when n_sample == nd. */
 int cmh_topk_threshold(const uint32_t* hist, int64_t nq, int nb, int64_t n_sample, int64_t nd, int K,
                        int32_t* thr, void* stream);
-/* Sort each query's candidates by key and emit the K smallest (UINT64_MAX pads when nd < K).  fail_flags[q]
- * (device uint32 [nq]) = 1 and *fail_count (device uint32) incremented when cnt[q] > cap or cnt[q] < min(K, nd):
- * those queries must be re-run through cmh_topk (the exact two-pass path). */
-int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, int64_t nq, int cap, int K, int64_t nd,
-                      uint64_t* keys, uint32_t* fail_flags, uint32_t* fail_count, void* stream);
+/* Per query: K-th distance from the candidates' own histogram, sort of the candidates at or below it, K smallest
+ * keys out (UINT64_MAX pads when nd < K; K <= 4096).  fail_flags[q] (device uint32 [nq]) = 1 and *fail_count
+ * (device uint32) incremented when the candidate list overflowed, lost an entry, holds fewer than min(K, nd) rows or
+ * more than 4096 rows at or below the K-th distance: those queries must be re-run through cmh_topk (exact path). */
+int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, const uint32_t* aux, int64_t nq, int cap, int K,
+                      int64_t nd, uint64_t* keys, uint32_t* fail_flags, uint32_t* fail_count, void* stream);
 
 #ifdef __cplusplus
 }

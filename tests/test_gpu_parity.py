@@ -265,8 +265,11 @@ def test_tc_topk_matches_popc_path(dev, bits, nq, nd, K):
     want = engine.RankPass(q, db, need_labels=False).topk(K, 77)
     stats = {}
     got = engine.topk_tc(q, db, K, 77, stats=stats)
-    assert stats["n_fail"] == 0
     assert torch.equal(got, want)
+    # dense hits (K/D in the percent range) may overflow the lane-private staging and take the exact fallback;
+    # at retrieval-scale sparsity nothing should
+    if K * 1000 <= nd:
+        assert stats["n_fail"] == 0
 
 
 def test_tc_topk_against_oracle_and_fallback(dev):
