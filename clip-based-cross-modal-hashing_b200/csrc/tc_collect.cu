@@ -21,13 +21,33 @@
 
 #include "common.cuh"
 
+// Pipeline trace (debug builds only, -DCMH_TC_TRACE): CTA (0,0) records clock64() at the hand-offs of its first
+// TC_TRACE_ITERS iterations into the buffer registered with cmh_tc_set_trace: [role][iteration][event].
+#ifdef CMH_TC_TRACE
+#define TC_TRACE_ITERS 96
+#define TC_TRACE_EVENTS 8
+#define TC_TRACE(role, iter, ev)                                                                         \
+    do {                                                                                                 \
+        if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && (iter) < TC_TRACE_ITERS)                    \
+            a.trace[((role) * TC_TRACE_ITERS + (iter)) * TC_TRACE_EVENTS + (ev)] = clock64();            \
+    } while (0)
+#else
+#define TC_TRACE(role, iter, ev) do {} while (0)
+#endif
+
 namespace cmh {
 
-constexpr int TC_M = 128;
-constexpr int TC_N = 256;
+constexpr int TC_M = 128;       // queries per MMA (TMEM lanes)
+constexpr int TC_N = 256;       // database rows per shared-memory stage (two MMAs of TC_NM columns)
+constexpr int TC_NM = 128;      // database rows per MMA = TMEM columns per accumulator buffer
+constexpr int TC_BUFS = 4;      // accumulator buffers (4 x 128 columns = the whole TMEM)
+constexpr int TC_MMA_WARPS = 4;   // one MMA issuer (elected lane) per accumulator buffer
 constexpr int TC_PROD_WARPS = 4;
-constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = (1 + TC_PROD_WARPS + TC_EPI_WARPS) * 32;
+constexpr int TC_EPI_WARPS = 16;  // 4 groups of 4 warps; group g drains buffer g
+constexpr int TC_GROUPS = TC_EPI_WARPS / 4;
+constexpr int TC_THREADS = (TC_MMA_WARPS + TC_PROD_WARPS + TC_EPI_WARPS) * 32;
+constexpr int TC_RING = 8;        // packed database tiles in flight (bulk copies)
+constexpr int TC_MAX_CHUNKS = 1024;  // candidate segments per query (cmh_topk_finalize walks them)
 constexpr int TC_MAX_T = 4;
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------------------
@@ -71,6 +91,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// 64 consecutive columns, two per register: column 2i in the low half of v[i], column 2i+1 in the high half (the
+// int32 accumulators are small - |dot| <= bits <= 128 - so their low 16 bits are the exact int16 value)
+__device__ __forceinline__ void tmem_ld64p(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor, version 1):
@@ -89,24 +123,28 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// 16 bits -> 16 bytes of +-1 (bit set -> +1 = 0x01, clear -> -1 = 0xFF) through the nibble LUT
-__device__ __forceinline__ uint4 expand16(uint32_t bits16, const uint32_t* __restrict__ lut) {
+// 4 bits -> 4 bytes of +-1 (bit set -> +1 = 0x01, clear -> -1 = 0xFF), ALU only: the multiply spreads bit j to bit 8j
+// (the four shifted copies of a nibble do not overlap, so the product is their OR), and 0xFF - 0xFE * {0,1} per byte
+// never borrows.
+__device__ __forceinline__ uint32_t expand4(uint32_t nib) {
+    const uint32_t x = (nib * 0x00204081u) & 0x01010101u;
+    return 0xFFFFFFFFu - x * 0xFEu;
+}
+__device__ __forceinline__ uint4 expand16(uint32_t bits16) {
     uint4 o;
-    o.x = lut[bits16 & 15u];
-    o.y = lut[(bits16 >> 4) & 15u];
-    o.z = lut[(bits16 >> 8) & 15u];
-    o.w = lut[(bits16 >> 12) & 15u];
+    o.x = expand4(bits16 & 15u);
+    o.y = expand4((bits16 >> 4) & 15u);
+    o.z = expand4((bits16 >> 8) & 15u);
+    o.w = expand4(bits16 >> 12);
     return o;
 }
 
-constexpr int TC_SLOTS = 8;        // staged hits per epilogue LANE (private slots: the hit path has no atomics)
-constexpr int TC_FLUSH_AT = 4;     // a warp flushes once any of its lanes holds this many staged hits
-constexpr int TC_REFRESH = 128;    // tile iterations between threshold refreshes
+constexpr int TC_REFRESH = 32;     // tiles (per epilogue group) between threshold refreshes
 
 // per-query bookkeeping shared by every CTA working on the query (global memory, zeroed by cmh_tc_collect)
 struct TcAux {
-    uint32_t cum_le[4];   // candidates found so far with dist <= thr0 - j   (j = 0..3)
-    uint32_t force_fail;  // a staging buffer overflowed: a candidate may have been dropped
+    uint32_t h[4];        // candidates seen so far at dist == thr0 - j (j = 0, 1, 2) and at dist <= thr0 - 3 (j = 3)
+    uint32_t force_fail;  // a candidate segment overflowed: entries were dropped
     uint32_t pad[3];
 };
 
@@ -114,35 +152,36 @@ struct TcArgs {
     const uint64_t* q;      // [nq][words]
     const uint64_t* d;      // [nd][words]
     const int32_t* thr;     // [nq] initial threshold bucket thr0 (Hamming distance): rows with dist <= thr qualify
-    uint64_t* cand;         // [nq][cap]
-    uint32_t* cnt;          // [nq] candidates found (may exceed cap)
+    uint64_t* cand;         // [nq][n_chunks][seg_cap]  one private candidate segment per (query, database chunk)
+    uint32_t* cnt;          // [n_chunks][nq]           candidates the chunk's CTA found (may exceed seg_cap)
     TcAux* aux;             // [nq]
     int64_t nq, nd, index_base;
     int chunk_rows;         // database rows per CTA (multiple of TC_N)
-    int cap, bits;
+    int n_chunks, seg_cap, bits;
     int K;                  // > 0: tighten thresholds while scanning (once K rows at dist <= thr0 - j are known)
+    long long* trace;       // CMH_TC_TRACE builds only
+    int probe;              // measurement aid (cmh_tc_probe): 1 = no tcgen05.mma, 2 = no TMEM drain, 4 = drain without scan
 };
 
-__device__ __forceinline__ int max8(const int* v) {
-    int m = __vimax3_s32(v[0], v[1], v[2]);
-    int n = __vimax3_s32(v[3], v[4], v[5]);
-    return __vimax3_s32(m, n, max(v[6], v[7]));
+// per-half maximum of 8 registers of packed int16 pairs (VIMNMX3.S16x2)
+__device__ __forceinline__ uint32_t max8p(const uint32_t* v) {
+    const uint32_t m = __vimax3_s16x2(v[0], v[1], v[2]);
+    const uint32_t n = __vimax3_s16x2(v[3], v[4], v[5]);
+    return __vimax3_s16x2(m, n, __vmaxs2(v[6], v[7]));
 }
 
-// Out of line on purpose: one copy of the append code keeps the epilogue's instruction footprint small (an inlined,
-// fully unrolled hit path was ~160 KB of SASS and every rare hit paid a chain of instruction-cache misses).
-__device__ __noinline__ int tc_stage_hit(uint64_t* my_key, unsigned char* my_t, int n_staged, uint64_t key, int t,
-                                         uint32_t* force_fail) {
-    if (n_staged < TC_SLOTS) {
-        my_key[n_staged * 32] = key;
-        my_t[n_staged * 32] = (unsigned char)t;
-        return n_staged + 1;
-    }
-    *force_fail = 1u;
-    return n_staged;
+// The hit path.  Out of line on purpose: one copy of the append keeps the epilogue's instruction footprint small (an
+// inlined, fully unrolled hit path was ~160 KB of SASS and every rare hit paid a chain of instruction-cache misses).
+// The slot comes from a shared-memory counter (the segment is private to this CTA), the key goes straight to global
+// memory and the tightening statistics are a fire-and-forget RED: nothing on this path waits for global memory.
+__device__ __noinline__ void tc_append(uint64_t* seg, uint32_t* pos_ctr, uint32_t seg_cap, uint32_t* h, int slack,
+                                       uint32_t key_hi, uint32_t key_lo) {
+    const uint32_t pos = atomicAdd(pos_ctr, 1u);
+    if (pos < seg_cap) seg[pos] = ((uint64_t)key_hi << 32) | key_lo;
+    if (h != nullptr) atomicAdd(h + min(slack, 3), 1u);
 }
 
-// smem: [A: T tiles][B: STAGES tiles][lut 64 B][barriers][tmem slot][staging][thresholds]
+// smem: [A: T tiles][B: STAGES tiles][packed ring][barriers][tmem slot][thr][thr0][pos]
 template <int WORDS, int T, int TC_STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs a) {
     constexpr int KBYTES = WORDS * 64;           // int8 elements (= bytes) per row
@@ -153,17 +192,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;
     unsigned char* sB = smem + T * A_TILE;
-    uint32_t* lut = reinterpret_cast<uint32_t*>(sB + TC_STAGES * B_TILE);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lut + 16);
+    uint64_t* ring = reinterpret_cast<uint64_t*>(sB + TC_STAGES * B_TILE);   // [TC_RING][256 rows][WORDS] packed words
+    uint64_t* bars = ring + TC_RING * TC_N * WORDS;
     uint64_t* b_full = bars;                     // [STAGES] producers -> MMA
     uint64_t* b_empty = bars + TC_STAGES;        // [STAGES] MMA -> producers
-    uint64_t* t_full = bars + 2 * TC_STAGES;     // [2] MMA -> epilogue
-    uint64_t* t_empty = bars + 2 * TC_STAGES + 2;  // [2] epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
-    // staged hits: [EPI_WARPS][SLOTS][32 lanes] (slot-major, lane fastest: conflict-free), 8-byte aligned
-    uint64_t* stg_key = reinterpret_cast<uint64_t*>(tmem_slot + 2);
-    unsigned char* stg_t = reinterpret_cast<unsigned char*>(stg_key + TC_EPI_WARPS * TC_SLOTS * 32);
-    int* s_thr = reinterpret_cast<int*>(stg_t + TC_EPI_WARPS * TC_SLOTS * 32);    // [T][128] current dot thresholds
+    uint64_t* t_full = bars + 2 * TC_STAGES;               // [BUFS] MMA -> epilogue group
+    uint64_t* t_empty = bars + 2 * TC_STAGES + TC_BUFS;    // [BUFS] epilogue group -> MMA
+    uint64_t* r_full = bars + 2 * TC_STAGES + 2 * TC_BUFS;               // [RING] bulk copy -> producers
+    uint64_t* r_empty = bars + 2 * TC_STAGES + 2 * TC_BUFS + TC_RING;    // [RING] producers -> bulk copy issuer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2 * TC_BUFS + 2 * TC_RING);
+    int* s_thr = reinterpret_cast<int*>(tmem_slot + 2);    // [T][128] current dot-product thresholds
+    int* s_thr0 = s_thr + T * TC_M;                        // [T][128] dot-product threshold of thr0
+    uint32_t* s_pos = reinterpret_cast<uint32_t*>(s_thr0 + T * TC_M);   // [T][128] entries appended by this CTA
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t q0 = (int64_t)blockIdx.x * (T * TC_M);
@@ -172,22 +212,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
     const int n_tiles = (int)((c_end - c_begin + TC_N - 1) / TC_N);
 
     // ---- prologue -----------------------------------------------------------------------------------------------
-    if (tid < 16) {
-        uint32_t w = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) w |= (((tid >> i) & 1) ? 0x01u : 0xFFu) << (8 * i);
-        lut[tid] = w;
-    }
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(&b_full[s], TC_PROD_WARPS * 32);
-            mbar_init(&b_empty[s], 1);
+            mbar_init(&b_empty[s], TC_MMA_WARPS);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < TC_BUFS; ++b) {
             mbar_init(&t_full[b], 1);
-            mbar_init(&t_empty[b], TC_EPI_WARPS * 32);
+            mbar_init(&t_empty[b], 128);         // the 4 warps that drain one accumulator tile
+        }
+        for (int r = 0; r < TC_RING; ++r) {
+            mbar_init(&r_full[r], 1);
+            mbar_init(&r_empty[r], TC_PROD_WARPS * 32);
         }
         mbar_fence_init();
+    }
+    // dist <= thr  <=>  dot = bits - 2 dist >= bits - 2 thr ; padding queries never fire (int16 max)
+    for (int e = tid; e < T * TC_M; e += TC_THREADS) {
+        const int64_t q = q0 + e;
+        const int v = q < a.nq ? a.bits - 2 * a.thr[q] : 0x7fff;
+        s_thr[e] = v;
+        s_thr0[e] = v;
+        s_pos[e] = 0u;
     }
     __syncthreads();
     // A operand: T x 128 query rows, expanded by everyone (rows beyond nq are all -1; their threshold never fires)
@@ -198,7 +244,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
         const int64_t q = q0 + t * TC_M + r;
         const uint64_t word = q < a.nq ? a.q[q * WORDS + (c >> 2)] : 0ull;
         const uint32_t b16 = (uint32_t)(word >> (16 * (c & 3))) & 0xffffu;
-        *reinterpret_cast<uint4*>(sA + t * A_TILE + c * (TC_M * 16) + r * 16) = expand16(b16, lut);
+        *reinterpret_cast<uint4*>(sA + t * A_TILE + c * (TC_M * 16) + r * 16) = expand16(b16);
     }
     fence_proxy_async_smem();
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -207,174 +253,222 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // ================= MMA issuer =================
+    if (warp < TC_MMA_WARPS) {
+        // ================= MMA issuers =================
+        // Issuer w owns accumulator buffer w: tiles w, w + 4, ...  One thread doing wait -> tcgen05.mma -> commit for
+        // every tile spends ~300 cycles per tile on instruction latency alone (measured), more than the 128 cycles
+        // the tensor pipe needs for it; four issuers overlap that latency.
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_i8(TC_M, TC_N);
+            constexpr uint32_t idesc = umma_idesc_i8(TC_M, TC_NM);
             const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
-            int it = 0;
-            for (int i = 0; i < n_tiles; ++i) {
+            const bool no_mma = (a.probe & 1) != 0;
+            const int n_iters = n_tiles * T * 2;     // iteration = (stage i, query tile t, row half h)
+            const uint32_t d_tmem = tmem_base + warp * TC_NM;
+            int round = 0;
+#pragma unroll 1
+            for (int it = warp; it < n_iters; it += TC_MMA_WARPS, ++round) {
+                const int i = it / (2 * T), rem = it - i * (2 * T);
+                const int t = rem >> 1, h = rem & 1;
                 const int s = i % TC_STAGES;
-                mbar_wait(&b_full[s], (i / TC_STAGES) & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int t = 0; t < T; ++t, ++it) {
-                    const int buf = it & 1;
-                    mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);
+                TC_TRACE(0, it, 3);
+                if (rem < TC_MMA_WARPS) {            // this issuer's first tile of the stage
+                    mbar_wait(&b_full[s], (i / TC_STAGES) & 1);
                     tc_fence_after();
+                }
+                TC_TRACE(0, it, 0);
+                mbar_wait(&t_empty[warp], (round & 1) ^ 1);
+                tc_fence_after();
+                TC_TRACE(0, it, 1);
+                if (!no_mma) {
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k) {
                         const uint64_t ad = umma_desc(a_addr + t * A_TILE + k * 2 * (TC_M * 16), TC_M * 16, 128);
-                        const uint64_t bd = umma_desc(b_addr + s * B_TILE + k * 2 * (TC_N * 16), TC_N * 16, 128);
-                        umma_i8(tmem_base + buf * TC_N, ad, bd, idesc, k > 0 ? 1u : 0u);
+                        const uint64_t bd = umma_desc(b_addr + s * B_TILE + k * 2 * (TC_N * 16) + h * (TC_NM * 16),
+                                                      TC_N * 16, 128);
+                        umma_i8(d_tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
                     }
-                    umma_commit(&t_full[buf]);
                 }
-                umma_commit(&b_empty[s]);
+                umma_commit(&t_full[warp]);
+                if (rem >= 2 * T - TC_MMA_WARPS) umma_commit(&b_empty[s]);   // ... and its last one
+                TC_TRACE(0, it, 2);
             }
         }
-    } else if (warp <= TC_PROD_WARPS) {
+    } else if (warp < TC_MMA_WARPS + TC_PROD_WARPS) {
         // ================= producers: packed bits -> +-1 int8 core matrices =================
-        const int pt = tid - 32;                 // 0..127
-        uint64_t w[2][WORDS];
-        auto fetch = [&](int i) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int64_t row = c_begin + (int64_t)i * TC_N + h * 128 + pt;
-#pragma unroll
-                for (int x = 0; x < WORDS; ++x) w[h][x] = row < c_end ? __ldg(a.d + row * WORDS + x) : 0ull;
+        // The packed words of a tile (256 rows, 2-4 KB) are staged in a TC_RING-deep shared-memory ring by the bulk-copy
+        // engine (cp.async.bulk, issued by one thread, completion on an mbarrier).  The producer threads must not have
+        // global loads of their own in flight: fence.proxy.async is a MEMBAR that waits for them, which bounded the
+        // kernel by one tile per global-memory round trip.  Tiles the engine cannot take (a ragged last tile, a shard
+        // view that is not 16-byte aligned) are read with plain loads.
+        const int pt = tid - TC_MMA_WARPS * 32;  // 0..127
+        const bool aligned = (reinterpret_cast<uintptr_t>(a.d) & 15) == 0;
+        auto bulk_tile = [&](int i) { return aligned && c_begin + (int64_t)(i + 1) * TC_N <= c_end; };
+        auto issue = [&](int i) {                // pt == 0
+            if (i >= n_tiles) return;
+            const int slot = i % TC_RING;
+            if (bulk_tile(i)) {
+                mbar_expect_tx(&r_full[slot], TC_N * WORDS * 8);
+                bulk_g2s(ring + slot * (TC_N * WORDS), a.d + (c_begin + (int64_t)i * TC_N) * WORDS, TC_N * WORDS * 8,
+                         &r_full[slot]);
+            } else {
+                mbar_arrive(&r_full[slot]);
             }
         };
-        if (n_tiles > 0) fetch(0);
+        if (pt == 0)
+            for (int j = 0; j < TC_RING; ++j) issue(j);
         for (int i = 0; i < n_tiles; ++i) {
-            const int s = i % TC_STAGES;
+            const int s = i % TC_STAGES, slot = i % TC_RING;
             uint64_t cur[2][WORDS];
+            if (pt == 0) TC_TRACE(1, i, 0);
+            mbar_wait(&r_full[slot], (i / TC_RING) & 1);
+            if (pt == 0) TC_TRACE(1, i, 1);
+            if (bulk_tile(i)) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int x = 0; x < WORDS; ++x) cur[h][x] = w[h][x];
-            if (i + 1 < n_tiles) fetch(i + 1);   // next tile's words are in flight while this one is expanded
+                    for (int x = 0; x < WORDS; ++x) cur[h][x] = ring[slot * (TC_N * WORDS) + (h * 128 + pt) * WORDS + x];
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int64_t row = c_begin + (int64_t)i * TC_N + h * 128 + pt;
+#pragma unroll
+                    for (int x = 0; x < WORDS; ++x) cur[h][x] = row < c_end ? __ldg(a.d + row * WORDS + x) : 0ull;
+                }
+            }
+            mbar_arrive(&r_empty[slot]);
+            if (pt == 0) {
+                mbar_wait(&r_empty[slot], (i / TC_RING) & 1);
+                issue(i + TC_RING);              // refill the slot everyone has just read
+            }
+            if (pt == 0) TC_TRACE(1, i, 2);
             mbar_wait(&b_empty[s], ((i / TC_STAGES) & 1) ^ 1);
+            if (pt == 0) TC_TRACE(1, i, 3);
             unsigned char* dst = sB + s * B_TILE;
+            // rows past the end of the chunk are expanded like any other (as all -1): the hit path checks the row
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int r = h * 128 + pt;
-                const bool live = c_begin + (int64_t)i * TC_N + r < c_end;
 #pragma unroll
                 for (int c = 0; c < CHUNKS; ++c) {
                     const uint32_t b16 = (uint32_t)(cur[h][c >> 2] >> (16 * (c & 3))) & 0xffffu;
-                    const uint4 e = live ? expand16(b16, lut) : make_uint4(0u, 0u, 0u, 0u);
-                    *reinterpret_cast<uint4*>(dst + c * (TC_N * 16) + r * 16) = e;
+                    *reinterpret_cast<uint4*>(dst + c * (TC_N * 16) + r * 16) = expand16(b16);
                 }
             }
+            if (pt == 0) TC_TRACE(1, i, 4);
             fence_proxy_async_smem();            // generic-proxy stores -> visible to the tensor core (async proxy)
+            if (pt == 0) TC_TRACE(1, i, 5);
             mbar_arrive(&b_full[s]);
+            if (pt == 0) TC_TRACE(1, i, 6);
         }
     } else {
         // ================= epilogue: threshold filter on the dot products =================
-        const int ew = warp - (1 + TC_PROD_WARPS);       // 0..7
+        const int ew = warp - (TC_MMA_WARPS + TC_PROD_WARPS);   // 0 .. TC_EPI_WARPS-1
+        const int grp = ew >> 2;                          // group of 4 warps (one per TMEM lane quarter)
         const int quarter = warp & 3;                     // TMEM lanes this warp may touch: 32 * (warp % 4)
-        const int col_half = ew >> 2;                     // columns [0,128) or [128,256)
         const int qrow = quarter * 32 + lane;             // query row inside the 128-row tile
-        uint64_t* my_key = stg_key + ew * (TC_SLOTS * 32) + lane;      // slot s at my_key[s * 32]
-        unsigned char* my_t = stg_t + ew * (TC_SLOTS * 32) + lane;
-        int n_staged = 0;                                              // this lane's staged hits
-        // dist <= thr  <=>  dot = bits - 2 dist >= bits - 2 thr ; padding queries never fire.  Both column halves
-        // own the same (t, qrow) entries and write identical values.
-        for (int t = 0; t < T; ++t) {
-            const int64_t q = q0 + t * TC_M + qrow;
-            s_thr[t * TC_M + qrow] = q < a.nq ? a.bits - 2 * a.thr[q] : 0x7fffffff;
-        }
-        __syncwarp();
-        // staged hits -> global candidate lists.  Every lane drains its own slots, so the 32 returning atomics of a
-        // trip are in flight together and their latency is paid once per flush instead of once per hit.
-        auto flush = [&](int at_least) {
-            if (__any_sync(0xffffffffu, n_staged >= at_least)) {
-                for (int e = 0; e < n_staged; ++e) {
-                    const uint64_t key = my_key[e * 32];
-                    const int64_t q = q0 + (int)my_t[e * 32] * TC_M + qrow;
-                    const uint32_t pos = atomicAdd(&a.cnt[q], 1u);
-                    if (pos < (uint32_t)a.cap) a.cand[q * a.cap + pos] = key;
-                    if (a.K > 0) {
-                        const int slack = a.thr[q] - (int)((uint32_t)(key >> 32) >> 1);   // thr0 - dist >= 0
+        const bool no_drain = (a.probe & 2) != 0, no_scan = (a.probe & 4) != 0;
+        // Rare: at least one of the 64 dot products in x reaches the threshold.  Two-level search (4 block maxima,
+        // then the 8 registers of a block), both halves of a register by a rolled loop: 32 call sites in all.
+        auto collect64 = [&](const uint32_t (&x)[32], const uint32_t (&mb)[4], int thr, uint32_t thr2m, int t,
+                             int64_t row0) {
+            const int e = t * TC_M + qrow;
+            const int64_t q = q0 + e;
+            uint64_t* seg = a.cand + ((uint64_t)q * a.n_chunks + blockIdx.y) * (uint64_t)a.seg_cap;
+            uint32_t* h = a.K > 0 ? a.aux[q].h : nullptr;
+            const int dthr0 = s_thr0[e];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (slack >= j) atomicAdd(&a.aux[q].cum_le[j], 1u);
-                    }
-                }
-                n_staged = 0;
-            }
-        };
-        // 32 dot products of this lane's query: block maxima (ILP 4), one compare; the hit path is rare
-        auto scan32 = [&](const int (&x)[32], int thr, int t, int64_t row0) {
-            int mb[4];
+            for (int b = 0; b < 4; ++b) {
+                if (__vmaxs2(mb[b], thr2m) == thr2m) continue;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) mb[b] = max8(x + 8 * b);
-            const int m = __vimax3_s32(mb[0], mb[1], max(mb[2], mb[3]));
-            if (m >= thr) {
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    if (mb[b] >= thr) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int val = x[8 * b + j];
-                            const int64_t row = row0 + 8 * b + j;
-                            if (val >= thr && row < c_end)
-                                n_staged = tc_stage_hit(my_key, my_t, n_staged,
-                                                        ((uint64_t)(uint32_t)(a.bits - val) << 32) |
-                                                            (uint64_t)(a.index_base + row),
-                                                        t, &a.aux[q0 + t * TC_M + qrow].force_fail);
-                        }
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t w = x[8 * b + j];
+                    if (__vmaxs2(w, thr2m) == thr2m) continue;
+#pragma unroll 1
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int val = hh ? ((int)w >> 16) : ((int)(w << 16) >> 16);
+                        const int64_t row = row0 + 16 * b + 2 * j + hh;
+                        if (val >= thr && row < c_end)
+                            tc_append(seg, &s_pos[e], (uint32_t)a.seg_cap, h, (val - dthr0) >> 1,
+                                      (uint32_t)(a.bits - val), (uint32_t)(a.index_base + row));
                     }
                 }
             }
         };
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + col_half * 128;
-        int it = 0;
-        for (int i = 0; i < n_tiles; ++i) {
-            const int64_t tile_row0 = c_begin + (int64_t)i * TC_N + col_half * 128;
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const int n_iters = n_tiles * T * 2;
+        int round = 0;
 #pragma unroll 1
-            for (int t = 0; t < T; ++t, ++it) {
-                const int buf = it & 1;
-                mbar_wait(&t_full[buf], (it >> 1) & 1);
-                tc_fence_after();
-                const int thr = s_thr[t * TC_M + qrow];
-                const uint32_t taddr = lane_addr + buf * TC_N;
-                int v0[32], v1[32];
-                tmem_ld32(taddr, v0);
-#pragma unroll 1
-                for (int gp = 0; gp < 2; ++gp) {      // rolled: two static scan sites in the whole epilogue
-                    tmem_ld_wait();
-                    tmem_ld32(taddr + (2 * gp + 1) * 32, v1);          // in flight while v0 is scanned
-                    scan32(v0, thr, t, tile_row0 + (2 * gp) * 32);
-                    tmem_ld_wait();
-                    if (gp == 0) tmem_ld32(taddr + 64, v0);
-                    scan32(v1, thr, t, tile_row0 + (2 * gp + 1) * 32);
-                }
+        for (int it = grp; it < n_iters; it += TC_GROUPS, ++round) {
+            const int i = it / (2 * T), rem = it - i * (2 * T);
+            const int t = rem >> 1, h = rem & 1;
+            const int buf = it & (TC_BUFS - 1);
+            const int64_t row0 = c_begin + (int64_t)i * TC_N + h * TC_NM;
+            if (qrow == 0) TC_TRACE(2 + grp, round, 0);
+            mbar_wait(&t_full[buf], (it / TC_BUFS) & 1);
+            tc_fence_after();
+            if (qrow == 0) TC_TRACE(2 + grp, round, 1);
+            const int thr = s_thr[t * TC_M + qrow];
+            const uint32_t thr2m = (uint32_t)((thr - 1) & 0xffff) * 0x10001u;   // "any half > thr - 1"
+            const uint32_t taddr = lane_taddr + buf * TC_NM;
+            if (no_drain) {
                 tc_fence_before();
                 mbar_arrive(&t_empty[buf]);
-                flush(TC_FLUSH_AT);
-                if (a.K > 0 && (it & (TC_REFRESH - 1)) == TC_REFRESH - 1) {
-                    // tighten: once K rows at dist <= thr0 - j are known, nothing beyond that bucket can be in the top K
-                    for (int u = 0; u < T; ++u) {
-                        const int64_t q = q0 + u * TC_M + qrow;
-                        if (q < a.nq) {
-                            const uint4 c = __ldcg(reinterpret_cast<const uint4*>(a.aux[q].cum_le));
-                            const uint32_t K = (uint32_t)a.K;
-                            const int j = c.w >= K ? 3 : (c.z >= K ? 2 : (c.y >= K ? 1 : 0));
-                            s_thr[u * TC_M + qrow] = a.bits - 2 * (a.thr[q] - j);
-                        }
-                    }
-                    __syncwarp();
+                if (qrow == 0) TC_TRACE(2 + grp, round, 4);
+                continue;
+            }
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {       // rolled: one scan site (and one hit path) in the kernel
+                uint32_t v[32];
+                tmem_ld64p(taddr + half * 64, v);
+                tmem_ld_wait();
+                if (qrow == 0) TC_TRACE(2 + grp, round, 2 + half);
+                if (half == 1) {
+                    tc_fence_before();
+                    mbar_arrive(&t_empty[buf]);          // the values are in registers: the tile can be overwritten
                 }
+                if (no_scan) {
+                    uint32_t o = 0;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) o |= v[r];
+                    if (o == 0xdeadbeefu) s_pos[0] = o;  // keep the loads alive
+                    continue;
+                }
+                uint32_t mb[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) mb[b] = max8p(v + 8 * b);
+                const uint32_t m = __vimax3_s16x2(mb[0], mb[1], __vmaxs2(mb[2], mb[3]));
+                if (__vmaxs2(m, thr2m) != thr2m) collect64(v, mb, thr, thr2m, t, row0 + half * 64);
+            }
+            if (qrow == 0) TC_TRACE(2 + grp, round, 4);
+            if (a.K > 0 && (round & (TC_REFRESH - 1)) == TC_REFRESH - 1) {
+                // tighten: once K rows at dist <= thr0 - j are known, nothing beyond that bucket can be in the top K
+                for (int u = 0; u < T; ++u) {
+                    const int e = u * TC_M + qrow;
+                    const int64_t q = q0 + e;
+                    if (q < a.nq) {
+                        const uint4 c = __ldcg(reinterpret_cast<const uint4*>(a.aux[q].h));
+                        const uint32_t K = (uint32_t)a.K;
+                        const uint32_t c3 = c.w, c2 = c3 + c.z, c1 = c2 + c.y;
+                        const int j = c3 >= K ? 3 : (c2 >= K ? 2 : (c1 >= K ? 1 : 0));
+                        s_thr[e] = s_thr0[e] + 2 * j;   // the four groups store the same or a newer (tighter) value
+                    }
+                }
+                __syncwarp();
             }
         }
-        flush(1);
     }
     // ---- teardown -----------------------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 512);
+    for (int e = tid; e < T * TC_M; e += TC_THREADS) {
+        const int64_t q = q0 + e;
+        if (q < a.nq) {
+            const uint32_t n = s_pos[e];
+            a.cnt[(int64_t)blockIdx.y * a.nq + q] = n;
+            if (n > (uint32_t)a.seg_cap) a.aux[q].force_fail = 1u;
+        }
+    }
 }
 
 // ---- threshold from a sample histogram -------------------------------------------------------------------------------
@@ -399,32 +493,43 @@ __global__ void __launch_bounds__(256) topk_threshold_kernel(const uint32_t* __r
 // One CTA per query.  Every database row at or below the query's final threshold was collected, and that threshold
 // is an upper bound of the K-th distance, so the smallest bucket T whose cumulative candidate count reaches K is the
 // true K-th distance; only candidates with dist <= T (between K and a few K of them) are sorted - by key, i.e. by
-// (distance, global index), which is the stable ranking.
+// (distance, global index), which is the stable ranking.  A warp walks one (query, chunk) segment at a time.
 constexpr int FIN_MAX = 4096;
 constexpr int FIN_BINS = 129;   // bits <= 128 on the tensor path
+constexpr int FIN_THREADS = 512;
 
-__global__ void __launch_bounds__(512) topk_finalize_kernel(const uint64_t* __restrict__ cand,
-                                                            const uint32_t* __restrict__ cnt,
-                                                            const TcAux* __restrict__ aux, int cap, int K, int64_t nd,
-                                                            uint64_t* __restrict__ keys,
-                                                            uint32_t* __restrict__ fail_flags,
-                                                            uint32_t* __restrict__ fail_count) {
+__global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64_t* __restrict__ cand,
+                                                                    const uint32_t* __restrict__ cnt,
+                                                                    const TcAux* __restrict__ aux, int64_t nq,
+                                                                    int n_chunks, int seg_cap, int K, int64_t nd,
+                                                                    uint64_t* __restrict__ keys,
+                                                                    uint32_t* __restrict__ fail_flags,
+                                                                    uint32_t* __restrict__ fail_count) {
     __shared__ uint64_t sk[FIN_MAX];
     __shared__ uint32_t hist[FIN_BINS];
     __shared__ int s_T, s_keep;
-    __shared__ uint32_t s_n;
+    __shared__ uint32_t s_n, s_total, s_over;
     const int64_t q = blockIdx.x;
-    const uint32_t n_found = cnt[q];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = FIN_THREADS / 32;
     const int64_t need = nd < (int64_t)K ? nd : (int64_t)K;
-    bool fail = n_found > (uint32_t)cap || (int64_t)n_found < need || aux[q].force_fail != 0u;
-    const int n = (int)n_found;
-    const uint64_t* __restrict__ mine = cand + q * cap;
+    const uint64_t* __restrict__ mine = cand + (uint64_t)q * n_chunks * (uint64_t)seg_cap;
+    for (int i = threadIdx.x; i < FIN_BINS; i += blockDim.x) hist[i] = 0u;
+    if (threadIdx.x == 0) { s_n = 0u; s_total = 0u; s_over = 0u; }
+    __syncthreads();
+    for (int c = warp; c < n_chunks; c += NW) {
+        uint32_t n = cnt[(int64_t)c * nq + q];
+        if (lane == 0) {
+            atomicAdd(&s_total, n);
+            if (n > (uint32_t)seg_cap) s_over = 1u;
+        }
+        n = min(n, (uint32_t)seg_cap);
+        const uint64_t* seg = mine + (uint64_t)c * seg_cap;
+        for (uint32_t i = lane; i < n; i += 32) atomicAdd(&hist[(uint32_t)(seg[i] >> 33)], 1u);
+    }
+    __syncthreads();
+    bool fail = s_over != 0u || (int64_t)s_total < need || aux[q].force_fail != 0u;
     if (!fail) {
-        for (int i = threadIdx.x; i < FIN_BINS; i += blockDim.x) hist[i] = 0u;
-        if (threadIdx.x == 0) s_n = 0u;
-        __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[(uint32_t)(mine[i] >> 33)], 1u);
-        __syncthreads();
         if (threadIdx.x == 0) {
             int64_t cum = 0;
             int T = -1;
@@ -444,9 +549,13 @@ __global__ void __launch_bounds__(512) topk_finalize_kernel(const uint64_t* __re
         return;
     }
     const int T = s_T, keep = s_keep;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint64_t key = mine[i];
-        if ((int)(uint32_t)(key >> 33) <= T) sk[atomicAdd(&s_n, 1u)] = key;
+    for (int c = warp; c < n_chunks; c += NW) {
+        const uint32_t n = cnt[(int64_t)c * nq + q];     // <= seg_cap (checked above)
+        const uint64_t* seg = mine + (uint64_t)c * seg_cap;
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint64_t key = seg[i];
+            if ((int)(uint32_t)(key >> 33) <= T) sk[atomicAdd(&s_n, 1u)] = key;
+        }
     }
     int p2 = 1;
     while (p2 < keep) p2 <<= 1;
@@ -473,58 +582,94 @@ __global__ void __launch_bounds__(512) topk_finalize_kernel(const uint64_t* __re
 
 using namespace cmh;
 
-// B-ring depth: 6 stages for 64-bit codes (128 KB of shared memory per CTA, so exactly one CTA - which owns the whole
-// TMEM - is resident per SM), 4 for 128-bit codes (192 KB).
-static int tc_stages(int words) { return words == 1 ? 6 : 4; }
+// B-ring depth: 6 stages for 64-bit codes (>114 KB of shared memory per CTA, so exactly one CTA - which owns the whole
+// TMEM - is resident per SM), 3 for 128-bit codes (64 KB of A + 96 KB of B).
+static int tc_stages(int words) { return words == 1 ? 6 : 3; }
 static size_t tc_smem_bytes(int words, int T) {
     const int st = tc_stages(words);
-    return (size_t)T * TC_M * words * 64 + (size_t)st * TC_N * words * 64 + 64 + (2 * st + 4) * 8 + 8 +
-           (size_t)TC_EPI_WARPS * TC_SLOTS * 32 * 9 + (size_t)T * TC_M * 4 + 16;
+    return (size_t)T * TC_M * words * 64 + (size_t)st * TC_N * words * 64 + 64 + (2 * st + 2 * TC_BUFS + 2 * TC_RING) * 8 + 8 +
+           (size_t)3 * T * TC_M * 4 + (size_t)TC_RING * 2 * words * 128 * 8 + 16;
 }
 
 extern "C" int cmh_tc_supported(int bits, int ternary) {
     return (!ternary && (bits == 64 || bits == 128)) ? 1 : 0;
 }
 
-extern "C" int cmh_tc_collect(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits,
-                              int64_t index_base, const int32_t* thr, int K, int cap, uint64_t* cand, uint32_t* cnt,
-                              uint32_t* aux, void* stream) {
+// launch geometry: query groups of TC_MAX_T x 128 rows, database chunks of whole tiles, ~4 CTAs per SM over the launch
+static void tc_geometry(int64_t nq, int64_t nd, int64_t* n_qgroups, int64_t* n_chunks, int64_t* chunk_rows) {
+    *n_qgroups = std::max<int64_t>(1, ceil_div(nq, (int64_t)TC_MAX_T * TC_M));
+    int64_t want = std::max<int64_t>(1, ceil_div((int64_t)sm_count() * 4, *n_qgroups));
+    want = std::min<int64_t>(want, TC_MAX_CHUNKS);
+    int64_t rows = round_up(std::max<int64_t>(1, ceil_div(nd, want)), TC_N);
+    rows = std::max<int64_t>(rows, 16 * TC_N);
+    *chunk_rows = rows;
+    *n_chunks = std::max<int64_t>(1, ceil_div(nd, rows));
+}
+
+static long long* g_tc_trace = nullptr;
+#ifdef CMH_TC_TRACE
+extern "C" int cmh_tc_set_trace(void* device_buffer) { g_tc_trace = (long long*)device_buffer; return CMH_OK; }
+#endif
+
+extern "C" int cmh_tc_plan(int64_t nq, int64_t nd, int bits, int* n_chunks) {
+    CMH_REQUIRE(cmh_tc_supported(bits, 0), CMH_ERR_UNSUPPORTED, "cmh_tc_plan: bits=%d (64 or 128, +-1 codes only)", bits);
+    CMH_REQUIRE(nq >= 0 && nd >= 0 && n_chunks, CMH_ERR_ARG, "cmh_tc_plan: bad arguments");
+    int64_t g, c, r;
+    tc_geometry(nq, nd, &g, &c, &r);
+    *n_chunks = (int)c;
+    return CMH_OK;
+}
+
+static int tc_collect_impl(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits,
+                           int64_t index_base, const int32_t* thr, int K, int n_chunks_in, int seg_cap, uint64_t* cand,
+                           uint32_t* cnt, uint32_t* aux, int probe, void* stream) {
     CMH_REQUIRE(cmh_tc_supported(bits, 0), CMH_ERR_UNSUPPORTED, "cmh_tc_collect: bits=%d (64 or 128, +-1 codes only)", bits);
-    CMH_REQUIRE(nq >= 0 && nd >= 0 && cap >= 1 && K >= 0 && index_base >= 0 && index_base + nd <= (1ll << 32), CMH_ERR_ARG,
-                "cmh_tc_collect: bad sizes");
+    CMH_REQUIRE(nq >= 0 && nd >= 0 && seg_cap >= 1 && K >= 0 && index_base >= 0 && index_base + nd <= (1ll << 32),
+                CMH_ERR_ARG, "cmh_tc_collect: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
     if (nq == 0) return CMH_OK;
+    int64_t n_qgroups, n_chunks, chunk_rows;
+    tc_geometry(nq, nd, &n_qgroups, &n_chunks, &chunk_rows);
+    CMH_REQUIRE(n_chunks_in == (int)n_chunks, CMH_ERR_ARG, "cmh_tc_collect: n_chunks=%d, cmh_tc_plan says %d",
+                n_chunks_in, (int)n_chunks);
     CMH_REQUIRE(q_sign && thr && cand && cnt && aux, CMH_ERR_ARG, "cmh_tc_collect: NULL pointer");
     static_assert(sizeof(TcAux) == 32, "cmh_tc_collect: aux is uint32 [nq][8]");
-    CMH_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, st));
+    CMH_CUDA(cudaMemsetAsync(cnt, 0, (size_t)n_chunks * nq * 4, st));
     CMH_CUDA(cudaMemsetAsync(aux, 0, (size_t)nq * sizeof(TcAux), st));
     if (nd == 0) return CMH_OK;
     CMH_REQUIRE(d_sign, CMH_ERR_ARG, "cmh_tc_collect: NULL database");
+    CMH_REQUIRE(n_qgroups <= 0x7fffffffll && chunk_rows <= 0x7fffffff, CMH_ERR_UNSUPPORTED,
+                "cmh_tc_collect: launch geometry out of range");
     const int words = bits / 64;
     const int T = TC_MAX_T;
-    const int64_t n_qgroups = ceil_div(nq, (int64_t)T * TC_M);
-    // enough chunks for ~4 CTAs per SM over the launch, chunk = whole tiles
-    int64_t n_chunks = std::max<int64_t>(1, ceil_div((int64_t)sm_count() * 4, n_qgroups));
-    int64_t chunk_rows = round_up(ceil_div(nd, n_chunks), TC_N);
-    chunk_rows = std::max<int64_t>(chunk_rows, 16 * TC_N);
-    n_chunks = ceil_div(nd, chunk_rows);
-    CMH_REQUIRE(n_chunks <= 65535 && n_qgroups <= 0x7fffffffll && chunk_rows <= 0x7fffffff, CMH_ERR_UNSUPPORTED,
-                "cmh_tc_collect: launch geometry out of range");
     TcArgs a;
     a.q = q_sign; a.d = d_sign; a.thr = thr; a.cand = cand; a.cnt = cnt; a.aux = reinterpret_cast<TcAux*>(aux);
-    a.nq = nq; a.nd = nd; a.index_base = index_base; a.chunk_rows = (int)chunk_rows; a.cap = cap; a.bits = bits;
-    a.K = K;
+    a.nq = nq; a.nd = nd; a.index_base = index_base; a.chunk_rows = (int)chunk_rows; a.n_chunks = (int)n_chunks;
+    a.seg_cap = seg_cap; a.bits = bits; a.K = K; a.probe = probe; a.trace = g_tc_trace;
     const size_t smem = tc_smem_bytes(words, T);
     const dim3 grid((unsigned)n_qgroups, (unsigned)n_chunks);
     if (words == 1) {
         CMH_CUDA(cudaFuncSetAttribute(tc_collect_kernel<1, TC_MAX_T, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_collect_kernel<1, TC_MAX_T, 6><<<grid, TC_THREADS, smem, st>>>(a);
     } else {
-        CMH_CUDA(cudaFuncSetAttribute(tc_collect_kernel<2, TC_MAX_T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_collect_kernel<2, TC_MAX_T, 4><<<grid, TC_THREADS, smem, st>>>(a);
+        CMH_CUDA(cudaFuncSetAttribute(tc_collect_kernel<2, TC_MAX_T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_collect_kernel<2, TC_MAX_T, 3><<<grid, TC_THREADS, smem, st>>>(a);
     }
     CMH_LAUNCH_CHECK("tc_collect_kernel");
     return CMH_OK;
+}
+
+extern "C" int cmh_tc_collect(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits,
+                              int64_t index_base, const int32_t* thr, int K, int n_chunks, int seg_cap, uint64_t* cand,
+                              uint32_t* cnt, uint32_t* aux, void* stream) {
+    return tc_collect_impl(q_sign, nq, d_sign, nd, bits, index_base, thr, K, n_chunks, seg_cap, cand, cnt, aux, 0, stream);
+}
+
+extern "C" int cmh_tc_probe(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits,
+                            const int32_t* thr, int n_chunks, int seg_cap, uint64_t* cand, uint32_t* cnt, uint32_t* aux,
+                            int probe, void* stream) {
+    CMH_REQUIRE(probe >= 0 && probe < 16, CMH_ERR_ARG, "cmh_tc_probe: probe=%d", probe);
+    return tc_collect_impl(q_sign, nq, d_sign, nd, bits, 0, thr, 0, n_chunks, seg_cap, cand, cnt, aux, probe, stream);
 }
 
 extern "C" int cmh_topk_threshold(const uint32_t* hist, int64_t nq, int nb, int64_t n_sample, int64_t nd, int K,
@@ -544,18 +689,18 @@ extern "C" int cmh_topk_threshold(const uint32_t* hist, int64_t nq, int nb, int6
     return CMH_OK;
 }
 
-extern "C" int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, const uint32_t* aux, int64_t nq, int cap,
-                                 int K, int64_t nd, uint64_t* keys, uint32_t* fail_flags, uint32_t* fail_count,
-                                 void* stream) {
-    CMH_REQUIRE(nq >= 0 && cap >= 1 && K >= 1 && nd >= 0, CMH_ERR_ARG, "cmh_topk_finalize: bad sizes");
+extern "C" int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, const uint32_t* aux, int64_t nq,
+                                 int n_chunks, int seg_cap, int K, int64_t nd, uint64_t* keys, uint32_t* fail_flags,
+                                 uint32_t* fail_count, void* stream) {
+    CMH_REQUIRE(nq >= 0 && n_chunks >= 1 && seg_cap >= 1 && K >= 1 && nd >= 0, CMH_ERR_ARG, "cmh_topk_finalize: bad sizes");
     CMH_REQUIRE(K <= FIN_MAX, CMH_ERR_UNSUPPORTED, "cmh_topk_finalize: K=%d > %d", K, FIN_MAX);
     if (nq == 0) return CMH_OK;
     CMH_REQUIRE(cand && cnt && aux && keys && fail_flags && fail_count, CMH_ERR_ARG, "cmh_topk_finalize: NULL pointer");
     CMH_REQUIRE(nq <= 0x7fffffffll, CMH_ERR_UNSUPPORTED, "cmh_topk_finalize: too many queries per call");
     cudaStream_t st = (cudaStream_t)stream;
     CMH_CUDA(cudaMemsetAsync(fail_count, 0, 4, st));
-    topk_finalize_kernel<<<(unsigned)nq, 512, 0, st>>>(cand, cnt, reinterpret_cast<const TcAux*>(aux), cap, K, nd, keys,
-                                                       fail_flags, fail_count);
+    topk_finalize_kernel<<<(unsigned)nq, FIN_THREADS, 0, st>>>(cand, cnt, reinterpret_cast<const TcAux*>(aux), nq, n_chunks,
+                                                              seg_cap, K, nd, keys, fail_flags, fail_count);
     CMH_LAUNCH_CHECK("topk_finalize_kernel");
     return CMH_OK;
 }

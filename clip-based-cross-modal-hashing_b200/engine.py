@@ -340,7 +340,8 @@ def topk_merge(keys_in: torch.Tensor, K: int) -> torch.Tensor:
 # top-K on the tensor cores (tcgen05 / TMEM): sample histogram -> thresholds -> fused GEMM + candidate filter ->
 # per-query sort; queries whose candidate list came out short or overflowed are redone by the exact two-pass path
 # ---------------------------------------------------------------------------------------------------------------
-TC_DEFAULT_CAP = 8192
+TC_DEFAULT_CAP = 32768      # candidate slots per query, split evenly over the (query, chunk) segments
+TC_MIN_SEG = 64
 TC_MAX_K = 4096
 
 
@@ -349,8 +350,27 @@ def tc_supported(q: PackedSet, d: PackedSet, K: int = 1) -> bool:
             and bool(_cabi.lib().cmh_tc_supported(q.bits, 0)))
 
 
+class TcBuffers:
+    """Device scratch of one `cmh_tc_collect` launch geometry: candidate segments uint64 [nq][n_chunks][seg_cap],
+    per-segment counts uint32 [n_chunks][nq], per-query bookkeeping uint32 [nq][8]."""
+
+    def __init__(self, nq: int, nd: int, bits: int, cap: int, device: torch.device, seg_cap: Optional[int] = None):
+        n_chunks = ctypes.c_int(0)
+        with torch.cuda.device(device):
+            check(_cabi.lib().cmh_tc_plan(nq, nd, bits, ctypes.byref(n_chunks)), "cmh_tc_plan")
+        self.n_chunks = int(n_chunks.value)
+        self.seg_cap = max(TC_MIN_SEG, int(cap) // self.n_chunks) if seg_cap is None else int(seg_cap)
+        self.cand = torch.empty((nq, self.n_chunks, self.seg_cap), dtype=torch.int64, device=device)
+        self.cnt = torch.empty((self.n_chunks, nq), dtype=torch.int32, device=device)
+        self.aux = torch.empty((nq, 8), dtype=torch.int32, device=device)
+        self.thr = torch.empty(nq, dtype=torch.int32, device=device)
+        self.fail_flags = torch.empty(nq, dtype=torch.int32, device=device)
+        self.fail_count = torch.zeros(1, dtype=torch.int32, device=device)
+
+
 def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Optional[PackedSet] = None,
-            cap: int = TC_DEFAULT_CAP, stats: Optional[dict] = None, tighten: bool = True) -> torch.Tensor:
+            cap: int = TC_DEFAULT_CAP, stats: Optional[dict] = None, tighten: bool = True,
+            seg_cap: Optional[int] = None) -> torch.Tensor:
     """int64 [nq, K] ascending keys, identical to ``RankPass(q, d).topk(K, index_base)``.
 
     ``sample``: a subset of the rows of ``d`` (any rows, contiguous in memory) used only to guess the per-query
@@ -368,26 +388,22 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     L = _cabi.lib()
     smp = d if sample is None else sample
     h_all, _ = RankPass(q.with_labels(None, 0), smp.with_labels(None, 0), need_labels=False).hist()
-    thr = torch.empty(nq, dtype=torch.int32, device=dev)
-    cand = torch.empty((nq, cap), dtype=torch.int64, device=dev)
-    cnt = torch.empty(nq, dtype=torch.int32, device=dev)
-    aux = torch.empty((nq, 8), dtype=torch.int32, device=dev)
-    fail_flags = torch.empty(nq, dtype=torch.int32, device=dev)
-    fail_count = torch.zeros(1, dtype=torch.int32, device=dev)
+    b = TcBuffers(nq, d.n, q.bits, cap, dev, seg_cap)
     with torch.cuda.device(dev):
         st = _stream(dev)
-        check(L.cmh_topk_threshold(_ptr(h_all), nq, q.bits + 1, smp.n, d.n, K, _ptr(thr), st), "cmh_topk_threshold")
-        check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign), d.n, q.bits, int(index_base), _ptr(thr),
-                               K if tighten else 0, cap, _ptr(cand), _ptr(cnt), _ptr(aux), st), "cmh_tc_collect")
-        check(L.cmh_topk_finalize(_ptr(cand), _ptr(cnt), _ptr(aux), nq, cap, K, d.n, _ptr(keys), _ptr(fail_flags),
-                                  _ptr(fail_count), st), "cmh_topk_finalize")
-    n_fail = int(fail_count.item())
+        check(L.cmh_topk_threshold(_ptr(h_all), nq, q.bits + 1, smp.n, d.n, K, _ptr(b.thr), st), "cmh_topk_threshold")
+        check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign), d.n, q.bits, int(index_base), _ptr(b.thr),
+                               K if tighten else 0, b.n_chunks, b.seg_cap, _ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), st),
+              "cmh_tc_collect")
+        check(L.cmh_topk_finalize(_ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), nq, b.n_chunks, b.seg_cap, K, d.n,
+                                  _ptr(keys), _ptr(b.fail_flags), _ptr(b.fail_count), st), "cmh_topk_finalize")
+    n_fail = int(b.fail_count.item())
     if stats is not None:
         stats["n_fail"] = n_fail
-        stats["candidates"] = cnt
-        stats["thr"] = thr
+        stats["candidates"] = b.cnt.sum(0)
+        stats["thr"] = b.thr
     if n_fail:
-        rows = torch.nonzero(fail_flags, as_tuple=False).squeeze(1)
+        rows = torch.nonzero(b.fail_flags, as_tuple=False).squeeze(1)
         sub = PackedSet(q.sign.index_select(0, rows).contiguous(), None, None, int(rows.numel()), q.bits)
         keys.index_copy_(0, rows, RankPass(sub, d.with_labels(None, 0), need_labels=False).topk(K, index_base))
     return keys

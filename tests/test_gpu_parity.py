@@ -266,7 +266,7 @@ def test_tc_topk_matches_popc_path(dev, bits, nq, nd, K):
     stats = {}
     got = engine.topk_tc(q, db, K, 77, stats=stats)
     assert torch.equal(got, want)
-    # dense hits (K/D in the percent range) may overflow the lane-private staging and take the exact fallback;
+    # dense hits (K/D in the percent range) may overflow a candidate segment and take the exact fallback;
     # at retrieval-scale sparsity nothing should
     if K * 1000 <= nd:
         assert stats["n_fail"] == 0
@@ -288,7 +288,7 @@ def test_tc_topk_against_oracle_and_fallback(dev):
     assert np.array_equal(got.cpu().numpy().view(np.uint64), want)
     # a candidate buffer that is far too small forces every query through the exact fallback
     stats = {}
-    got = engine.topk_tc(q, db, K, 0, cap=512, stats=stats)
+    got = engine.topk_tc(q, db, K, 0, seg_cap=1, stats=stats)
     assert stats["n_fail"] == Q
     assert np.array_equal(got.cpu().numpy().view(np.uint64), want)
     # massive ties (identical codes): candidate lists overflow -> fallback -> index order
