@@ -3,16 +3,32 @@
 // on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM), with the top-K candidate filter
 // fused as the epilogue so that the Q x D distance matrix never exists.
 //
-// One CTA = TC_T x 128 queries (the A operand, expanded once to +-1 int8 in shared memory) x one database chunk.
+// One CTA = T x 128 queries x one contiguous database chunk, walked in tiles of 256 rows.
+//
+// Two database rows per accumulator.  The pipeline is bound by the round trip of an accumulator buffer (fill, drain
+// through tcgen05.ld, hand back) over the 512 TMEM columns, so every 32-bit accumulator carries TWO dot products and
+// the per-query threshold, all produced by the tensor core:
+//     acc[q][j] = bias_q + <q, d_j> + B * <q, d_{j+128}>            (j = 0..127 inside a 256-row tile)
+// from 2 * KSTEPS + 1 K-steps into the same TMEM columns: A = +-1 bytes against rows 0..127 expanded to +-1, then
+// A' = +-S bytes against rows 128..255 expanded to +-S (S * S = B), then one K-step of per-query digits against a
+// constant row of weights whose product is  bias_q = B - (B + 1) * T_q  (T_q = the dot product a row needs to qualify).
+// With e1 = dot1 - T and e2 = dot2 - T + 1,  acc = e1 + B * e2  and, F = log2 B,
+//     bit F-1  of acc clear  <=>  e1 >= 0  <=>  row j qualifies
+//     bit 2F-1 of acc clear  <=>  e2 - [e1 < 0] >= 0  <=>  row j+128 qualifies  (or dot2 == T - 1 next to a hit: harmless)
+// so the filter is an AND-reduction of the registers and one mask test per slice.  64-bit codes: F = 8, S = 16, acc
+// fits 16 bits and tcgen05.ld packs two columns per register (4 rows per register); 128-bit codes: F = 10, S = 32.
+// The fields cannot wrap (|e| < 2^(F-1) for 1 <= T <= bits), and dot products have the parity of the code length.
+// The fields of a flagged accumulator decode to the exact distances, which are compared with the query's CURRENT
+// threshold - it tightens while the scan proceeds - before the row is appended.
+//
 // Warp roles (warp-specialised, mbarrier pipelines, no __syncthreads in the main loop):
-//   warp 0        TMEM allocation; one elected lane issues tcgen05.mma + tcgen05.commit
-//   warps 1-4     producers: read packed 64-bit code words (8 B per row, coalesced), expand every bit to a +-1 byte
-//                 with a 16-entry nibble LUT and store 128x... core matrices (no-swizzle K-major UMMA layout) into a
-//                 TC_STAGES-deep ring of B tiles (256 database rows each)
-//   warps 5-12    epilogue: thread = query (TMEM lane), tcgen05.ld 32 columns at a time, VIMNMX3 max-tree, compare
-//                 with the query's threshold; a rare hit appends key (2*dist << 32 | global row) to the query's
-//                 candidate list in global memory
-// TMEM: 2 accumulator buffers x 256 columns (the whole 512-column TMEM, one CTA per SM).
+//   warps 0-3     MMA issuers, one per accumulator buffer (an elected lane: wait, 2 * KSTEPS tcgen05.mma, commit)
+//   warps 4-7     producers: packed code words arrive through a bulk-copy (cp.async.bulk) ring; every bit is expanded
+//                 to a +-1 / +-32 byte with two integer multiplies per nibble and stored as 8x16 B core matrices
+//                 (no-swizzle K-major UMMA layout) into a STAGES-deep ring of B tiles
+//   warps 8-23    epilogue: 4 groups of 4 warps, group g drains accumulator buffer g; thread = one query (a TMEM
+//                 lane) for the whole CTA, so its threshold, candidate count and code words live in registers
+// TMEM: 4 accumulator buffers x 128 columns (the whole 512-column TMEM, one CTA per SM).
 //
 // Exactness: thresholds only have to be upper bounds of the K-th distance (cmh_topk_threshold derives them from a
 // sample histogram); cmh_topk_finalize sorts the candidates by key - (distance, index), all keys distinct - which IS
@@ -38,17 +54,23 @@
 namespace cmh {
 
 constexpr int TC_M = 128;       // queries per MMA (TMEM lanes)
-constexpr int TC_N = 256;       // database rows per shared-memory stage (two MMAs of TC_NM columns)
-constexpr int TC_NM = 128;      // database rows per MMA = TMEM columns per accumulator buffer
+constexpr int TC_N = 256;       // database rows per tile (shared-memory stage): 2 rows per accumulator column
+constexpr int TC_NM = 128;      // accumulator columns per tile = N of one tcgen05.mma
 constexpr int TC_BUFS = 4;      // accumulator buffers (4 x 128 columns = the whole TMEM)
 constexpr int TC_MMA_WARPS = 4;   // one MMA issuer (elected lane) per accumulator buffer
 constexpr int TC_PROD_WARPS = 4;
 constexpr int TC_EPI_WARPS = 16;  // 4 groups of 4 warps; group g drains buffer g
-constexpr int TC_GROUPS = TC_EPI_WARPS / 4;
 constexpr int TC_THREADS = (TC_MMA_WARPS + TC_PROD_WARPS + TC_EPI_WARPS) * 32;
+// registers per thread: launched with 80 (768 threads); the issuer and producer warpgroups hand theirs to the 16 epilogue
+// warps, which keep two 32-column slices of accumulators in flight:  24 * 128 + 40 * 128 + 104 * 512 = 80 * 768
+constexpr int TC_REGS_MMA = 24, TC_REGS_PROD = 40, TC_REGS_EPI = 104;
+static_assert(TC_REGS_MMA * TC_MMA_WARPS * 32 + TC_REGS_PROD * TC_PROD_WARPS * 32 + TC_REGS_EPI * TC_EPI_WARPS * 32 <=
+              80 * TC_THREADS, "register budget");
 constexpr int TC_RING = 8;        // packed database tiles in flight (bulk copies)
 constexpr int TC_MAX_CHUNKS = 1024;  // candidate segments per query (cmh_topk_finalize walks them)
-constexpr int TC_MAX_T = 4;
+constexpr int TC_REFRESH = 16;    // tiles (per epilogue group) between threshold refreshes
+constexpr int TC_PARK = 4;        // lanes of a warp whose flagged slices are parked per round of the hit path
+constexpr int TC_BIAS_SLOTS = 12; // K slots of the bias step that carry weight 127 (the 13th carries weight 1)
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -79,7 +101,8 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+// 32 consecutive columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -91,8 +114,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// register reallocation between the role warpgroups (all 4 warps of an aligned warpgroup execute it)
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // 64 consecutive columns, two per register: column 2i in the low half of v[i], column 2i+1 in the high half (the
-// int32 accumulators are small - |dot| <= bits <= 128 - so their low 16 bits are the exact int16 value)
+// accumulators of 64-bit codes fit 16 bits, so their low halves are the exact values)
 __device__ __forceinline__ void tmem_ld64p(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
@@ -105,7 +134,6 @@ __device__ __forceinline__ void tmem_ld64p(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor, version 1):
 //   16-byte units: element (row r, 16-byte K chunk c) lives at  (r % 8) + (r / 8) * SBO + c * LBO
@@ -123,23 +151,23 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// 4 bits -> 4 bytes of +-1 (bit set -> +1 = 0x01, clear -> -1 = 0xFF), ALU only: the multiply spreads bit j to bit 8j
-// (the four shifted copies of a nibble do not overlap, so the product is their OR), and 0xFF - 0xFE * {0,1} per byte
-// never borrows.
+// 4 bits -> 4 bytes of +-S (bit set -> +S, clear -> -S), ALU only: the multiply spreads bit j to bit 8j (the four
+// shifted copies of a nibble do not overlap, so the product is their OR), and (256 - S) - (256 - 2S) * {0,1} per byte
+// never borrows.  S = 1: 0xFF / 0x01;  S = 32: 0xE0 / 0x20.
+template <int S>
 __device__ __forceinline__ uint32_t expand4(uint32_t nib) {
     const uint32_t x = (nib * 0x00204081u) & 0x01010101u;
-    return 0xFFFFFFFFu - x * 0xFEu;
+    return (uint32_t)(0x100 - S) * 0x01010101u - x * (uint32_t)(0x100 - 2 * S);
 }
+template <int S>
 __device__ __forceinline__ uint4 expand16(uint32_t bits16) {
     uint4 o;
-    o.x = expand4(bits16 & 15u);
-    o.y = expand4((bits16 >> 4) & 15u);
-    o.z = expand4((bits16 >> 8) & 15u);
-    o.w = expand4(bits16 >> 12);
+    o.x = expand4<S>(bits16 & 15u);
+    o.y = expand4<S>((bits16 >> 4) & 15u);
+    o.z = expand4<S>((bits16 >> 8) & 15u);
+    o.w = expand4<S>(bits16 >> 12);
     return o;
 }
-
-constexpr int TC_REFRESH = 32;     // tiles (per epilogue group) between threshold refreshes
 
 // per-query bookkeeping shared by every CTA working on the query (global memory, zeroed by cmh_tc_collect)
 struct TcAux {
@@ -152,47 +180,39 @@ struct TcArgs {
     const uint64_t* q;      // [nq][words]
     const uint64_t* d;      // [nd][words]
     const int32_t* thr;     // [nq] initial threshold bucket thr0 (Hamming distance): rows with dist <= thr qualify
-    uint64_t* cand;         // [nq][n_chunks][seg_cap]  one private candidate segment per (query, database chunk)
-    uint32_t* cnt;          // [n_chunks][nq]           candidates the chunk's CTA found (may exceed seg_cap)
+    uint64_t* cand;         // [nq][n_segs][seg_cap]  one private candidate segment per (query, chunk, draining thread)
+    uint32_t* cnt;          // [n_segs][nq]           candidates found per segment (may exceed seg_cap)
     TcAux* aux;             // [nq]
     int64_t nq, nd, index_base;
     int chunk_rows;         // database rows per CTA (multiple of TC_N)
-    int n_chunks, seg_cap, bits;
+    int n_segs, seg_base, seg_cap, bits;   // segments per query in all, first segment of this launch
     int K;                  // > 0: tighten thresholds while scanning (once K rows at dist <= thr0 - j are known)
     long long* trace;       // CMH_TC_TRACE builds only
     int probe;              // measurement aid (cmh_tc_probe): 1 = no tcgen05.mma, 2 = no TMEM drain, 4 = drain without scan
 };
 
-// per-half maximum of 8 registers of packed int16 pairs (VIMNMX3.S16x2)
-__device__ __forceinline__ uint32_t max8p(const uint32_t* v) {
-    const uint32_t m = __vimax3_s16x2(v[0], v[1], v[2]);
-    const uint32_t n = __vimax3_s16x2(v[3], v[4], v[5]);
-    return __vimax3_s16x2(m, n, __vmaxs2(v[6], v[7]));
-}
-
-// The hit path.  Out of line on purpose: one copy of the append keeps the epilogue's instruction footprint small (an
-// inlined, fully unrolled hit path was ~160 KB of SASS and every rare hit paid a chain of instruction-cache misses).
-// The slot comes from a shared-memory counter (the segment is private to this CTA), the key goes straight to global
-// memory and the tightening statistics are a fire-and-forget RED: nothing on this path waits for global memory.
-__device__ __noinline__ void tc_append(uint64_t* seg, uint32_t* pos_ctr, uint32_t seg_cap, uint32_t* h, int slack,
-                                       uint32_t key_hi, uint32_t key_lo) {
-    const uint32_t pos = atomicAdd(pos_ctr, 1u);
-    if (pos < seg_cap) seg[pos] = ((uint64_t)key_hi << 32) | key_lo;
-    if (h != nullptr) atomicAdd(h + min(slack, 3), 1u);
-}
-
-// smem: [A: T tiles][B: STAGES tiles][packed ring][barriers][tmem slot][thr][thr0][pos]
+// smem: [A: T tiles x {+-1, +-S, bias digits}][B: STAGES tiles][bias weights][packed ring][barriers][tmem slot][park]
 template <int WORDS, int T, int TC_STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs a) {
     constexpr int KBYTES = WORDS * 64;           // int8 elements (= bytes) per row
     constexpr int KSTEPS = KBYTES / 32;          // tcgen05.mma kind::i8 has K = 32
     constexpr int CHUNKS = KBYTES / 16;          // 16-byte K chunks per row
-    constexpr uint32_t A_TILE = TC_M * KBYTES;
+    constexpr int FIELD = WORDS == 1 ? 8 : 10;   // bits per packed dot-product field
+    constexpr int SCALE = 1 << (FIELD / 2);      // SCALE * SCALE = 1 << FIELD
+    constexpr bool PACKED = WORDS == 1;          // accumulators fit 16 bits: two columns per register
+    constexpr uint32_t FLAG_LO = 1u << (FIELD - 1), FLAG_HI = 1u << (2 * FIELD - 1);
+    constexpr uint32_t FLAGS = PACKED ? (FLAG_LO | FLAG_HI) * 0x10001u : (FLAG_LO | FLAG_HI);
+    constexpr uint32_t A_TILE = TC_M * KBYTES;   // one scale of one query tile
+    constexpr uint32_t A_BIAS = TC_M * 32;       // the bias K-step of one query tile
+    constexpr uint32_t A_ALL = 2 * A_TILE + A_BIAS;
     constexpr uint32_t B_TILE = TC_N * KBYTES;
+    constexpr uint32_t B_BIAS = TC_NM * 32;
+    static_assert(TC_BUFS % T == 0, "a group of epilogue warps serves one query tile");
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* sA = smem;
-    unsigned char* sB = smem + T * A_TILE;
-    uint64_t* ring = reinterpret_cast<uint64_t*>(sB + TC_STAGES * B_TILE);   // [TC_RING][256 rows][WORDS] packed words
+    unsigned char* sA = smem;                    // [T][A_ALL]
+    unsigned char* sB = smem + T * A_ALL;
+    unsigned char* sW = sB + TC_STAGES * B_TILE; // bias weights: 128 identical rows of 32 bytes
+    uint64_t* ring = reinterpret_cast<uint64_t*>(sW + B_BIAS);   // [TC_RING][256 rows][WORDS] packed words
     uint64_t* bars = ring + TC_RING * TC_N * WORDS;
     uint64_t* b_full = bars;                     // [STAGES] producers -> MMA
     uint64_t* b_empty = bars + TC_STAGES;        // [STAGES] MMA -> producers
@@ -201,21 +221,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
     uint64_t* r_full = bars + 2 * TC_STAGES + 2 * TC_BUFS;               // [RING] bulk copy -> producers
     uint64_t* r_empty = bars + 2 * TC_STAGES + 2 * TC_BUFS + TC_RING;    // [RING] producers -> bulk copy issuer
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2 * TC_BUFS + 2 * TC_RING);
-    int* s_thr = reinterpret_cast<int*>(tmem_slot + 2);    // [T][128] current dot-product thresholds
-    int* s_thr0 = s_thr + T * TC_M;                        // [T][128] dot-product threshold of thr0
-    uint32_t* s_pos = reinterpret_cast<uint32_t*>(s_thr0 + T * TC_M);   // [T][128] entries appended by this CTA
+    uint32_t* scratch = tmem_slot + 4;           // [EPI_WARPS][TC_PARK][32] parked slices of the hit path (16-byte aligned)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t q0 = (int64_t)blockIdx.x * (T * TC_M);
     const int64_t c_begin = (int64_t)blockIdx.y * a.chunk_rows;
     const int64_t c_end = min(a.nd, c_begin + a.chunk_rows);
     const int n_tiles = (int)((c_end - c_begin + TC_N - 1) / TC_N);
+    const int n_iters = n_tiles * T;             // iteration it = (tile i, query tile t) -> buffer / issuer / group it % 4
+    // the flag arithmetic needs 1 <= T_q; a larger threshold is clamped (the query then comes out short and takes the
+    // exact path)
+    const int thr_max = (a.bits - 1) >> 1;
 
     // ---- prologue -----------------------------------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(&b_full[s], TC_PROD_WARPS * 32);
-            mbar_init(&b_empty[s], TC_MMA_WARPS);
+            mbar_init(&b_empty[s], T);           // one commit per query tile
         }
         for (int b = 0; b < TC_BUFS; ++b) {
             mbar_init(&t_full[b], 1);
@@ -227,24 +249,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
         }
         mbar_fence_init();
     }
-    // dist <= thr  <=>  dot = bits - 2 dist >= bits - 2 thr ; padding queries never fire (int16 max)
-    for (int e = tid; e < T * TC_M; e += TC_THREADS) {
-        const int64_t q = q0 + e;
-        const int v = q < a.nq ? a.bits - 2 * a.thr[q] : 0x7fff;
-        s_thr[e] = v;
-        s_thr0[e] = v;
-        s_pos[e] = 0u;
-    }
-    __syncthreads();
-    // A operand: T x 128 query rows, expanded by everyone (rows beyond nq are all -1; their threshold never fires)
-    for (int i = tid; i < T * TC_M * WORDS * 4; i += TC_THREADS) {
-        const int c = i % (WORDS * 4);           // 16-byte chunk of the row
-        const int r = (i / (WORDS * 4)) % TC_M;
-        const int t = i / (WORDS * 4 * TC_M);
+    // A operand: T x 128 query rows at both scales, expanded by everyone (rows beyond nq are all -1 / -S; their
+    // threshold never fires)
+    for (int i = tid; i < T * TC_M * CHUNKS; i += TC_THREADS) {
+        const int c = i % CHUNKS;                // 16-byte chunk of the row
+        const int r = (i / CHUNKS) % TC_M;
+        const int t = i / (CHUNKS * TC_M);
         const int64_t q = q0 + t * TC_M + r;
         const uint64_t word = q < a.nq ? a.q[q * WORDS + (c >> 2)] : 0ull;
         const uint32_t b16 = (uint32_t)(word >> (16 * (c & 3))) & 0xffffu;
-        *reinterpret_cast<uint4*>(sA + t * A_TILE + c * (TC_M * 16) + r * 16) = expand16(b16);
+        unsigned char* dst = sA + t * A_ALL + c * (TC_M * 16) + r * 16;
+        *reinterpret_cast<uint4*>(dst) = expand16<1>(b16);
+        *reinterpret_cast<uint4*>(dst + A_TILE) = expand16<SCALE>(b16);
+    }
+    // bias K-step: digits of  bias_q = B - (B + 1) * T_q  against the weights (127 x TC_BIAS_SLOTS, 1, 0 ...)
+    for (int i = tid; i < T * TC_M; i += TC_THREADS) {
+        const int r = i % TC_M, t = i / TC_M;
+        const int64_t q = q0 + i;
+        // padding queries (all -1) get the tightest valid threshold; whatever they flag is dropped by the hit path
+        const int Tq = q < a.nq ? a.bits - 2 * max(0, min(a.thr[q], thr_max)) : a.bits;
+        int rest = (1 << FIELD) - ((1 << FIELD) + 1) * Tq;                             // < 0
+        int c1 = rest / 127;
+        const int c0 = rest - c1 * 127;
+        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < TC_BIAS_SLOTS; ++k) {
+            const int dgt = max(c1, -127);       // c1 <= 0
+            c1 -= dgt;
+            w[k >> 2] |= (uint32_t)(dgt & 0xff) << (8 * (k & 3));
+        }
+        w[TC_BIAS_SLOTS >> 2] |= (uint32_t)(c0 & 0xff) << (8 * (TC_BIAS_SLOTS & 3));
+        unsigned char* dst = sA + t * A_ALL + 2 * A_TILE + r * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(dst + TC_M * 16) = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+    for (int i = tid; i < TC_NM * 2; i += TC_THREADS) {          // weights: row i % 128, 16-byte chunk i / 128
+        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < TC_BIAS_SLOTS; ++k) w[k >> 2] |= 127u << (8 * (k & 3));
+        w[TC_BIAS_SLOTS >> 2] |= 1u << (8 * (TC_BIAS_SLOTS & 3));
+        const int c = i / TC_NM;
+        *reinterpret_cast<uint4*>(sW + c * (TC_NM * 16) + (i % TC_NM) * 16) =
+            make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
     }
     fence_proxy_async_smem();
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -255,52 +299,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
 
     if (warp < TC_MMA_WARPS) {
         // ================= MMA issuers =================
-        // Issuer w owns accumulator buffer w: tiles w, w + 4, ...  One thread doing wait -> tcgen05.mma -> commit for
-        // every tile spends ~300 cycles per tile on instruction latency alone (measured), more than the 128 cycles
-        // the tensor pipe needs for it; four issuers overlap that latency.
+        // Issuer w owns accumulator buffer w: iterations w, w + 4, ...  One thread doing wait -> tcgen05.mma -> commit
+        // for every tile spends ~300 cycles per tile on instruction latency alone (measured), more than the tensor
+        // pipe needs for it; four issuers overlap that latency.
+        reg_dec<TC_REGS_MMA>();
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_i8(TC_M, TC_NM);
-            const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+            const uint32_t b_addr = smem_u32(sB);
             const bool no_mma = (a.probe & 1) != 0;
-            const int n_iters = n_tiles * T * 2;     // iteration = (stage i, query tile t, row half h)
             const uint32_t d_tmem = tmem_base + warp * TC_NM;
+            const uint32_t a_addr = smem_u32(sA) + (warp % T) * A_ALL;           // this issuer's query tile
+            const uint64_t bias_a = umma_desc(a_addr + 2 * A_TILE, TC_M * 16, 128);
+            const uint64_t bias_b = umma_desc(smem_u32(sW), TC_NM * 16, 128);
             int round = 0;
 #pragma unroll 1
             for (int it = warp; it < n_iters; it += TC_MMA_WARPS, ++round) {
-                const int i = it / (2 * T), rem = it - i * (2 * T);
-                const int t = rem >> 1, h = rem & 1;
+                const int i = it / T;
                 const int s = i % TC_STAGES;
                 TC_TRACE(0, it, 3);
-                if (rem < TC_MMA_WARPS) {            // this issuer's first tile of the stage
-                    mbar_wait(&b_full[s], (i / TC_STAGES) & 1);
-                    tc_fence_after();
-                }
+                mbar_wait(&b_full[s], (i / TC_STAGES) & 1);
                 TC_TRACE(0, it, 0);
                 mbar_wait(&t_empty[warp], (round & 1) ^ 1);
                 tc_fence_after();
                 TC_TRACE(0, it, 1);
                 if (!no_mma) {
+                    umma_i8(d_tmem, bias_a, bias_b, idesc, 0u);      // acc = bias_q
 #pragma unroll
-                    for (int k = 0; k < KSTEPS; ++k) {
-                        const uint64_t ad = umma_desc(a_addr + t * A_TILE + k * 2 * (TC_M * 16), TC_M * 16, 128);
-                        const uint64_t bd = umma_desc(b_addr + s * B_TILE + k * 2 * (TC_N * 16) + h * (TC_NM * 16),
-                                                      TC_N * 16, 128);
-                        umma_i8(d_tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
+                    for (int f = 0; f < 2; ++f) {            // field 0: rows 0..127 (+-1); field 1: rows 128..255 (+-S)
+#pragma unroll
+                        for (int k = 0; k < KSTEPS; ++k) {
+                            const uint64_t ad = umma_desc(a_addr + f * A_TILE + k * 2 * (TC_M * 16), TC_M * 16, 128);
+                            const uint64_t bd = umma_desc(
+                                b_addr + s * B_TILE + k * 2 * (TC_N * 16) + f * (TC_NM * 16), TC_N * 16, 128);
+                            umma_i8(d_tmem, ad, bd, idesc, 1u);
+                        }
                     }
                 }
                 umma_commit(&t_full[warp]);
-                if (rem >= 2 * T - TC_MMA_WARPS) umma_commit(&b_empty[s]);   // ... and its last one
+                umma_commit(&b_empty[s]);
                 TC_TRACE(0, it, 2);
             }
         }
     } else if (warp < TC_MMA_WARPS + TC_PROD_WARPS) {
-        // ================= producers: packed bits -> +-1 int8 core matrices =================
+        // ================= producers: packed bits -> int8 core matrices =================
         // The packed words of a tile (256 rows, 2-4 KB) are staged in a TC_RING-deep shared-memory ring by the bulk-copy
-        // engine (cp.async.bulk, issued by one thread, completion on an mbarrier).  The producer threads must not have
-        // global loads of their own in flight: fence.proxy.async is a MEMBAR that waits for them, which bounded the
-        // kernel by one tile per global-memory round trip.  Tiles the engine cannot take (a ragged last tile, a shard
-        // view that is not 16-byte aligned) are read with plain loads.
-        const int pt = tid - TC_MMA_WARPS * 32;  // 0..127
+        // engine (cp.async.bulk, issued by one thread, completion on an mbarrier), so the producer threads have no
+        // global loads of their own in flight when they reach fence.proxy.async (a MEMBAR).  Tiles the engine cannot
+        // take (a ragged last tile, a shard view that is not 16-byte aligned) are read with plain loads.
+        reg_dec<TC_REGS_PROD>();
+        const int pt = tid - TC_MMA_WARPS * 32;  // 0..127: rows pt (scale 1) and 128 + pt (scale S) of every tile
         const bool aligned = (reinterpret_cast<uintptr_t>(a.d) & 15) == 0;
         auto bulk_tile = [&](int i) { return aligned && c_begin + (int64_t)(i + 1) * TC_N <= c_end; };
         auto issue = [&](int i) {                // pt == 0
@@ -343,16 +390,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
             if (pt == 0) TC_TRACE(1, i, 2);
             mbar_wait(&b_empty[s], ((i / TC_STAGES) & 1) ^ 1);
             if (pt == 0) TC_TRACE(1, i, 3);
-            unsigned char* dst = sB + s * B_TILE;
+            unsigned char* dst = sB + s * B_TILE + pt * 16;
             // rows past the end of the chunk are expanded like any other (as all -1): the hit path checks the row
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int r = h * 128 + pt;
-#pragma unroll
-                for (int c = 0; c < CHUNKS; ++c) {
-                    const uint32_t b16 = (uint32_t)(cur[h][c >> 2] >> (16 * (c & 3))) & 0xffffu;
-                    *reinterpret_cast<uint4*>(dst + c * (TC_N * 16) + r * 16) = expand16(b16);
-                }
+            for (int c = 0; c < CHUNKS; ++c) {
+                const uint32_t lo16 = (uint32_t)(cur[0][c >> 2] >> (16 * (c & 3))) & 0xffffu;
+                const uint32_t hi16 = (uint32_t)(cur[1][c >> 2] >> (16 * (c & 3))) & 0xffffu;
+                *reinterpret_cast<uint4*>(dst + c * (TC_N * 16)) = expand16<1>(lo16);
+                *reinterpret_cast<uint4*>(dst + c * (TC_N * 16) + 128 * 16) = expand16<SCALE>(hi16);
             }
             if (pt == 0) TC_TRACE(1, i, 4);
             fence_proxy_async_smem();            // generic-proxy stores -> visible to the tensor core (async proxy)
@@ -361,114 +406,154 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
             if (pt == 0) TC_TRACE(1, i, 6);
         }
     } else {
-        // ================= epilogue: threshold filter on the dot products =================
-        const int ew = warp - (TC_MMA_WARPS + TC_PROD_WARPS);   // 0 .. TC_EPI_WARPS-1
-        const int grp = ew >> 2;                          // group of 4 warps (one per TMEM lane quarter)
+        // ================= epilogue: flag filter on the packed dot products =================
+        reg_inc<TC_REGS_EPI>();
+        const int ew = warp - (TC_MMA_WARPS + TC_PROD_WARPS);   // 0 .. 15
+        const int grp = ew >> 2;                          // accumulator buffer this warp drains
         const int quarter = warp & 3;                     // TMEM lanes this warp may touch: 32 * (warp % 4)
         const int qrow = quarter * 32 + lane;             // query row inside the 128-row tile
+        const int t = grp % T;                            // ... of query tile t, for the whole CTA
         const bool no_drain = (a.probe & 2) != 0, no_scan = (a.probe & 4) != 0;
-        // Rare: at least one of the 64 dot products in x reaches the threshold.  Two-level search (4 block maxima,
-        // then the 8 registers of a block), both halves of a register by a rolled loop: 32 call sites in all.
-        auto collect64 = [&](const uint32_t (&x)[32], const uint32_t (&mb)[4], int thr, uint32_t thr2m, int t,
-                             int64_t row0) {
-            const int e = t * TC_M + qrow;
-            const int64_t q = q0 + e;
-            uint64_t* seg = a.cand + ((uint64_t)q * a.n_chunks + blockIdx.y) * (uint64_t)a.seg_cap;
-            uint32_t* h = a.K > 0 ? a.aux[q].h : nullptr;
-            const int dthr0 = s_thr0[e];
+        const int64_t q = q0 + t * TC_M + qrow;
+        const bool live = q < a.nq;
+        // this thread's query: rows with dist <= thr qualify; thr0 is what the bias K-step (the flags) was built from
+        const int thr0 = live ? min(a.thr[q], thr_max) : -1;
+        int thr = thr0;
+        const int dot_thr0 = a.bits - 2 * max(0, thr0);  // T0: the dot product behind the bias K-step of this query
+        // with T < 4 a query is drained by 4 / T threads of this CTA (one per group): each owns a segment of its own
+        const int seg_id = a.seg_base + blockIdx.y * (TC_BUFS / T) + grp / T;
+        uint64_t* seg = a.cand + ((uint64_t)(live ? q : 0) * a.n_segs + seg_id) * (uint64_t)a.seg_cap;
+        uint32_t* hq = (a.K > 0 && live) ? a.aux[q].h : nullptr;
+        uint32_t pos = 0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + grp * TC_NM;
+        // The hit path.  A lane whose slice holds a flagged row parks its 32 registers in a small shared-memory slot
+        // and walks them with ONE rolled loop (dynamic index): the code is a few dozen instructions per scan site
+        // instead of 32 unrolled sites, and nothing in it waits - the candidate segment is private to the thread (one
+        // query of one chunk), so the slot is a register counter, the key goes straight to global memory and the
+        // tightening statistics are a fire-and-forget RED.  Up to TC_PARK lanes of a warp per round.
+        uint32_t* park = scratch + ew * (TC_PARK * 32);
+        auto collect = [&](const uint32_t (&v)[32], bool flagged, int64_t row0) {
+            uint32_t pend = __ballot_sync(0xffffffffu, flagged);
+            while (pend) {                       // warp-uniform
+                const int rank = __popc(pend & lanemask_lt());
+                const bool mine = ((pend >> lane) & 1u) && rank < TC_PARK;
+                if (mine) {
+                    uint32_t regs = 0;           // registers of the slice that hold a flagged row
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                if (__vmaxs2(mb[b], thr2m) == thr2m) continue;
+                    for (int r = 0; r < 32; ++r) regs |= ((~v[r] & FLAGS) != 0u ? 1u : 0u) << r;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t w = x[8 * b + j];
-                    if (__vmaxs2(w, thr2m) == thr2m) continue;
+                    for (int r = 0; r < 32; r += 4)
+                        *reinterpret_cast<uint4*>(park + rank * 32 + r) = make_uint4(v[r], v[r + 1], v[r + 2], v[r + 3]);
 #pragma unroll 1
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const int val = hh ? ((int)w >> 16) : ((int)(w << 16) >> 16);
-                        const int64_t row = row0 + 16 * b + 2 * j + hh;
-                        if (val >= thr && row < c_end)
-                            tc_append(seg, &s_pos[e], (uint32_t)a.seg_cap, h, (val - dthr0) >> 1,
-                                      (uint32_t)(a.bits - val), (uint32_t)(a.index_base + row));
+                    while (regs) {
+                        const int r = __ffs(regs) - 1;
+                        regs &= regs - 1;
+                        const uint32_t xr = park[rank * 32 + r];
+                        uint32_t fl = ~xr & FLAGS;
+#pragma unroll 1
+                        while (fl) {
+                            const int bit = 31 - __clz(fl);
+                            fl &= ~(1u << bit);
+                            // packed: bit 7 / 15 = column 2r, field 0 / 1; bit 23 / 31 = column 2r + 1, field 0 / 1
+                            const int col = PACKED ? 2 * r + (bit >> 4) : r;
+                            const int f = PACKED ? ((bit >> 3) & 1) : (bit >= FIELD ? 1 : 0);
+                            // acc = e1 + B * e2, e1 = dot1 - T0, e2 = dot2 - T0 + 1 (no wrap): decode the flagged field
+                            const int val = PACKED ? ((bit >> 4) ? (int)xr >> 16 : (int)(xr << 16) >> 16) : (int)xr;
+                            const int e1 = (int)((uint32_t)val << (32 - FIELD)) >> (32 - FIELD);
+                            const int dot = f ? ((val - e1) >> FIELD) + dot_thr0 - 1 : e1 + dot_thr0;
+                            const int dist = (a.bits - dot) >> 1;
+                            const int64_t row = row0 + col + f * TC_NM;
+                            if (dist <= thr && row < c_end && live) {
+                                if (pos < (uint32_t)a.seg_cap)
+                                    seg[pos] = ((uint64_t)(uint32_t)(2 * dist) << 32) | (uint32_t)(a.index_base + row);
+                                if (hq != nullptr) atomicAdd(hq + min(thr0 - dist, 3), 1u);
+                                ++pos;
+                            }
+                        }
                     }
                 }
+                __syncwarp();                    // the slots are reused by the next round
+#pragma unroll
+                for (int k = 0; k < TC_PARK; ++k) pend &= pend - 1;
             }
         };
-        const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const int n_iters = n_tiles * T * 2;
+        // one slice (32 registers: 64 or 128 rows): AND-reduce, one mask test, one vote; the hit path is rare
+        auto scan = [&](const uint32_t (&v)[32], int64_t r0) {
+            if (no_scan) {
+                uint32_t o = 0;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) o |= v[r];
+                if (o == 0xdeadbeefu) a.cnt[0] = o;      // keep the loads alive
+                return;
+            }
+            uint32_t ab[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                ab[b] = (v[8 * b] & v[8 * b + 1] & v[8 * b + 2]) & (v[8 * b + 3] & v[8 * b + 4] & v[8 * b + 5]) &
+                        (v[8 * b + 6] & v[8 * b + 7]);
+            const bool flagged = ((ab[0] & ab[1] & ab[2] & ab[3]) & FLAGS) != FLAGS;
+            if (__any_sync(0xffffffffu, flagged)) collect(v, flagged, r0);
+        };
+        auto release = [&]() {                   // the values are in registers: the buffer goes back to its issuer
+            tc_fence_before();
+            mbar_arrive(&t_empty[grp]);
+        };
         int round = 0;
 #pragma unroll 1
-        for (int it = grp; it < n_iters; it += TC_GROUPS, ++round) {
-            const int i = it / (2 * T), rem = it - i * (2 * T);
-            const int t = rem >> 1, h = rem & 1;
-            const int buf = it & (TC_BUFS - 1);
-            const int64_t row0 = c_begin + (int64_t)i * TC_N + h * TC_NM;
+        for (int it = grp; it < n_iters; it += TC_BUFS, ++round) {
+            const int i = it / T;
+            const int64_t row0 = c_begin + (int64_t)i * TC_N;
             if (qrow == 0) TC_TRACE(2 + grp, round, 0);
-            mbar_wait(&t_full[buf], (it / TC_BUFS) & 1);
+            mbar_wait(&t_full[grp], round & 1);
             tc_fence_after();
             if (qrow == 0) TC_TRACE(2 + grp, round, 1);
-            const int thr = s_thr[t * TC_M + qrow];
-            const uint32_t thr2m = (uint32_t)((thr - 1) & 0xffff) * 0x10001u;   // "any half > thr - 1"
-            const uint32_t taddr = lane_taddr + buf * TC_NM;
             if (no_drain) {
-                tc_fence_before();
-                mbar_arrive(&t_empty[buf]);
-                if (qrow == 0) TC_TRACE(2 + grp, round, 4);
+                release();
                 continue;
             }
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {       // rolled: one scan site (and one hit path) in the kernel
-                uint32_t v[32];
-                tmem_ld64p(taddr + half * 64, v);
+            if (hq != nullptr && (round & (TC_REFRESH - 1)) == TC_REFRESH - 1) {
+                // tighten: once K rows at dist <= thr0 - j are known, nothing beyond that bucket can be in the top K
+                const uint4 c4 = __ldcg(reinterpret_cast<const uint4*>(hq));
+                const uint32_t K = (uint32_t)a.K;
+                const uint32_t c3 = c4.w, c2 = c3 + c4.z, c1 = c2 + c4.y;
+                const int j = c3 >= K ? 3 : (c2 >= K ? 2 : (c1 >= K ? 1 : 0));
+                thr = thr0 - j;
+            }
+            // two slices (register buffers) per trip to TMEM
+            uint32_t va[32], vb[32];
+            if (PACKED) {
+                tmem_ld64p(taddr, va);
+                tmem_ld64p(taddr + 64, vb);
                 tmem_ld_wait();
-                if (qrow == 0) TC_TRACE(2 + grp, round, 2 + half);
-                if (half == 1) {
-                    tc_fence_before();
-                    mbar_arrive(&t_empty[buf]);          // the values are in registers: the tile can be overwritten
-                }
-                if (no_scan) {
-                    uint32_t o = 0;
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) o |= v[r];
-                    if (o == 0xdeadbeefu) s_pos[0] = o;  // keep the loads alive
-                    continue;
-                }
-                uint32_t mb[4];
-#pragma unroll
-                for (int b = 0; b < 4; ++b) mb[b] = max8p(v + 8 * b);
-                const uint32_t m = __vimax3_s16x2(mb[0], mb[1], __vmaxs2(mb[2], mb[3]));
-                if (__vmaxs2(m, thr2m) != thr2m) collect64(v, mb, thr, thr2m, t, row0 + half * 64);
+                if (qrow == 0) TC_TRACE(2 + grp, round, 2);
+                release();                       // before anything is looked at: a hit never holds the buffer
+                scan(va, row0);
+                scan(vb, row0 + 64);
+            } else {
+                tmem_ld32(taddr, va);
+                tmem_ld32(taddr + 32, vb);
+                tmem_ld_wait();
+                scan(va, row0);
+                scan(vb, row0 + 32);
+                tmem_ld32(taddr + 64, va);
+                tmem_ld32(taddr + 96, vb);
+                tmem_ld_wait();
+                if (qrow == 0) TC_TRACE(2 + grp, round, 2);
+                release();
+                scan(va, row0 + 64);
+                scan(vb, row0 + 96);
             }
             if (qrow == 0) TC_TRACE(2 + grp, round, 4);
-            if (a.K > 0 && (round & (TC_REFRESH - 1)) == TC_REFRESH - 1) {
-                // tighten: once K rows at dist <= thr0 - j are known, nothing beyond that bucket can be in the top K
-                for (int u = 0; u < T; ++u) {
-                    const int e = u * TC_M + qrow;
-                    const int64_t q = q0 + e;
-                    if (q < a.nq) {
-                        const uint4 c = __ldcg(reinterpret_cast<const uint4*>(a.aux[q].h));
-                        const uint32_t K = (uint32_t)a.K;
-                        const uint32_t c3 = c.w, c2 = c3 + c.z, c1 = c2 + c.y;
-                        const int j = c3 >= K ? 3 : (c2 >= K ? 2 : (c1 >= K ? 1 : 0));
-                        s_thr[e] = s_thr0[e] + 2 * j;   // the four groups store the same or a newer (tighter) value
-                    }
-                }
-                __syncwarp();
-            }
+        }
+        if (live) {
+            a.cnt[(int64_t)seg_id * a.nq + q] = pos;
+            if (pos > (uint32_t)a.seg_cap) a.aux[q].force_fail = 1u;
         }
     }
     // ---- teardown -----------------------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 512);
-    for (int e = tid; e < T * TC_M; e += TC_THREADS) {
-        const int64_t q = q0 + e;
-        if (q < a.nq) {
-            const uint32_t n = s_pos[e];
-            a.cnt[(int64_t)blockIdx.y * a.nq + q] = n;
-            if (n > (uint32_t)a.seg_cap) a.aux[q].force_fail = 1u;
-        }
-    }
 }
 
 // ---- threshold from a sample histogram -------------------------------------------------------------------------------
@@ -489,6 +574,44 @@ __global__ void __launch_bounds__(256) topk_threshold_kernel(const uint32_t* __r
     thr[q] = t;
 }
 
+// ---- refine: thresholds from the candidates of a pilot launch ----------------------------------------------------------
+// The pilot launch scanned n_seen of the nd rows with thresholds thr_in and kept EVERY row at or below them (no
+// tightening), so per query the candidates' histogram is an exact sample of the distance distribution below thr_in.
+// thr_out = the smallest bucket whose cumulative pilot count reaches `need` (K f + sigma sqrt(K f) + 4), capped by
+// thr_in; unchanged when a pilot segment overflowed.  As with cmh_topk_threshold any outcome is safe.
+__global__ void __launch_bounds__(128) tc_refine_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt,
+                                                        int64_t nq, int seg_lo, int seg_hi, int seg_total, int seg_cap,
+                                                        double need, const int32_t* __restrict__ thr_in,
+                                                        int32_t* __restrict__ thr_out) {
+    __shared__ uint32_t hist[129];
+    __shared__ uint32_t s_over;
+    const int64_t q = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 129; i += blockDim.x) hist[i] = 0u;
+    if (threadIdx.x == 0) s_over = 0u;
+    __syncthreads();
+    const uint64_t* __restrict__ mine = cand + (uint64_t)q * seg_total * (uint64_t)seg_cap;
+    for (int c = seg_lo + warp; c < seg_hi; c += 4) {
+        uint32_t n = cnt[(int64_t)c * nq + q];
+        if (n > (uint32_t)seg_cap) { s_over = 1u; n = (uint32_t)seg_cap; }
+        const uint64_t* seg = mine + (uint64_t)c * seg_cap;
+        for (uint32_t i = lane; i < n; i += 32) atomicAdd(&hist[min((uint32_t)(seg[i] >> 33), 128u)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t_in = thr_in[q];
+        int t = t_in;
+        if (s_over == 0u) {
+            double cum = 0.0;
+            for (int b = 0; b <= min(t_in, 128); ++b) {
+                cum += (double)hist[b];
+                if (cum >= need) { t = b; break; }
+            }
+        }
+        thr_out[q] = t;
+    }
+}
+
 // ---- finalize: exact K-th bucket from the candidates' own histogram, compact, sort, emit -------------------------------
 // One CTA per query.  Every database row at or below the query's final threshold was collected, and that threshold
 // is an upper bound of the K-th distance, so the smallest bucket T whose cumulative candidate count reaches K is the
@@ -500,7 +623,8 @@ constexpr int FIN_THREADS = 512;
 
 __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64_t* __restrict__ cand,
                                                                     const uint32_t* __restrict__ cnt,
-                                                                    const TcAux* __restrict__ aux, int64_t nq,
+                                                                    const TcAux* __restrict__ aux,
+                                                                    const int32_t* __restrict__ thr_limit, int64_t nq,
                                                                     int n_chunks, int seg_cap, int K, int64_t nd,
                                                                     uint64_t* __restrict__ keys,
                                                                     uint32_t* __restrict__ fail_flags,
@@ -535,7 +659,9 @@ __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64
             int T = -1;
             for (int b = 0; b < FIN_BINS && cum < need; ++b) { cum += hist[b]; T = b; }
             s_T = T;
-            s_keep = cum > FIN_MAX ? -1 : (int)cum;
+            // buckets above thr_limit may be incomplete (launches with different thresholds): the K-th distance must
+            // not come from there
+            s_keep = (cum > FIN_MAX || (thr_limit != nullptr && T > thr_limit[q])) ? -1 : (int)cum;
         }
         __syncthreads();
         fail = s_keep < 0;
@@ -582,24 +708,27 @@ __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64
 
 using namespace cmh;
 
-// B-ring depth: 6 stages for 64-bit codes (>114 KB of shared memory per CTA, so exactly one CTA - which owns the whole
-// TMEM - is resident per SM), 3 for 128-bit codes (64 KB of A + 96 KB of B).
+// Per code length: query tiles per CTA and B-ring depth.  64-bit codes: 4 x 128 queries (80 KB of A: two scales + bias),
+// 6 stages of 16 KB; 128-bit codes: 2 x 128 queries (64 KB), 3 stages of 32 KB.  Either way > 114 KB of shared memory,
+// so exactly one CTA - which owns the whole TMEM - is resident per SM.
+static int tc_T(int words) { return words == 1 ? 4 : 2; }
 static int tc_stages(int words) { return words == 1 ? 6 : 3; }
-static size_t tc_smem_bytes(int words, int T) {
-    const int st = tc_stages(words);
-    return (size_t)T * TC_M * words * 64 + (size_t)st * TC_N * words * 64 + 64 + (2 * st + 2 * TC_BUFS + 2 * TC_RING) * 8 + 8 +
-           (size_t)3 * T * TC_M * 4 + (size_t)TC_RING * 2 * words * 128 * 8 + 16;
+static size_t tc_smem_bytes(int words) {
+    const int st = tc_stages(words), T = tc_T(words);
+    return (size_t)T * (2 * TC_M * words * 64 + TC_M * 32) + (size_t)st * TC_N * words * 64 + TC_NM * 32 +
+           (size_t)TC_RING * TC_N * words * 8 + (2 * st + 2 * TC_BUFS + 2 * TC_RING) * 8 + 16 +
+           (size_t)TC_EPI_WARPS * TC_PARK * 32 * 4;
 }
 
 extern "C" int cmh_tc_supported(int bits, int ternary) {
     return (!ternary && (bits == 64 || bits == 128)) ? 1 : 0;
 }
 
-// launch geometry: query groups of TC_MAX_T x 128 rows, database chunks of whole tiles, ~4 CTAs per SM over the launch
-static void tc_geometry(int64_t nq, int64_t nd, int64_t* n_qgroups, int64_t* n_chunks, int64_t* chunk_rows) {
-    *n_qgroups = std::max<int64_t>(1, ceil_div(nq, (int64_t)TC_MAX_T * TC_M));
+// launch geometry: query groups of T x 128 rows, database chunks of whole tiles, ~4 CTAs per SM over the launch
+static void tc_geometry(int64_t nq, int64_t nd, int words, int64_t* n_qgroups, int64_t* n_chunks, int64_t* chunk_rows) {
+    *n_qgroups = std::max<int64_t>(1, ceil_div(nq, (int64_t)tc_T(words) * TC_M));
     int64_t want = std::max<int64_t>(1, ceil_div((int64_t)sm_count() * 4, *n_qgroups));
-    want = std::min<int64_t>(want, TC_MAX_CHUNKS);
+    want = std::min<int64_t>(want, TC_MAX_CHUNKS / (TC_BUFS / tc_T(words)));
     int64_t rows = round_up(std::max<int64_t>(1, ceil_div(nd, want)), TC_N);
     rows = std::max<int64_t>(rows, 16 * TC_N);
     *chunk_rows = rows;
@@ -615,61 +744,80 @@ extern "C" int cmh_tc_plan(int64_t nq, int64_t nd, int bits, int* n_chunks) {
     CMH_REQUIRE(cmh_tc_supported(bits, 0), CMH_ERR_UNSUPPORTED, "cmh_tc_plan: bits=%d (64 or 128, +-1 codes only)", bits);
     CMH_REQUIRE(nq >= 0 && nd >= 0 && n_chunks, CMH_ERR_ARG, "cmh_tc_plan: bad arguments");
     int64_t g, c, r;
-    tc_geometry(nq, nd, &g, &c, &r);
-    *n_chunks = (int)c;
+    tc_geometry(nq, nd, bits / 64, &g, &c, &r);
+    *n_chunks = (int)c * (TC_BUFS / tc_T(bits / 64));     // candidate segments per query of one launch
     return CMH_OK;
 }
 
 static int tc_collect_impl(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits,
-                           int64_t index_base, const int32_t* thr, int K, int n_chunks_in, int seg_cap, uint64_t* cand,
-                           uint32_t* cnt, uint32_t* aux, int probe, void* stream) {
+                           int64_t index_base, const int32_t* thr, int K, int seg_base, int seg_total, int seg_cap,
+                           uint64_t* cand, uint32_t* cnt, uint32_t* aux, int probe, void* stream) {
     CMH_REQUIRE(cmh_tc_supported(bits, 0), CMH_ERR_UNSUPPORTED, "cmh_tc_collect: bits=%d (64 or 128, +-1 codes only)", bits);
     CMH_REQUIRE(nq >= 0 && nd >= 0 && seg_cap >= 1 && K >= 0 && index_base >= 0 && index_base + nd <= (1ll << 32),
                 CMH_ERR_ARG, "cmh_tc_collect: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
     if (nq == 0) return CMH_OK;
     int64_t n_qgroups, n_chunks, chunk_rows;
-    tc_geometry(nq, nd, &n_qgroups, &n_chunks, &chunk_rows);
-    CMH_REQUIRE(n_chunks_in == (int)n_chunks, CMH_ERR_ARG, "cmh_tc_collect: n_chunks=%d, cmh_tc_plan says %d",
-                n_chunks_in, (int)n_chunks);
+    tc_geometry(nq, nd, bits / 64, &n_qgroups, &n_chunks, &chunk_rows);
+    const int words = bits / 64;
+    const int n_segs = (int)n_chunks * (TC_BUFS / tc_T(words));
+    CMH_REQUIRE(seg_base >= 0 && seg_base + n_segs <= seg_total, CMH_ERR_ARG,
+                "cmh_tc_collect: segments [%d, %d) do not fit seg_total=%d (see cmh_tc_plan)", seg_base, seg_base + n_segs,
+                seg_total);
     CMH_REQUIRE(q_sign && thr && cand && cnt && aux, CMH_ERR_ARG, "cmh_tc_collect: NULL pointer");
     static_assert(sizeof(TcAux) == 32, "cmh_tc_collect: aux is uint32 [nq][8]");
-    CMH_CUDA(cudaMemsetAsync(cnt, 0, (size_t)n_chunks * nq * 4, st));
+    CMH_CUDA(cudaMemsetAsync(cnt + (size_t)seg_base * nq, 0, (size_t)n_segs * nq * 4, st));
     CMH_CUDA(cudaMemsetAsync(aux, 0, (size_t)nq * sizeof(TcAux), st));
     if (nd == 0) return CMH_OK;
     CMH_REQUIRE(d_sign, CMH_ERR_ARG, "cmh_tc_collect: NULL database");
     CMH_REQUIRE(n_qgroups <= 0x7fffffffll && chunk_rows <= 0x7fffffff, CMH_ERR_UNSUPPORTED,
                 "cmh_tc_collect: launch geometry out of range");
-    const int words = bits / 64;
-    const int T = TC_MAX_T;
     TcArgs a;
     a.q = q_sign; a.d = d_sign; a.thr = thr; a.cand = cand; a.cnt = cnt; a.aux = reinterpret_cast<TcAux*>(aux);
-    a.nq = nq; a.nd = nd; a.index_base = index_base; a.chunk_rows = (int)chunk_rows; a.n_chunks = (int)n_chunks;
-    a.seg_cap = seg_cap; a.bits = bits; a.K = K; a.probe = probe; a.trace = g_tc_trace;
-    const size_t smem = tc_smem_bytes(words, T);
+    a.nq = nq; a.nd = nd; a.index_base = index_base; a.chunk_rows = (int)chunk_rows; a.n_segs = seg_total;
+    a.seg_base = seg_base; a.seg_cap = seg_cap; a.bits = bits; a.K = K; a.probe = probe; a.trace = g_tc_trace;
+    const size_t smem = tc_smem_bytes(words);
     const dim3 grid((unsigned)n_qgroups, (unsigned)n_chunks);
     if (words == 1) {
-        CMH_CUDA(cudaFuncSetAttribute(tc_collect_kernel<1, TC_MAX_T, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_collect_kernel<1, TC_MAX_T, 6><<<grid, TC_THREADS, smem, st>>>(a);
+        CMH_CUDA(cudaFuncSetAttribute(tc_collect_kernel<1, 4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_collect_kernel<1, 4, 6><<<grid, TC_THREADS, smem, st>>>(a);
     } else {
-        CMH_CUDA(cudaFuncSetAttribute(tc_collect_kernel<2, TC_MAX_T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_collect_kernel<2, TC_MAX_T, 3><<<grid, TC_THREADS, smem, st>>>(a);
+        CMH_CUDA(cudaFuncSetAttribute(tc_collect_kernel<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_collect_kernel<2, 2, 3><<<grid, TC_THREADS, smem, st>>>(a);
     }
     CMH_LAUNCH_CHECK("tc_collect_kernel");
     return CMH_OK;
 }
 
 extern "C" int cmh_tc_collect(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits,
-                              int64_t index_base, const int32_t* thr, int K, int n_chunks, int seg_cap, uint64_t* cand,
-                              uint32_t* cnt, uint32_t* aux, void* stream) {
-    return tc_collect_impl(q_sign, nq, d_sign, nd, bits, index_base, thr, K, n_chunks, seg_cap, cand, cnt, aux, 0, stream);
+                              int64_t index_base, const int32_t* thr, int K, int seg_base, int seg_total, int seg_cap,
+                              uint64_t* cand, uint32_t* cnt, uint32_t* aux, void* stream) {
+    return tc_collect_impl(q_sign, nq, d_sign, nd, bits, index_base, thr, K, seg_base, seg_total, seg_cap, cand, cnt, aux,
+                           0, stream);
 }
 
 extern "C" int cmh_tc_probe(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits,
-                            const int32_t* thr, int n_chunks, int seg_cap, uint64_t* cand, uint32_t* cnt, uint32_t* aux,
+                            const int32_t* thr, int seg_total, int seg_cap, uint64_t* cand, uint32_t* cnt, uint32_t* aux,
                             int probe, void* stream) {
-    CMH_REQUIRE(probe >= 0 && probe < 16, CMH_ERR_ARG, "cmh_tc_probe: probe=%d", probe);
-    return tc_collect_impl(q_sign, nq, d_sign, nd, bits, 0, thr, 0, n_chunks, seg_cap, cand, cnt, aux, probe, stream);
+    CMH_REQUIRE(probe >= 0 && probe < 8, CMH_ERR_ARG, "cmh_tc_probe: probe=%d", probe);
+    return tc_collect_impl(q_sign, nq, d_sign, nd, bits, 0, thr, 0, 0, seg_total, seg_cap, cand, cnt, aux, probe, stream);
+}
+
+extern "C" int cmh_tc_refine(const uint64_t* cand, const uint32_t* cnt, int64_t nq, int seg_lo, int seg_hi, int seg_total,
+                             int seg_cap, int64_t n_seen, int64_t nd, int K, double sigma, const int32_t* thr_in,
+                             int32_t* thr_out, void* stream) {
+    CMH_REQUIRE(nq >= 0 && 0 <= seg_lo && seg_lo <= seg_hi && seg_hi <= seg_total && seg_cap >= 1 && n_seen >= 0 &&
+                    nd >= n_seen && K >= 1 && sigma >= 0.0,
+                CMH_ERR_ARG, "cmh_tc_refine: bad sizes");
+    if (nq == 0) return CMH_OK;
+    CMH_REQUIRE(cand && cnt && thr_in && thr_out, CMH_ERR_ARG, "cmh_tc_refine: NULL pointer");
+    CMH_REQUIRE(nq <= 0x7fffffffll, CMH_ERR_UNSUPPORTED, "cmh_tc_refine: too many queries per call");
+    const double kf = (double)K * (double)n_seen / (double)std::max<int64_t>(nd, 1);
+    const double need = n_seen >= nd ? (double)std::min<int64_t>(K, nd) : kf + sigma * std::sqrt(kf) + 4.0;
+    tc_refine_kernel<<<(unsigned)nq, 128, 0, (cudaStream_t)stream>>>(cand, cnt, nq, seg_lo, seg_hi, seg_total, seg_cap, need,
+                                                                    thr_in, thr_out);
+    CMH_LAUNCH_CHECK("tc_refine_kernel");
+    return CMH_OK;
 }
 
 extern "C" int cmh_topk_threshold(const uint32_t* hist, int64_t nq, int nb, int64_t n_sample, int64_t nd, int K,
@@ -689,9 +837,9 @@ extern "C" int cmh_topk_threshold(const uint32_t* hist, int64_t nq, int nb, int6
     return CMH_OK;
 }
 
-extern "C" int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, const uint32_t* aux, int64_t nq,
-                                 int n_chunks, int seg_cap, int K, int64_t nd, uint64_t* keys, uint32_t* fail_flags,
-                                 uint32_t* fail_count, void* stream) {
+extern "C" int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, const uint32_t* aux, const int32_t* thr_limit,
+                                 int64_t nq, int n_chunks, int seg_cap, int K, int64_t nd, uint64_t* keys,
+                                 uint32_t* fail_flags, uint32_t* fail_count, void* stream) {
     CMH_REQUIRE(nq >= 0 && n_chunks >= 1 && seg_cap >= 1 && K >= 1 && nd >= 0, CMH_ERR_ARG, "cmh_topk_finalize: bad sizes");
     CMH_REQUIRE(K <= FIN_MAX, CMH_ERR_UNSUPPORTED, "cmh_topk_finalize: K=%d > %d", K, FIN_MAX);
     if (nq == 0) return CMH_OK;
@@ -699,8 +847,8 @@ extern "C" int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, cons
     CMH_REQUIRE(nq <= 0x7fffffffll, CMH_ERR_UNSUPPORTED, "cmh_topk_finalize: too many queries per call");
     cudaStream_t st = (cudaStream_t)stream;
     CMH_CUDA(cudaMemsetAsync(fail_count, 0, 4, st));
-    topk_finalize_kernel<<<(unsigned)nq, FIN_THREADS, 0, st>>>(cand, cnt, reinterpret_cast<const TcAux*>(aux), nq, n_chunks,
-                                                              seg_cap, K, nd, keys, fail_flags, fail_count);
+    topk_finalize_kernel<<<(unsigned)nq, FIN_THREADS, 0, st>>>(cand, cnt, reinterpret_cast<const TcAux*>(aux), thr_limit, nq,
+                                                              n_chunks, seg_cap, K, nd, keys, fail_flags, fail_count);
     CMH_LAUNCH_CHECK("topk_finalize_kernel");
     return CMH_OK;
 }

@@ -340,9 +340,12 @@ def topk_merge(keys_in: torch.Tensor, K: int) -> torch.Tensor:
 # top-K on the tensor cores (tcgen05 / TMEM): sample histogram -> thresholds -> fused GEMM + candidate filter ->
 # per-query sort; queries whose candidate list came out short or overflowed are redone by the exact two-pass path
 # ---------------------------------------------------------------------------------------------------------------
-TC_DEFAULT_CAP = 32768      # candidate slots per query, split evenly over the (query, chunk) segments
+TC_DEFAULT_CAP = 32768      # candidate slots per query, split evenly over its segments
 TC_MIN_SEG = 64
 TC_MAX_K = 4096
+TC_PILOT_MIN_ROWS = 8_000_000     # databases at least this long get a pilot launch over their first rows
+TC_PILOT_FRACTION = 16            # ... 1/16 of them
+TC_PILOT_SIGMA = 5.0
 
 
 def tc_supported(q: PackedSet, d: PackedSet, K: int = 1) -> bool:
@@ -351,30 +354,47 @@ def tc_supported(q: PackedSet, d: PackedSet, K: int = 1) -> bool:
 
 
 class TcBuffers:
-    """Device scratch of one `cmh_tc_collect` launch geometry: candidate segments uint64 [nq][n_chunks][seg_cap],
-    per-segment counts uint32 [n_chunks][nq], per-query bookkeeping uint32 [nq][8]."""
+    """Device scratch of the `cmh_tc_collect` launches over the row ranges ``regions`` of one database: candidate
+    segments uint64 [nq][seg_total][seg_cap], per-segment counts uint32 [seg_total][nq], per-query bookkeeping
+    uint32 [nq][8].  ``seg_base[i]`` / ``n_segs[i]``: the segments launch i fills."""
 
-    def __init__(self, nq: int, nd: int, bits: int, cap: int, device: torch.device, seg_cap: Optional[int] = None):
-        n_chunks = ctypes.c_int(0)
+    def __init__(self, nq: int, regions: Sequence[int], bits: int, cap: int, device: torch.device,
+                 seg_cap: Optional[int] = None):
+        self.n_segs, self.seg_base = [], []
         with torch.cuda.device(device):
-            check(_cabi.lib().cmh_tc_plan(nq, nd, bits, ctypes.byref(n_chunks)), "cmh_tc_plan")
-        self.n_chunks = int(n_chunks.value)
-        self.seg_cap = max(TC_MIN_SEG, int(cap) // self.n_chunks) if seg_cap is None else int(seg_cap)
-        self.cand = torch.empty((nq, self.n_chunks, self.seg_cap), dtype=torch.int64, device=device)
-        self.cnt = torch.empty((self.n_chunks, nq), dtype=torch.int32, device=device)
+            for nd in regions:
+                n = ctypes.c_int(0)
+                check(_cabi.lib().cmh_tc_plan(nq, int(nd), bits, ctypes.byref(n)), "cmh_tc_plan")
+                self.seg_base.append(sum(self.n_segs))
+                self.n_segs.append(int(n.value))
+        self.seg_total = sum(self.n_segs)
+        self.n_chunks = self.seg_total
+        self.seg_cap = max(TC_MIN_SEG, int(cap) // max(self.n_segs)) if seg_cap is None else int(seg_cap)
+        self.cand = torch.empty((nq, self.seg_total, self.seg_cap), dtype=torch.int64, device=device)
+        self.cnt = torch.empty((self.seg_total, nq), dtype=torch.int32, device=device)
         self.aux = torch.empty((nq, 8), dtype=torch.int32, device=device)
         self.thr = torch.empty(nq, dtype=torch.int32, device=device)
+        self.thr2 = torch.empty(nq, dtype=torch.int32, device=device)
         self.fail_flags = torch.empty(nq, dtype=torch.int32, device=device)
         self.fail_count = torch.zeros(1, dtype=torch.int32, device=device)
 
 
+def tc_pilot_rows(nd: int) -> int:
+    """Rows of the pilot launch (0 = none): a multiple of the 256-row tile."""
+    if nd < TC_PILOT_MIN_ROWS:
+        return 0
+    return (nd // TC_PILOT_FRACTION) // 256 * 256
+
+
 def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Optional[PackedSet] = None,
             cap: int = TC_DEFAULT_CAP, stats: Optional[dict] = None, tighten: bool = True,
-            seg_cap: Optional[int] = None) -> torch.Tensor:
+            seg_cap: Optional[int] = None, pilot: Optional[int] = None) -> torch.Tensor:
     """int64 [nq, K] ascending keys, identical to ``RankPass(q, d).topk(K, index_base)``.
 
     ``sample``: a subset of the rows of ``d`` (any rows, contiguous in memory) used only to guess the per-query
-    thresholds; None = use ``d`` itself (exact thresholds, an extra popc pass)."""
+    thresholds; None = use ``d`` itself (exact thresholds, an extra popc pass).
+    ``pilot``: rows of the pilot launch (None = `tc_pilot_rows`): the first ``pilot`` rows are scanned with the sample
+    thresholds, and what they hold refines the thresholds for the rest of the database."""
     if not tc_supported(q, d, K):
         raise ValueError("tensor-core top-K needs +-1 codes of 64 or 128 bits and K <= 4096")
     K = int(K)
@@ -388,20 +408,36 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     L = _cabi.lib()
     smp = d if sample is None else sample
     h_all, _ = RankPass(q.with_labels(None, 0), smp.with_labels(None, 0), need_labels=False).hist()
-    b = TcBuffers(nq, d.n, q.bits, cap, dev, seg_cap)
+    n_pilot = tc_pilot_rows(d.n) if pilot is None else int(pilot)
+    if sample is None or n_pilot <= 0 or n_pilot >= d.n:
+        n_pilot = 0                                  # exact thresholds need no refinement
+    regions = [n_pilot, d.n - n_pilot] if n_pilot else [d.n]
+    b = TcBuffers(nq, regions, q.bits, cap, dev, seg_cap)
     with torch.cuda.device(dev):
         st = _stream(dev)
         check(L.cmh_topk_threshold(_ptr(h_all), nq, q.bits + 1, smp.n, d.n, K, _ptr(b.thr), st), "cmh_topk_threshold")
-        check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign), d.n, q.bits, int(index_base), _ptr(b.thr),
-                               K if tighten else 0, b.n_chunks, b.seg_cap, _ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), st),
-              "cmh_tc_collect")
-        check(L.cmh_topk_finalize(_ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), nq, b.n_chunks, b.seg_cap, K, d.n,
-                                  _ptr(keys), _ptr(b.fail_flags), _ptr(b.fail_count), st), "cmh_topk_finalize")
+        thr_main = b.thr
+        row0 = 0
+        if n_pilot:
+            check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign), n_pilot, q.bits, int(index_base), _ptr(b.thr), 0,
+                                   b.seg_base[0], b.seg_total, b.seg_cap, _ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), st),
+                  "cmh_tc_collect")
+            check(L.cmh_tc_refine(_ptr(b.cand), _ptr(b.cnt), nq, b.seg_base[0], b.seg_base[0] + b.n_segs[0], b.seg_total,
+                                  b.seg_cap, n_pilot, d.n, K, TC_PILOT_SIGMA, _ptr(b.thr), _ptr(b.thr2), st),
+                  "cmh_tc_refine")
+            thr_main = b.thr2
+            row0 = n_pilot
+        check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign[row0:]), d.n - row0, q.bits, int(index_base) + row0,
+                               _ptr(thr_main), K if tighten else 0, b.seg_base[-1], b.seg_total, b.seg_cap, _ptr(b.cand),
+                               _ptr(b.cnt), _ptr(b.aux), st), "cmh_tc_collect")
+        check(L.cmh_topk_finalize(_ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), _ptr(thr_main), nq, b.seg_total, b.seg_cap, K,
+                                  d.n, _ptr(keys), _ptr(b.fail_flags), _ptr(b.fail_count), st), "cmh_topk_finalize")
     n_fail = int(b.fail_count.item())
     if stats is not None:
         stats["n_fail"] = n_fail
         stats["candidates"] = b.cnt.sum(0)
-        stats["thr"] = b.thr
+        stats["thr"] = thr_main
+        stats["pilot_rows"] = n_pilot
     if n_fail:
         rows = torch.nonzero(b.fail_flags, as_tuple=False).squeeze(1)
         sub = PackedSet(q.sign.index_select(0, rows).contiguous(), None, None, int(rows.numel()), q.bits)

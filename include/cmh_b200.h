@@ -172,37 +172,46 @@ int cmh_topk_merge(const uint64_t* keys_in, int n_lists, int64_t nq, int K, uint
  * candidate filter fused as the epilogue.  Supported: +-1 codes (no valid plane) of 64 or 128 bits. */
 int cmh_tc_supported(int bits, int ternary);
 /* Launch geometry of cmh_tc_collect for an (nq, nd) problem on the current device: the database is cut into
- * *n_chunks contiguous chunks, one CTA per (group of 512 queries, chunk); every (query, chunk) pair owns a private
- * candidate segment. */
+ * contiguous chunks, one CTA per (group of 512 / 256 queries, chunk); *n_chunks = the number of private candidate
+ * segments every query owns in ONE launch (one per chunk for 64-bit codes, two for 128-bit codes). */
 int cmh_tc_plan(int64_t nq, int64_t nd, int bits, int* n_chunks);
 /* thr: device int32 [nq] - per-query upper bound of the K-th Hamming distance; every database row with
- * dist <= thr[q] (or <= a tighter bound derived while scanning when K > 0: once K rows at dist <= thr[q] - j are
- * known, j <= 3) is appended, in no particular order, to its (query, chunk) segment
- * cand[q][c][0..seg_cap) (device uint64 [nq][n_chunks][seg_cap]) as key (2*dist << 32) | (index_base + row).
- * cnt (device uint32 [n_chunks][nq]) counts the rows found per segment and may exceed seg_cap; aux: device uint32
- * [nq][8] bookkeeping; both are written by the call.  n_chunks must be the value cmh_tc_plan returns.  K = 0 keeps
- * the thresholds fixed. */
+ * dist <= thr[q] (or <= a tighter bound derived while scanning when K > 0: once K rows of THIS launch at
+ * dist <= thr[q] - j are known, j <= 3) is appended, in no particular order, to one of the query's segments
+ * cand[q][seg_base + s][0..seg_cap) (device uint64 [nq][seg_total][seg_cap]; s < cmh_tc_plan's count) as key
+ * (2*dist << 32) | (index_base + row).  cnt (device uint32 [seg_total][nq]) counts the rows found per segment and may
+ * exceed seg_cap; aux: device uint32 [nq][8] bookkeeping; the launch's own segments of cnt and aux are written by the
+ * call.  Several launches (row ranges of one database, e.g. a pilot range and the rest) fill disjoint segment
+ * ranges of the same arrays.  K = 0 keeps the thresholds fixed.  Thresholds above (bits-1)/2 are clamped. */
 int cmh_tc_collect(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits,
-                   int64_t index_base, const int32_t* thr, int K, int n_chunks, int seg_cap, uint64_t* cand,
-                   uint32_t* cnt, uint32_t* aux, void* stream);
+                   int64_t index_base, const int32_t* thr, int K, int seg_base, int seg_total, int seg_cap,
+                   uint64_t* cand, uint32_t* cnt, uint32_t* aux, void* stream);
 /* Measurement aid for the roofline of cmh_tc_collect: the same kernel and launch with parts of the pipeline
  * disabled, to time the ceilings in situ.  probe bit 0: no tcgen05.mma is issued (operand expansion + TMEM drain +
  * filter only); bit 1: accumulators are not drained (operand expansion + MMA only = tensor-pipe ceiling);
  * bit 2: accumulators are drained but not scanned.  Outputs are meaningless. */
 int cmh_tc_probe(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits, const int32_t* thr,
-                 int n_chunks, int seg_cap, uint64_t* cand, uint32_t* cnt, uint32_t* aux, int probe, void* stream);
+                 int seg_total, int seg_cap, uint64_t* cand, uint32_t* cnt, uint32_t* aux, int probe, void* stream);
+/* Thresholds from a pilot launch: segments [seg_lo, seg_hi) hold every row at or below thr_in[q] (a K = 0 launch)
+ * among n_seen of the nd rows.  thr_out[q] = the smallest bucket whose cumulative pilot count reaches
+ * K*f + sigma*sqrt(K*f) + 4 (f = n_seen / nd), never above thr_in[q]. */
+int cmh_tc_refine(const uint64_t* cand, const uint32_t* cnt, int64_t nq, int seg_lo, int seg_hi, int seg_total,
+                  int seg_cap, int64_t n_seen, int64_t nd, int K, double sigma, const int32_t* thr_in, int32_t* thr_out,
+                  void* stream);
 /* thr[q] from a histogram (cmh_eval_hist, binary mode, nb = bits + 1) over a SAMPLE of n_sample rows of an nd-row
  * shard: smallest bucket whose cumulative sample count reaches K*f + 6*sqrt(K*f) + 8 (f = n_sample / nd), exactly
  * min(K, nd) when n_sample == nd. */
 int cmh_topk_threshold(const uint32_t* hist, int64_t nq, int nb, int64_t n_sample, int64_t nd, int K,
                        int32_t* thr, void* stream);
-/* Per query: K-th distance from the candidates' own histogram, sort of the candidates at or below it, K smallest
- * keys out (UINT64_MAX pads when nd < K; K <= 4096).  fail_flags[q] (device uint32 [nq]) = 1 and *fail_count
- * (device uint32) incremented when a candidate segment overflowed, the query holds fewer than min(K, nd) candidates
- * or more than 4096 at or below the K-th distance: those queries must be re-run through cmh_topk (exact path). */
-int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, const uint32_t* aux, int64_t nq, int n_chunks,
-                      int seg_cap, int K, int64_t nd, uint64_t* keys, uint32_t* fail_flags, uint32_t* fail_count,
-                      void* stream);
+/* Per query: K-th distance from the candidates' own histogram over all n_chunks (= seg_total) segments, sort of the
+ * candidates at or below it, K smallest keys out (UINT64_MAX pads when nd < K; K <= 4096).  thr_limit (device int32
+ * [nq] or NULL): the smallest initial threshold any launch used for the query - buckets above it are incomplete.
+ * fail_flags[q] (device uint32 [nq]) = 1 and *fail_count (device uint32) incremented when a candidate segment
+ * overflowed, the query holds fewer than min(K, nd) candidates, more than 4096 at or below the K-th distance, or
+ * its K-th distance lies above thr_limit: those queries must be re-run through cmh_topk (exact path). */
+int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, const uint32_t* aux, const int32_t* thr_limit,
+                      int64_t nq, int n_chunks, int seg_cap, int K, int64_t nd, uint64_t* keys, uint32_t* fail_flags,
+                      uint32_t* fail_count, void* stream);
 
 #ifdef __cplusplus
 }

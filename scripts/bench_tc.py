@@ -28,25 +28,31 @@ def timed(fn, reps=3):
 rp = engine.RankPass(q, sample, need_labels=False)
 t_hist = timed(lambda: rp.hist())
 h_all, _ = rp.hist()
-b = engine.TcBuffers(Q, D, BITS, CAP, dev)
+b = engine.TcBuffers(Q, [D], BITS, CAP, dev)
 engine.check(L.cmh_topk_threshold(p(h_all), Q, BITS + 1, sample.n, D, K, p(b.thr), st))
 keys = torch.empty((Q, K), dtype=torch.int64, device=dev)
 
 
-def collect(k):
-    engine.check(L.cmh_tc_collect(p(q.sign), Q, p(db.sign), D, BITS, 0, p(b.thr), k, b.n_chunks, b.seg_cap,
+def collect(k, thr):
+    engine.check(L.cmh_tc_collect(p(q.sign), Q, p(db.sign), D, BITS, 0, p(thr), k, 0, b.seg_total, b.seg_cap,
                                   p(b.cand), p(b.cnt), p(b.aux), st))
 
 
-t_static = timed(lambda: collect(0))
+t_static = timed(lambda: collect(0, b.thr))
 c_static = b.cnt.sum(0).cpu().float(); seg_static_max = int(b.cnt.max())
-t_collect = timed(lambda: collect(K))
+t_collect = timed(lambda: collect(K, b.thr))
 c = b.cnt.sum(0).cpu().float(); seg_max = int(b.cnt.max())
-t_final = timed(lambda: engine.check(L.cmh_topk_finalize(p(b.cand), p(b.cnt), p(b.aux), Q, b.n_chunks, b.seg_cap, K, D,
+t_final = timed(lambda: engine.check(L.cmh_topk_finalize(p(b.cand), p(b.cnt), p(b.aux), p(b.thr), Q, b.seg_total, b.seg_cap, K, D,
                                                          p(keys), p(b.fail_flags), p(b.fail_count), st)))
 n_fail = int(b.fail_count.item())
-out = {"Q": Q, "D": D, "bits": BITS, "n_chunks": b.n_chunks, "seg_cap": b.seg_cap, "sample_rows": sample.n,
+# exact thresholds (the K-th distance itself): the least work the hit path can be given
+cum = torch.cumsum(torch.zeros(1), 0)
+kth = (keys[:, K - 1] >> 33).to(torch.int32).contiguous()
+t_exact_thr = timed(lambda: collect(0, kth))
+c_exact = b.cnt.sum(0).cpu().float()
+out = {"Q": Q, "D": D, "bits": BITS, "seg_total": b.seg_total, "seg_cap": b.seg_cap, "sample_rows": sample.n,
        "hist_sample_ms": t_hist, "collect_ms": t_collect, "collect_static_thr_ms": t_static,
+       "collect_exact_thr_ms": t_exact_thr, "cand_exact_mean": float(c_exact.mean()),
        "cand_static_mean": float(c_static.mean()), "cand_static_max": float(c_static.max()),
        "seg_static_max": seg_static_max, "seg_max": seg_max, "finalize_ms": t_final,
        "pairs_per_s_collect": Q * D / t_collect * 1e3, "cand_mean": float(c.mean()), "cand_max": float(c.max()),
@@ -55,14 +61,19 @@ if PROBES:
     # in-situ ceilings: impossible threshold (no hits) with parts of the pipeline disabled
     thr0 = torch.full((Q,), -1, dtype=torch.int32, device=dev)
     for name, mode in (("nohit", 0), ("no_mma", 1), ("mma_only", 2), ("drain_noscan", 4), ("no_mma_noscan", 5),
-                       ("no_mma_no_drain", 3), ("no_mma_no_drain_plain_arrive", 11), ("no_mma_plain_arrive", 9)):
-        t = timed(lambda: engine.check(L.cmh_tc_probe(p(q.sign), Q, p(db.sign), D, BITS, p(thr0), b.n_chunks, b.seg_cap,
+                       ("no_mma_no_drain", 3)):
+        t = timed(lambda: engine.check(L.cmh_tc_probe(p(q.sign), Q, p(db.sign), D, BITS, p(thr0), b.seg_total, b.seg_cap,
                                                       p(b.cand), p(b.cnt), p(b.aux), mode, st)))
         out[f"probe_{name}_ms"] = t
         out[f"probe_{name}_pairs_per_clk_sm"] = Q * D / (t * 1e-3) / 148 / 1.965e9
-t_total = timed(lambda: engine.topk_tc(q, db, K, 0, sample=sample, cap=CAP))
+stats = {}
+t_total = timed(lambda: engine.topk_tc(q, db, K, 0, sample=sample, cap=CAP, stats=stats))
 out["topk_tc_total_ms"] = t_total
 out["pairs_per_s_total"] = Q * D / t_total * 1e3
+out["total_cand_mean"] = float(stats["candidates"].float().mean()); out["total_n_fail"] = stats["n_fail"]
+out["pilot_rows"] = stats["pilot_rows"]
+t_nopilot = timed(lambda: engine.topk_tc(q, db, K, 0, sample=sample, cap=CAP, pilot=0))
+out["topk_tc_nopilot_ms"] = t_nopilot
 import subprocess
 out["clocks_after"] = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,power.draw",
                                       "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
