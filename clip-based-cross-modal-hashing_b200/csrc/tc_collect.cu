@@ -574,20 +574,26 @@ __global__ void __launch_bounds__(256) topk_threshold_kernel(const uint32_t* __r
     thr[q] = t;
 }
 
-// ---- refine: thresholds from the candidates of a pilot launch ----------------------------------------------------------
+constexpr int FIN_MAX = 4096;
+constexpr int FIN_BINS = 129;   // bits <= 128 on the tensor path
+constexpr int FIN_THREADS = 512;
+
+// ---- thresholds from the candidates of a pilot launch ------------------------------------------------------------------
 // The pilot launch scanned n_seen of the nd rows with thresholds thr_in and kept EVERY row at or below them (no
 // tightening), so per query the candidates' histogram is an exact sample of the distance distribution below thr_in.
-// thr_out = the smallest bucket whose cumulative pilot count reaches `need` (K f + sigma sqrt(K f) + 4), capped by
-// thr_in; unchanged when a pilot segment overflowed.  As with cmh_topk_threshold any outcome is safe.
-__global__ void __launch_bounds__(128) tc_refine_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt,
-                                                        int64_t nq, int seg_lo, int seg_hi, int seg_total, int seg_cap,
-                                                        double need, const int32_t* __restrict__ thr_in,
-                                                        int32_t* __restrict__ thr_out) {
-    __shared__ uint32_t hist[129];
+// Step 1 (tc_cand_hist_kernel): that histogram, uint32 [nq][nb] (bucket = Hamming distance), and whether a segment
+// overflowed.  Sharded databases all-reduce the histograms here.  Step 2 (tc_choose_kernel): thr_out = the smallest
+// bucket whose cumulative count reaches `need`, capped by thr_in; unchanged when a segment overflowed.  As with
+// cmh_topk_threshold any outcome is safe: a threshold that turns out too low is caught after the merge.
+__global__ void __launch_bounds__(128) tc_cand_hist_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt,
+                                                           int64_t nq, int seg_lo, int seg_hi, int seg_total, int seg_cap,
+                                                           int nb, uint32_t* __restrict__ hist_out,
+                                                           uint32_t* __restrict__ overflow) {
+    __shared__ uint32_t hist[FIN_BINS];
     __shared__ uint32_t s_over;
     const int64_t q = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < 129; i += blockDim.x) hist[i] = 0u;
+    for (int i = threadIdx.x; i < FIN_BINS; i += blockDim.x) hist[i] = 0u;
     if (threadIdx.x == 0) s_over = 0u;
     __syncthreads();
     const uint64_t* __restrict__ mine = cand + (uint64_t)q * seg_total * (uint64_t)seg_cap;
@@ -595,21 +601,43 @@ __global__ void __launch_bounds__(128) tc_refine_kernel(const uint64_t* __restri
         uint32_t n = cnt[(int64_t)c * nq + q];
         if (n > (uint32_t)seg_cap) { s_over = 1u; n = (uint32_t)seg_cap; }
         const uint64_t* seg = mine + (uint64_t)c * seg_cap;
-        for (uint32_t i = lane; i < n; i += 32) atomicAdd(&hist[min((uint32_t)(seg[i] >> 33), 128u)], 1u);
+        for (uint32_t i = lane; i < n; i += 32) atomicAdd(&hist[min((uint32_t)(seg[i] >> 33), (uint32_t)(FIN_BINS - 1))], 1u);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const int t_in = thr_in[q];
-        int t = t_in;
-        if (s_over == 0u) {
-            double cum = 0.0;
-            for (int b = 0; b <= min(t_in, 128); ++b) {
-                cum += (double)hist[b];
-                if (cum >= need) { t = b; break; }
-            }
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) hist_out[q * nb + i] = i < FIN_BINS ? hist[i] : 0u;
+    if (threadIdx.x == 0) overflow[q] = s_over;
+}
+
+__global__ void __launch_bounds__(256) tc_choose_kernel(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ overflow,
+                                                        int64_t nq, int nb, double need, const int32_t* __restrict__ thr_in,
+                                                        int32_t* __restrict__ thr_out) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const int t_in = thr_in[q];
+    int t = t_in;
+    if (overflow == nullptr || overflow[q] == 0u) {
+        double cum = 0.0;
+        for (int b = 0; b <= min(t_in, nb - 1); ++b) {
+            cum += (double)hist[q * nb + b];
+            if (cum >= need) { t = b; break; }
         }
-        thr_out[q] = t;
     }
+    thr_out[q] = t;
+}
+
+// ---- verify: the K-th key of a (merged) result must come from complete buckets ------------------------------------------
+__global__ void __launch_bounds__(256) topk_verify_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ thr_limit,
+                                                          int64_t nq, int K, int64_t need, uint32_t* __restrict__ fail_flags,
+                                                          uint32_t* __restrict__ fail_count) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    bool fail = fail_flags[q] != 0u;
+    if (!fail && need > 0) {
+        const uint64_t last = keys[q * K + (need - 1)];
+        fail = last == ~0ull || (int)(uint32_t)(last >> 33) > thr_limit[q];
+    }
+    fail_flags[q] = fail ? 1u : 0u;
+    if (fail) atomicAdd(fail_count, 1u);
 }
 
 // ---- finalize: exact K-th bucket from the candidates' own histogram, compact, sort, emit -------------------------------
@@ -617,15 +645,12 @@ __global__ void __launch_bounds__(128) tc_refine_kernel(const uint64_t* __restri
 // is an upper bound of the K-th distance, so the smallest bucket T whose cumulative candidate count reaches K is the
 // true K-th distance; only candidates with dist <= T (between K and a few K of them) are sorted - by key, i.e. by
 // (distance, global index), which is the stable ranking.  A warp walks one (query, chunk) segment at a time.
-constexpr int FIN_MAX = 4096;
-constexpr int FIN_BINS = 129;   // bits <= 128 on the tensor path
-constexpr int FIN_THREADS = 512;
 
 __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64_t* __restrict__ cand,
                                                                     const uint32_t* __restrict__ cnt,
                                                                     const TcAux* __restrict__ aux,
                                                                     const int32_t* __restrict__ thr_limit, int64_t nq,
-                                                                    int n_chunks, int seg_cap, int K, int64_t nd,
+                                                                    int n_chunks, int seg_cap, int K, int64_t nd, int partial,
                                                                     uint64_t* __restrict__ keys,
                                                                     uint32_t* __restrict__ fail_flags,
                                                                     uint32_t* __restrict__ fail_count) {
@@ -652,12 +677,14 @@ __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64
         for (uint32_t i = lane; i < n; i += 32) atomicAdd(&hist[(uint32_t)(seg[i] >> 33)], 1u);
     }
     __syncthreads();
-    bool fail = s_over != 0u || (int64_t)s_total < need || aux[q].force_fail != 0u;
+    // partial (one shard of several): emit what there is, up to K; the K-th key is judged after the merge
+    const int64_t want = partial ? min(need, (int64_t)s_total) : need;
+    bool fail = s_over != 0u || (int64_t)s_total < want || aux[q].force_fail != 0u;
     if (!fail) {
         if (threadIdx.x == 0) {
             int64_t cum = 0;
             int T = -1;
-            for (int b = 0; b < FIN_BINS && cum < need; ++b) { cum += hist[b]; T = b; }
+            for (int b = 0; b < FIN_BINS && cum < want; ++b) { cum += hist[b]; T = b; }
             s_T = T;
             // buckets above thr_limit may be incomplete (launches with different thresholds): the K-th distance must
             // not come from there
@@ -803,20 +830,42 @@ extern "C" int cmh_tc_probe(const uint64_t* q_sign, int64_t nq, const uint64_t* 
     return tc_collect_impl(q_sign, nq, d_sign, nd, bits, 0, thr, 0, 0, seg_total, seg_cap, cand, cnt, aux, probe, stream);
 }
 
-extern "C" int cmh_tc_refine(const uint64_t* cand, const uint32_t* cnt, int64_t nq, int seg_lo, int seg_hi, int seg_total,
-                             int seg_cap, int64_t n_seen, int64_t nd, int K, double sigma, const int32_t* thr_in,
-                             int32_t* thr_out, void* stream) {
-    CMH_REQUIRE(nq >= 0 && 0 <= seg_lo && seg_lo <= seg_hi && seg_hi <= seg_total && seg_cap >= 1 && n_seen >= 0 &&
-                    nd >= n_seen && K >= 1 && sigma >= 0.0,
-                CMH_ERR_ARG, "cmh_tc_refine: bad sizes");
+extern "C" int cmh_tc_cand_hist(const uint64_t* cand, const uint32_t* cnt, int64_t nq, int seg_lo, int seg_hi, int seg_total,
+                                int seg_cap, int nb, uint32_t* hist, uint32_t* overflow, void* stream) {
+    CMH_REQUIRE(nq >= 0 && 0 <= seg_lo && seg_lo <= seg_hi && seg_hi <= seg_total && seg_cap >= 1 && nb >= 1, CMH_ERR_ARG,
+                "cmh_tc_cand_hist: bad sizes");
     if (nq == 0) return CMH_OK;
-    CMH_REQUIRE(cand && cnt && thr_in && thr_out, CMH_ERR_ARG, "cmh_tc_refine: NULL pointer");
-    CMH_REQUIRE(nq <= 0x7fffffffll, CMH_ERR_UNSUPPORTED, "cmh_tc_refine: too many queries per call");
+    CMH_REQUIRE(cand && cnt && hist && overflow, CMH_ERR_ARG, "cmh_tc_cand_hist: NULL pointer");
+    CMH_REQUIRE(nq <= 0x7fffffffll, CMH_ERR_UNSUPPORTED, "cmh_tc_cand_hist: too many queries per call");
+    tc_cand_hist_kernel<<<(unsigned)nq, 128, 0, (cudaStream_t)stream>>>(cand, cnt, nq, seg_lo, seg_hi, seg_total, seg_cap, nb,
+                                                                       hist, overflow);
+    CMH_LAUNCH_CHECK("tc_cand_hist_kernel");
+    return CMH_OK;
+}
+
+extern "C" int cmh_tc_choose(const uint32_t* hist, const uint32_t* overflow, int64_t nq, int nb, int64_t n_seen, int64_t nd,
+                             int K, double sigma, const int32_t* thr_in, int32_t* thr_out, void* stream) {
+    CMH_REQUIRE(nq >= 0 && nb >= 1 && n_seen >= 0 && nd >= n_seen && K >= 1 && sigma >= 0.0, CMH_ERR_ARG,
+                "cmh_tc_choose: bad sizes");
+    if (nq == 0) return CMH_OK;
+    CMH_REQUIRE(hist && thr_in && thr_out, CMH_ERR_ARG, "cmh_tc_choose: NULL pointer");
     const double kf = (double)K * (double)n_seen / (double)std::max<int64_t>(nd, 1);
     const double need = n_seen >= nd ? (double)std::min<int64_t>(K, nd) : kf + sigma * std::sqrt(kf) + 4.0;
-    tc_refine_kernel<<<(unsigned)nq, 128, 0, (cudaStream_t)stream>>>(cand, cnt, nq, seg_lo, seg_hi, seg_total, seg_cap, need,
-                                                                    thr_in, thr_out);
-    CMH_LAUNCH_CHECK("tc_refine_kernel");
+    tc_choose_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, (cudaStream_t)stream>>>(hist, overflow, nq, nb, need, thr_in, thr_out);
+    CMH_LAUNCH_CHECK("tc_choose_kernel");
+    return CMH_OK;
+}
+
+extern "C" int cmh_topk_verify(const uint64_t* keys, const int32_t* thr_limit, int64_t nq, int K, int64_t nd,
+                               uint32_t* fail_flags, uint32_t* fail_count, void* stream) {
+    CMH_REQUIRE(nq >= 0 && K >= 1 && nd >= 0, CMH_ERR_ARG, "cmh_topk_verify: bad sizes");
+    if (nq == 0) return CMH_OK;
+    CMH_REQUIRE(keys && thr_limit && fail_flags && fail_count, CMH_ERR_ARG, "cmh_topk_verify: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    CMH_CUDA(cudaMemsetAsync(fail_count, 0, 4, st));
+    topk_verify_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(keys, thr_limit, nq, K, std::min<int64_t>(K, nd), fail_flags,
+                                                                   fail_count);
+    CMH_LAUNCH_CHECK("topk_verify_kernel");
     return CMH_OK;
 }
 
@@ -838,7 +887,7 @@ extern "C" int cmh_topk_threshold(const uint32_t* hist, int64_t nq, int nb, int6
 }
 
 extern "C" int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, const uint32_t* aux, const int32_t* thr_limit,
-                                 int64_t nq, int n_chunks, int seg_cap, int K, int64_t nd, uint64_t* keys,
+                                 int64_t nq, int n_chunks, int seg_cap, int K, int64_t nd, int partial, uint64_t* keys,
                                  uint32_t* fail_flags, uint32_t* fail_count, void* stream) {
     CMH_REQUIRE(nq >= 0 && n_chunks >= 1 && seg_cap >= 1 && K >= 1 && nd >= 0, CMH_ERR_ARG, "cmh_topk_finalize: bad sizes");
     CMH_REQUIRE(K <= FIN_MAX, CMH_ERR_UNSUPPORTED, "cmh_topk_finalize: K=%d > %d", K, FIN_MAX);
@@ -847,8 +896,9 @@ extern "C" int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, cons
     CMH_REQUIRE(nq <= 0x7fffffffll, CMH_ERR_UNSUPPORTED, "cmh_topk_finalize: too many queries per call");
     cudaStream_t st = (cudaStream_t)stream;
     CMH_CUDA(cudaMemsetAsync(fail_count, 0, 4, st));
-    topk_finalize_kernel<<<(unsigned)nq, FIN_THREADS, 0, st>>>(cand, cnt, reinterpret_cast<const TcAux*>(aux), thr_limit, nq,
-                                                              n_chunks, seg_cap, K, nd, keys, fail_flags, fail_count);
+    topk_finalize_kernel<<<(unsigned)nq, FIN_THREADS, 0, st>>>(cand, cnt, reinterpret_cast<const TcAux*>(aux),
+                                                              partial ? nullptr : thr_limit, nq, n_chunks, seg_cap, K, nd,
+                                                              partial, keys, fail_flags, fail_count);
     CMH_LAUNCH_CHECK("topk_finalize_kernel");
     return CMH_OK;
 }

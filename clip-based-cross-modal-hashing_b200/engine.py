@@ -386,52 +386,120 @@ def tc_pilot_rows(nd: int) -> int:
     return (nd // TC_PILOT_FRACTION) // 256 * 256
 
 
+class LocalComm:
+    """The exchange steps of the tensor-core top-K for a database that lives on ONE GPU (no-ops).  `sharded.GroupComm`
+    is the `torch.distributed` version for a database sharded over the ranks of a process group."""
+    world = 1
+
+    def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+        return t
+
+    def all_reduce_max(self, t: torch.Tensor) -> torch.Tensor:
+        return t
+
+    def all_gather_stack(self, t: torch.Tensor) -> torch.Tensor:
+        return t.unsqueeze(0)
+
+
 def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Optional[PackedSet] = None,
             cap: int = TC_DEFAULT_CAP, stats: Optional[dict] = None, tighten: bool = True,
-            seg_cap: Optional[int] = None, pilot: Optional[int] = None) -> torch.Tensor:
-    """int64 [nq, K] ascending keys, identical to ``RankPass(q, d).topk(K, index_base)``.
+            seg_cap: Optional[int] = None, pilot: Optional[int] = None, comm=None, nd_total: Optional[int] = None,
+            exact_fallback=None) -> torch.Tensor:
+    """int64 [nq, K] ascending keys, identical to ``RankPass(q, d).topk(K, index_base)`` (to the global stable
+    ranking when ``d`` is one shard of a database of ``nd_total`` rows and ``comm`` spans the shards).
 
-    ``sample``: a subset of the rows of ``d`` (any rows, contiguous in memory) used only to guess the per-query
-    thresholds; None = use ``d`` itself (exact thresholds, an extra popc pass).
-    ``pilot``: rows of the pilot launch (None = `tc_pilot_rows`): the first ``pilot`` rows are scanned with the sample
-    thresholds, and what they hold refines the thresholds for the rest of the database."""
+    sample  a subset of the rows of ``d`` (any rows, contiguous in memory) used only to guess the per-query
+            thresholds; None = use ``d`` itself (exact thresholds when unsharded, an extra popc pass)
+    pilot   rows of the pilot launch (None = `tc_pilot_rows`): the first ``pilot`` rows of ``d`` are scanned with the
+            sample thresholds, and what they hold refines the thresholds for the rest
+    comm    exchange steps (`LocalComm`, `sharded.GroupComm`): the sample / pilot histograms are all-reduced so that
+            every shard filters with the same global thresholds - a shard then contributes only its share of the ~K
+            rows below them - and the per-shard results are all-gathered and merged
+    exact_fallback(sub_q) -> keys for the queries whose candidate lists came out short or overflowed (the exact
+            two-pass path; default: `RankPass.topk` on ``d``, which is only right when unsharded)"""
     if not tc_supported(q, d, K):
         raise ValueError("tensor-core top-K needs +-1 codes of 64 or 128 bits and K <= 4096")
+    comm = LocalComm() if comm is None else comm
     K = int(K)
     dev = q.device
     nq = q.n
+    nd_total = d.n if nd_total is None else int(nd_total)
     keys = torch.empty((nq, K), dtype=torch.int64, device=dev)
     if nq == 0:
         return keys
-    if d.n == 0:
+    if nd_total == 0:
         return keys.fill_(-1)
     L = _cabi.lib()
+    nb = q.bits + 1
     smp = d if sample is None else sample
-    h_all, _ = RankPass(q.with_labels(None, 0), smp.with_labels(None, 0), need_labels=False).hist()
     n_pilot = tc_pilot_rows(d.n) if pilot is None else int(pilot)
-    if sample is None or n_pilot <= 0 or n_pilot >= d.n:
+    if (sample is None and comm.world == 1) or n_pilot <= 0 or n_pilot >= d.n:
         n_pilot = 0                                  # exact thresholds need no refinement
     regions = [n_pilot, d.n - n_pilot] if n_pilot else [d.n]
     b = TcBuffers(nq, regions, q.bits, cap, dev, seg_cap)
+    counts = torch.tensor([smp.n, n_pilot], dtype=torch.int64, device=dev)
+    if comm.world > 1:
+        counts = comm.all_reduce_sum(counts)
+        n_sample_all, n_pilot_all = (int(v) for v in counts.tolist())
+        if n_pilot_all == 0:
+            n_pilot_all = 0
+    else:
+        n_sample_all, n_pilot_all = smp.n, n_pilot
+    if smp.n:
+        h_all, _ = RankPass(q.with_labels(None, 0), smp.with_labels(None, 0), need_labels=False).hist()
+    else:
+        h_all = torch.zeros((nq, nb), dtype=torch.int32, device=dev)
+    h_all = comm.all_reduce_sum(h_all)
     with torch.cuda.device(dev):
         st = _stream(dev)
-        check(L.cmh_topk_threshold(_ptr(h_all), nq, q.bits + 1, smp.n, d.n, K, _ptr(b.thr), st), "cmh_topk_threshold")
+        check(L.cmh_topk_threshold(_ptr(h_all), nq, nb, n_sample_all, nd_total, K, _ptr(b.thr), st), "cmh_topk_threshold")
         thr_main = b.thr
         row0 = 0
-        if n_pilot:
-            check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign), n_pilot, q.bits, int(index_base), _ptr(b.thr), 0,
-                                   b.seg_base[0], b.seg_total, b.seg_cap, _ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), st),
-                  "cmh_tc_collect")
-            check(L.cmh_tc_refine(_ptr(b.cand), _ptr(b.cnt), nq, b.seg_base[0], b.seg_base[0] + b.n_segs[0], b.seg_total,
-                                  b.seg_cap, n_pilot, d.n, K, TC_PILOT_SIGMA, _ptr(b.thr), _ptr(b.thr2), st),
-                  "cmh_tc_refine")
+        timed = stats is not None and stats.get("time_collect")
+
+        def mark():
+            if timed:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(torch.cuda.current_stream(dev))
+                stats.setdefault("collect_events", []).append(e)
+
+        if n_pilot_all:
+            # every shard takes part in the exchange, also one too short for a pilot of its own
+            if n_pilot:
+                mark()
+                check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign), n_pilot, q.bits, int(index_base), _ptr(b.thr), 0,
+                                       b.seg_base[0], b.seg_total, b.seg_cap, _ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), st),
+                      "cmh_tc_collect")
+                mark()
+            ph = torch.zeros((nq, nb), dtype=torch.int32, device=dev)
+            over = torch.zeros(nq, dtype=torch.int32, device=dev)
+            if n_pilot:
+                check(L.cmh_tc_cand_hist(_ptr(b.cand), _ptr(b.cnt), nq, b.seg_base[0], b.seg_base[0] + b.n_segs[0],
+                                         b.seg_total, b.seg_cap, nb, _ptr(ph), _ptr(over), st), "cmh_tc_cand_hist")
+            ph, over = comm.all_reduce_sum(ph), comm.all_reduce_max(over)
+            check(L.cmh_tc_choose(_ptr(ph), _ptr(over), nq, nb, n_pilot_all, nd_total, K, TC_PILOT_SIGMA, _ptr(b.thr),
+                                  _ptr(b.thr2), st), "cmh_tc_choose")
             thr_main = b.thr2
             row0 = n_pilot
-        check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign[row0:]), d.n - row0, q.bits, int(index_base) + row0,
-                               _ptr(thr_main), K if tighten else 0, b.seg_base[-1], b.seg_total, b.seg_cap, _ptr(b.cand),
-                               _ptr(b.cnt), _ptr(b.aux), st), "cmh_tc_collect")
+        if d.n - row0 > 0:
+            # tightening uses this launch's own counts: K rows found locally are K rows found globally
+            mark()
+            check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign[row0:]), d.n - row0, q.bits, int(index_base) + row0,
+                                   _ptr(thr_main), K if tighten else 0, b.seg_base[-1], b.seg_total, b.seg_cap,
+                                   _ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), st), "cmh_tc_collect")
+            mark()
+        else:
+            b.cnt[b.seg_base[-1]:].zero_()
+            b.aux.zero_()
+        partial = 1 if comm.world > 1 else 0
         check(L.cmh_topk_finalize(_ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), _ptr(thr_main), nq, b.seg_total, b.seg_cap, K,
-                                  d.n, _ptr(keys), _ptr(b.fail_flags), _ptr(b.fail_count), st), "cmh_topk_finalize")
+                                  nd_total, partial, _ptr(keys), _ptr(b.fail_flags), _ptr(b.fail_count), st),
+              "cmh_topk_finalize")
+        if comm.world > 1:
+            keys = topk_merge(comm.all_gather_stack(keys), K)
+            b.fail_flags = comm.all_reduce_max(b.fail_flags)
+            check(L.cmh_topk_verify(_ptr(keys), _ptr(thr_main), nq, K, nd_total, _ptr(b.fail_flags), _ptr(b.fail_count),
+                                    st), "cmh_topk_verify")
     n_fail = int(b.fail_count.item())
     if stats is not None:
         stats["n_fail"] = n_fail
@@ -441,5 +509,11 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     if n_fail:
         rows = torch.nonzero(b.fail_flags, as_tuple=False).squeeze(1)
         sub = PackedSet(q.sign.index_select(0, rows).contiguous(), None, None, int(rows.numel()), q.bits)
-        keys.index_copy_(0, rows, RankPass(sub, d.with_labels(None, 0), need_labels=False).topk(K, index_base))
+        if exact_fallback is None:
+            if comm.world > 1:
+                raise RuntimeError("a sharded tensor-core top-K needs exact_fallback")
+            redo = RankPass(sub, d.with_labels(None, 0), need_labels=False).topk(K, index_base)
+        else:
+            redo = exact_fallback(sub)
+        keys.index_copy_(0, rows, redo)
     return keys

@@ -4,8 +4,9 @@
 The reference only ever ranks inside `calc_map_k_matrix` (`utils/calc_utils.py:30-31`: distance row + full sort per
 query); this class is that ranking, truncated to the first K entries, for databases far beyond what a per-query
 sort can touch.  The database stays packed in HBM (8 B per 64-bit row: 100M rows = 800 MB); queries stream
-through in chunks; each chunk is two counting passes over the shard (histogram -> threshold -> ordered select)
-and, when sharded, one all-gather + merge.
+through in chunks.  +-1 codes of 64 / 128 bits are searched on the tensor cores (`engine.topk_tc`: int8 GEMM with
+a fused candidate filter, global thresholds, all-gather + merge when sharded); anything else - ternary codes, other
+code lengths, small databases - by two counting passes over the shard (histogram -> threshold -> ordered select).
 """
 from __future__ import annotations
 
@@ -25,12 +26,41 @@ class HammingIndex:
     ``index_base`` is the global row index of the shard's first row; with ``group`` (a `torch.distributed`
     process group, one rank per GPU) `search` returns the global top-K on every rank."""
 
-    def __init__(self, db: PackedSet, index_base: int = 0, group=None):
+    # databases at least this long (all shards together) are searched on the tensor cores; shorter ones by the two
+    # counting passes, whose fixed costs are lower
+    TC_MIN_ROWS = 1_000_000
+    SAMPLE_ROWS = 262_144
+
+    def __init__(self, db: PackedSet, index_base: int = 0, group=None, nd_total: Optional[int] = None):
         if db.labels is not None:
             db = db.with_labels(None, 0)
+        if db.n and db.sign.data_ptr() % 16:
+            # the bulk-copy engine stages 16-byte-aligned tiles; an odd-row view of 64-bit codes is re-homed once
+            db = PackedSet(db.sign.clone(), None if db.valid is None else db.valid.clone(), None, db.n, db.bits)
         self.db = db
         self.index_base = int(index_base)
         self.group = group
+        distributed = group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                            and torch.distributed.get_world_size() > 1)
+        if nd_total is None:
+            nd_total = db.n
+            if distributed:
+                t = torch.tensor([db.n], dtype=torch.int64, device=db.device)
+                torch.distributed.all_reduce(t, group=group)
+                nd_total = int(t.item())
+        self.nd_total = int(nd_total)
+        # every rank must take the same path: the tensor cores need +-1 codes (no valid plane) on ALL shards
+        tc_ok = db.valid is None and _e.tc_supported(db, db)
+        if distributed:
+            t = torch.tensor([1 if tc_ok else 0], dtype=torch.int64, device=db.device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=group)
+            tc_ok = bool(int(t.item()))
+        # a strided sample of the shard: first guess of the per-query thresholds of the tensor-core search
+        self.sample = None
+        if tc_ok and self.nd_total >= self.TC_MIN_ROWS:
+            stride = max(1, db.n // self.SAMPLE_ROWS)
+            rows = db.sign[::stride].contiguous()
+            self.sample = PackedSet(rows, None, None, rows.shape[0], db.bits)
 
     @classmethod
     def from_codes(cls, rB, device=None, index_base: int = 0, group=None) -> "HammingIndex":
@@ -38,19 +68,23 @@ class HammingIndex:
         return cls(_cu.pack_codes(rB, device), index_base, group)
 
     @classmethod
-    def from_packed(cls, words: torch.Tensor, bits: int, index_base: int = 0, group=None) -> "HammingIndex":
+    def from_packed(cls, words: torch.Tensor, bits: int, index_base: int = 0, group=None,
+                    nd_total: Optional[int] = None) -> "HammingIndex":
         """Adopt already packed +-1 codes: int64 / uint64-bit-pattern tensor ``[D, ceil(bits/64)]`` on a GPU,
         padding bits zero."""
         if words.dim() != 2 or words.shape[1] != (bits + 63) // 64:
             raise ValueError(f"packed words must be [D, {(bits + 63) // 64}]")
         if not words.is_cuda:
             raise RuntimeError("packed database must be on a CUDA device")
-        return cls(PackedSet(words.contiguous().view(torch.int64), None, None, words.shape[0], bits), index_base, group)
+        return cls(PackedSet(words.contiguous().view(torch.int64), None, None, words.shape[0], bits), index_base, group,
+                   nd_total)
 
-    def search_packed(self, q: PackedSet, K: int) -> torch.Tensor:
+    def search_packed(self, q: PackedSet, K: int, stats: Optional[dict] = None) -> torch.Tensor:
         """int64 [Q, K] ascending keys ``(2*dist << 32) | global_row`` (-1 pads rows beyond the database)."""
-        ternary = None
-        return _sh.topk_sharded(q, self.db, int(K), self.index_base, self.group, ternary=ternary)
+        if self.sample is not None and q.valid is None and q.bits == self.db.bits and 1 <= int(K) <= _e.TC_MAX_K:
+            return _sh.topk_tc_sharded(q, self.db, int(K), self.index_base, self.nd_total, sample=self.sample,
+                                       group=self.group, stats=stats)
+        return _sh.topk_sharded(q, self.db, int(K), self.index_base, self.group, ternary=None)
 
     def search(self, qB, K: int):
         """Float query codes in -> (dist float32 [Q, K], index int64 [Q, K]) on the device; pads have index -1."""

@@ -88,13 +88,48 @@ def map_k_sharded(q, d_shard, k: Optional[int], nd_total: int, topn: Sequence[in
     return {"map": m, "ap": ap, "n_rel": n_rel, "prec": prec, "pr": pr}
 
 
+class GroupComm:
+    """The exchange steps of `engine.topk_tc` over the ranks of a process group (NCCL on GPUs)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = _world(group)[1]
+
+    def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_reduce_max(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def all_gather_stack(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return t.unsqueeze(0)
+        return _all_gather_stack(t, self.world, self.group)
+
+
 def topk_sharded(q, d_shard, K: int, index_base: int, group=None, eng=_engine,
                  ternary: Optional[bool] = None) -> torch.Tensor:
     """Global top-``K`` keys int64 [Q, K] (ascending, ``-1`` pads) - identical on every rank.
-    ``index_base`` is the global index of this shard's first row."""
+    ``index_base`` is the global index of this shard's first row.  The exact two-pass (popc) path: every rank
+    selects its local top-K, one all-gather, K-way merge."""
     rp = eng.RankPass(q, d_shard, need_labels=False, ternary=ternary)
     local = rp.topk(K, index_base)
     _, world = _world(group)
     if world == 1:
         return local
     return eng.topk_merge(_all_gather_stack(local, world, group), K)
+
+
+def topk_tc_sharded(q, d_shard, K: int, index_base: int, nd_total: int, sample=None, group=None, eng=_engine,
+                    stats: Optional[dict] = None, **kw) -> torch.Tensor:
+    """Global top-``K`` keys on the tensor cores (`engine.topk_tc`): the shards filter with the same global
+    thresholds (all-reduced sample and pilot histograms, a few KB per query chunk), so each contributes only its
+    share of the ~K rows below them; the per-shard results are all-gathered and merged, and the merged K-th key is
+    verified against the thresholds.  Queries that fail the check are redone by `topk_sharded` on every rank."""
+    comm = GroupComm(group)
+    return eng.topk_tc(q, d_shard, K, index_base, sample=sample, comm=comm, nd_total=nd_total, stats=stats,
+                       exact_fallback=lambda sub: topk_sharded(sub, d_shard, K, index_base, group, eng), **kw)

@@ -192,26 +192,36 @@ int cmh_tc_collect(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, i
  * bit 2: accumulators are drained but not scanned.  Outputs are meaningless. */
 int cmh_tc_probe(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits, const int32_t* thr,
                  int seg_total, int seg_cap, uint64_t* cand, uint32_t* cnt, uint32_t* aux, int probe, void* stream);
-/* Thresholds from a pilot launch: segments [seg_lo, seg_hi) hold every row at or below thr_in[q] (a K = 0 launch)
- * among n_seen of the nd rows.  thr_out[q] = the smallest bucket whose cumulative pilot count reaches
- * K*f + sigma*sqrt(K*f) + 4 (f = n_seen / nd), never above thr_in[q]. */
-int cmh_tc_refine(const uint64_t* cand, const uint32_t* cnt, int64_t nq, int seg_lo, int seg_hi, int seg_total,
-                  int seg_cap, int64_t n_seen, int64_t nd, int K, double sigma, const int32_t* thr_in, int32_t* thr_out,
-                  void* stream);
+/* Thresholds from a pilot launch.  Step 1: hist (device uint32 [nq][nb], bucket = Hamming distance) of the candidates
+ * in segments [seg_lo, seg_hi) - every row at or below thr_in[q] among the rows a K = 0 launch scanned - and
+ * overflow[q] (device uint32 [nq]) = 1 when one of those segments lost entries.  A sharded database all-reduces the
+ * histograms (sum) and the flags (max) between the two steps. */
+int cmh_tc_cand_hist(const uint64_t* cand, const uint32_t* cnt, int64_t nq, int seg_lo, int seg_hi, int seg_total,
+                     int seg_cap, int nb, uint32_t* hist, uint32_t* overflow, void* stream);
+/* Step 2: thr_out[q] = the smallest bucket whose cumulative count reaches K*f + sigma*sqrt(K*f) + 4 (f = n_seen / nd,
+ * n_seen = rows behind the histogram), never above thr_in[q]; thr_in[q] when overflow[q] (overflow may be NULL). */
+int cmh_tc_choose(const uint32_t* hist, const uint32_t* overflow, int64_t nq, int nb, int64_t n_seen, int64_t nd, int K,
+                  double sigma, const int32_t* thr_in, int32_t* thr_out, void* stream);
 /* thr[q] from a histogram (cmh_eval_hist, binary mode, nb = bits + 1) over a SAMPLE of n_sample rows of an nd-row
  * shard: smallest bucket whose cumulative sample count reaches K*f + 6*sqrt(K*f) + 8 (f = n_sample / nd), exactly
  * min(K, nd) when n_sample == nd. */
 int cmh_topk_threshold(const uint32_t* hist, int64_t nq, int nb, int64_t n_sample, int64_t nd, int K,
                        int32_t* thr, void* stream);
 /* Per query: K-th distance from the candidates' own histogram over all n_chunks (= seg_total) segments, sort of the
- * candidates at or below it, K smallest keys out (UINT64_MAX pads when nd < K; K <= 4096).  thr_limit (device int32
- * [nq] or NULL): the smallest initial threshold any launch used for the query - buckets above it are incomplete.
- * fail_flags[q] (device uint32 [nq]) = 1 and *fail_count (device uint32) incremented when a candidate segment
- * overflowed, the query holds fewer than min(K, nd) candidates, more than 4096 at or below the K-th distance, or
- * its K-th distance lies above thr_limit: those queries must be re-run through cmh_topk (exact path). */
+ * candidates at or below it, K smallest keys out (UINT64_MAX pads; K <= 4096).  thr_limit (device int32 [nq] or
+ * NULL): the smallest initial threshold any launch used for the query - buckets above it are incomplete.
+ * partial = 0: the segments cover the whole nd-row database; fail_flags[q] (device uint32 [nq]) = 1 and *fail_count
+ * (device uint32) incremented when a candidate segment overflowed, the query holds fewer than min(K, nd) candidates,
+ * more than 4096 at or below the K-th distance, or its K-th distance lies above thr_limit: those queries must be
+ * re-run through cmh_topk (exact path).  partial = 1: the segments cover one shard; whatever the query holds (up to K)
+ * is emitted, only overflow fails, and the merged result is judged by cmh_topk_verify. */
 int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, const uint32_t* aux, const int32_t* thr_limit,
-                      int64_t nq, int n_chunks, int seg_cap, int K, int64_t nd, uint64_t* keys, uint32_t* fail_flags,
-                      uint32_t* fail_count, void* stream);
+                      int64_t nq, int n_chunks, int seg_cap, int K, int64_t nd, int partial, uint64_t* keys,
+                      uint32_t* fail_flags, uint32_t* fail_count, void* stream);
+/* After the merge of per-shard results: fail_flags[q] |= the min(K, nd)-th key is a pad or its distance lies above
+ * thr_limit[q] (an incomplete bucket); *fail_count = number of flagged queries. */
+int cmh_topk_verify(const uint64_t* keys, const int32_t* thr_limit, int64_t nq, int K, int64_t nd, uint32_t* fail_flags,
+                    uint32_t* fail_count, void* stream);
 
 #ifdef __cplusplus
 }

@@ -298,6 +298,81 @@ def test_tc_topk_against_oracle_and_fallback(dev):
     assert torch.equal(got.cpu(), torch.arange(100).expand(3, 100))
 
 
+class _ThreadComm:
+    """Test double of `sharded.GroupComm`: the shards of one database are driven by threads on ONE GPU, and the
+    exchange steps meet at a barrier (what NCCL does between the ranks of a real box)."""
+
+    def __init__(self, world):
+        import threading
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots = [None] * world
+        self.local = threading.local()
+
+    def bind(self, rank):
+        self.local.rank = rank
+
+    def _exchange(self, t):
+        self.slots[self.local.rank] = t
+        self.barrier.wait()
+        got = list(self.slots)
+        self.barrier.wait()
+        return got
+
+    def all_reduce_sum(self, t):
+        torch.cuda.synchronize()
+        return torch.stack(self._exchange(t)).sum(0).to(t.dtype)
+
+    def all_reduce_max(self, t):
+        torch.cuda.synchronize()
+        return torch.stack(self._exchange(t)).max(0).values
+
+    def all_gather_stack(self, t):
+        torch.cuda.synchronize()
+        return torch.stack(self._exchange(t))
+
+
+@pytest.mark.parametrize("bits,world,D,K,pilot", [(64, 2, 3_000_001, 1000, 200_000), (64, 3, 2_000_000, 100, 0),
+                                                  (128, 2, 1_500_000, 500, 150_016)])
+def test_tc_topk_sharded_matches_single(dev, bits, world, D, K, pilot):
+    """Shards that filter with all-reduced (global) thresholds + merge + verify == the exact single-shard ranking."""
+    import threading
+    from cmh_b200 import engine, sharded
+    Q = 300
+    db = engine.synth_codes(500 + bits, 0, D, bits, dev)
+    q = engine.synth_codes(600 + bits, 0, Q, bits, dev)
+    want = engine.RankPass(q, db, need_labels=False).topk(K, 0)
+    comm = _ThreadComm(world)
+    out, errs = [None] * world, []
+
+    def run(rank):
+        try:
+            comm.bind(rank)
+            torch.cuda.set_device(dev)
+            lo, hi = sharded.shard_bounds(D, world, rank)
+            shard = db.rows(lo, hi)
+            if shard.sign.data_ptr() % 16:
+                shard = engine.PackedSet(shard.sign.clone(), None, None, shard.n, shard.bits)
+            smp = engine.PackedSet(shard.sign[::97].contiguous(), None, None, (shard.n + 96) // 97, bits)
+            st = {}
+            out[rank] = (engine.topk_tc(q, shard, K, lo, sample=smp, comm=comm, nd_total=D, stats=st, pilot=pilot,
+                                        exact_fallback=lambda sub: engine.RankPass(sub, db, need_labels=False).topk(K, 0)),
+                         st)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+            comm.barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errs, errs
+    for keys, st in out:
+        assert torch.equal(keys, want)
+        assert st["n_fail"] == 0
+    # each shard collected only its share of the candidates
+    assert sum(int(st["candidates"].sum()) for _, st in out) < 40 * K * Q
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # size-independent properties (sizes beyond what the oracle is asked to do)
 # ---------------------------------------------------------------------------------------------------------------
