@@ -404,7 +404,7 @@ class LocalComm:
 def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Optional[PackedSet] = None,
             cap: int = TC_DEFAULT_CAP, stats: Optional[dict] = None, tighten: bool = True,
             seg_cap: Optional[int] = None, pilot: Optional[int] = None, comm=None, nd_total: Optional[int] = None,
-            exact_fallback=None) -> torch.Tensor:
+            exact_fallback=None, buffers: Optional[dict] = None) -> torch.Tensor:
     """int64 [nq, K] ascending keys, identical to ``RankPass(q, d).topk(K, index_base)`` (to the global stable
     ranking when ``d`` is one shard of a database of ``nd_total`` rows and ``comm`` spans the shards).
 
@@ -415,6 +415,8 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     comm    exchange steps (`LocalComm`, `sharded.GroupComm`): the sample / pilot histograms are all-reduced so that
             every shard filters with the same global thresholds - a shard then contributes only its share of the ~K
             rows below them - and the per-shard results are all-gathered and merged
+    buffers a dict the caller keeps between calls: the multi-GB candidate scratch is allocated once per query-chunk
+            size instead of per call
     exact_fallback(sub_q) -> keys for the queries whose candidate lists came out short or overflowed (the exact
             two-pass path; default: `RankPass.topk` on ``d``, which is only right when unsharded)"""
     if not tc_supported(q, d, K):
@@ -436,13 +438,22 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     if (sample is None and comm.world == 1) or n_pilot <= 0 or n_pilot >= d.n:
         n_pilot = 0                                  # exact thresholds need no refinement
     regions = [n_pilot, d.n - n_pilot] if n_pilot else [d.n]
-    b = TcBuffers(nq, regions, q.bits, cap, dev, seg_cap)
-    counts = torch.tensor([smp.n, n_pilot], dtype=torch.int64, device=dev)
+    bkey = (nq, tuple(regions), q.bits, int(cap), seg_cap, str(dev))
+    b = buffers.get(bkey) if buffers is not None else None
+    if b is None:
+        b = TcBuffers(nq, regions, q.bits, cap, dev, seg_cap)
+        if buffers is not None:
+            buffers.clear()                          # one geometry at a time: the scratch is large
+            buffers[bkey] = b
     if comm.world > 1:
-        counts = comm.all_reduce_sum(counts)
-        n_sample_all, n_pilot_all = (int(v) for v in counts.tolist())
-        if n_pilot_all == 0:
-            n_pilot_all = 0
+        ckey = ("counts", smp.n, n_pilot)
+        got = buffers.get(ckey) if buffers is not None else None
+        if got is None:
+            counts = comm.all_reduce_sum(torch.tensor([smp.n, n_pilot], dtype=torch.int64, device=dev))
+            got = tuple(int(v) for v in counts.tolist())
+            if buffers is not None:
+                buffers[ckey] = got
+        n_sample_all, n_pilot_all = got
     else:
         n_sample_all, n_pilot_all = smp.n, n_pilot
     if smp.n:

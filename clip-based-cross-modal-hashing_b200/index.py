@@ -29,7 +29,7 @@ class HammingIndex:
     # databases at least this long (all shards together) are searched on the tensor cores; shorter ones by the two
     # counting passes, whose fixed costs are lower
     TC_MIN_ROWS = 1_000_000
-    SAMPLE_ROWS = 262_144
+    SAMPLE_ROWS = 65_536
 
     def __init__(self, db: PackedSet, index_base: int = 0, group=None, nd_total: Optional[int] = None):
         if db.labels is not None:
@@ -55,6 +55,7 @@ class HammingIndex:
             t = torch.tensor([1 if tc_ok else 0], dtype=torch.int64, device=db.device)
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=group)
             tc_ok = bool(int(t.item()))
+        self._tc_buffers: dict = {}
         # a strided sample of the shard: first guess of the per-query thresholds of the tensor-core search
         self.sample = None
         if tc_ok and self.nd_total >= self.TC_MIN_ROWS:
@@ -83,7 +84,7 @@ class HammingIndex:
         """int64 [Q, K] ascending keys ``(2*dist << 32) | global_row`` (-1 pads rows beyond the database)."""
         if self.sample is not None and q.valid is None and q.bits == self.db.bits and 1 <= int(K) <= _e.TC_MAX_K:
             return _sh.topk_tc_sharded(q, self.db, int(K), self.index_base, self.nd_total, sample=self.sample,
-                                       group=self.group, stats=stats)
+                                       group=self.group, stats=stats, buffers=self._tc_buffers)
         return _sh.topk_sharded(q, self.db, int(K), self.index_base, self.group, ternary=None)
 
     def search(self, qB, K: int):
