@@ -400,6 +400,9 @@ class LocalComm:
     def all_gather_stack(self, t: torch.Tensor) -> torch.Tensor:
         return t.unsqueeze(0)
 
+    def all_to_all(self, t: torch.Tensor) -> torch.Tensor:
+        return t
+
 
 def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Optional[PackedSet] = None,
             cap: int = TC_DEFAULT_CAP, stats: Optional[dict] = None, tighten: bool = True,
@@ -414,7 +417,8 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
             sample thresholds, and what they hold refines the thresholds for the rest
     comm    exchange steps (`LocalComm`, `sharded.GroupComm`): the sample / pilot histograms are all-reduced so that
             every shard filters with the same global thresholds - a shard then contributes only its share of the ~K
-            rows below them - and the per-shard results are all-gathered and merged
+            rows below them; the per-shard results are exchanged all-to-all (rank r merges the r-th slice of the
+            queries: 1/N of the traffic and of the merge work of an all-gather) and the merged slices all-gathered
     buffers a dict the caller keeps between calls: the multi-GB candidate scratch is allocated once per query-chunk
             size instead of per call
     exact_fallback(sub_q) -> keys for the queries whose candidate lists came out short or overflowed (the exact
@@ -426,11 +430,15 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     dev = q.device
     nq = q.n
     nd_total = d.n if nd_total is None else int(nd_total)
-    keys = torch.empty((nq, K), dtype=torch.int64, device=dev)
+    per_rank = -(-nq // comm.world)                  # queries merged by each rank (the last slice may be padded)
+    keys_all = torch.empty((per_rank * comm.world, K), dtype=torch.int64, device=dev)
+    keys = keys_all[:nq]
     if nq == 0:
         return keys
     if nd_total == 0:
         return keys.fill_(-1)
+    if keys_all.shape[0] > nq:
+        keys_all[nq:].fill_(-1)
     L = _cabi.lib()
     nb = q.bits + 1
     smp = d if sample is None else sample
@@ -507,7 +515,8 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
                                   nd_total, partial, _ptr(keys), _ptr(b.fail_flags), _ptr(b.fail_count), st),
               "cmh_topk_finalize")
         if comm.world > 1:
-            keys = topk_merge(comm.all_gather_stack(keys), K)
+            mine = topk_merge(comm.all_to_all(keys_all.view(comm.world, per_rank, K)), K)     # [per_rank, K]
+            keys = comm.all_gather_stack(mine).view(per_rank * comm.world, K)[:nq]
             b.fail_flags = comm.all_reduce_max(b.fail_flags)
             check(L.cmh_topk_verify(_ptr(keys), _ptr(thr_main), nq, K, nd_total, _ptr(b.fail_flags), _ptr(b.fail_count),
                                     st), "cmh_topk_verify")

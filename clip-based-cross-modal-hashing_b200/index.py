@@ -59,7 +59,9 @@ class HammingIndex:
         # a strided sample of the shard: first guess of the per-query thresholds of the tensor-core search
         self.sample = None
         if tc_ok and self.nd_total >= self.TC_MIN_ROWS:
-            stride = max(1, db.n // self.SAMPLE_ROWS)
+            # SAMPLE_ROWS is the budget of the whole database: a shard contributes its share (the histograms are summed)
+            share = max(4096, self.SAMPLE_ROWS * max(db.n, 1) // max(self.nd_total, 1))
+            stride = max(1, db.n // share)
             rows = db.sign[::stride].contiguous()
             self.sample = PackedSet(rows, None, None, rows.shape[0], db.bits)
 

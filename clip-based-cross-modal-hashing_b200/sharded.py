@@ -110,6 +110,18 @@ class GroupComm:
             return t.unsqueeze(0)
         return _all_gather_stack(t, self.world, self.group)
 
+    def all_to_all(self, t: torch.Tensor) -> torch.Tensor:
+        """t [world, ...]: slice s goes to rank s; returns [world, ...] with slice s received from rank s."""
+        if self.world == 1:
+            return t
+        t = t.contiguous()
+        if dist.get_backend(self.group) == "gloo":       # gloo has no all-to-all: gather everything, keep my column
+            rank = dist.get_rank(self.group)
+            return _all_gather_stack(t, self.world, self.group)[:, rank].contiguous()
+        out = torch.empty_like(t)
+        dist.all_to_all_single(out, t, group=self.group)
+        return out
+
 
 def topk_sharded(q, d_shard, K: int, index_base: int, group=None, eng=_engine,
                  ternary: Optional[bool] = None) -> torch.Tensor:

@@ -331,6 +331,11 @@ class _ThreadComm:
         torch.cuda.synchronize()
         return torch.stack(self._exchange(t))
 
+    def all_to_all(self, t):
+        torch.cuda.synchronize()
+        rank = self.local.rank
+        return torch.stack([x[rank] for x in self._exchange(t)])
+
 
 @pytest.mark.parametrize("bits,world,D,K,pilot", [(64, 2, 3_000_001, 1000, 200_000), (64, 3, 2_000_000, 100, 0),
                                                   (128, 2, 1_500_000, 500, 150_016)])

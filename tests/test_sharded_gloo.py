@@ -79,6 +79,58 @@ def test_sharded_equals_single(tmp_path, world, ternary_frac):
         assert np.array_equal(z["keys"].view(np.uint64), want_keys)       # bit-exact merged ranking
 
 
+def _comm_worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import cpu_engine
+        from cmh_b200 import sharded
+        from oracle import cmh_oracle as orc
+        comm = sharded.GroupComm(None)
+        assert comm.world == world
+        # primitives
+        t = torch.arange(6, dtype=torch.int64) + 10 * rank
+        assert torch.equal(comm.all_reduce_sum(t.clone()), sum(torch.arange(6, dtype=torch.int64) + 10 * r for r in range(world)))
+        assert torch.equal(comm.all_reduce_max(t.clone()), torch.arange(6, dtype=torch.int64) + 10 * (world - 1))
+        x = (torch.arange(world * 4, dtype=torch.int64).view(world, 2, 2) + 100 * rank)
+        got = comm.all_to_all(x)
+        for s in range(world):
+            assert torch.equal(got[s], torch.arange(world * 4, dtype=torch.int64).view(world, 2, 2)[rank] + 100 * s)
+        # the exchange of the tensor-core top-K: global threshold -> partial per-shard lists -> all-to-all by query
+        # slice -> merge -> all-gather of the merged slices
+        q, d, tt = _packed_sets(0.0)
+        K, nq = 25, q.n
+        lo, hi = sharded.shard_bounds(d.n, world, rank)
+        want = orc.topk_counting(tt["q_img"], tt["r_txt"], K).view(np.int64)
+        thr_key = want[:, K - 1] | 0xFFFFFFFF                              # everything up to the K-th distance bucket
+        local = orc.topk_counting(tt["q_img"], tt["r_txt"][lo:hi], K).view(np.int64)
+        local = np.where(local >= 0, local + lo, local)                    # global row index
+        local = np.where((local >= 0) & (local <= thr_key[:, None]), local, -1)  # only rows at or below the threshold
+        per_rank = -(-nq // world)
+        keys_all = torch.full((per_rank * world, K), -1, dtype=torch.int64)
+        keys_all[:nq] = torch.from_numpy(local)
+        mine = cpu_engine.topk_merge(comm.all_to_all(keys_all.view(world, per_rank, K)), K)
+        keys = comm.all_gather_stack(mine).view(per_rank * world, K)[:nq]
+        np.save(os.path.join(out_dir, f"c{rank}.npy"), keys.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_group_comm_exchange(tmp_path, world):
+    port = _free_port()
+    mp.spawn(_comm_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    from oracle import cmh_oracle as orc
+    _, _, t = _packed_sets(0.0)
+    want = orc.topk_counting(t["q_img"], t["r_txt"], 25)
+    for r in range(world):
+        assert np.array_equal(np.load(os.path.join(str(tmp_path), f"c{r}.npy")).view(np.uint64), want)
+
+
 def test_shard_bounds_cover_rows():
     from cmh_b200.sharded import shard_bounds
     for n in (0, 1, 7, 100, 100_000_000):
