@@ -69,7 +69,9 @@ static_assert(TC_REGS_MMA * TC_MMA_WARPS * 32 + TC_REGS_PROD * TC_PROD_WARPS * 3
 constexpr int TC_RING = 8;        // packed database tiles in flight (bulk copies)
 constexpr int TC_MAX_CHUNKS = 1024;  // candidate segments per query (cmh_topk_finalize walks them)
 constexpr int TC_REFRESH = 16;    // tiles (per epilogue group) between threshold refreshes
-constexpr int TC_PARK = 4;        // lanes of a warp whose flagged slices are parked per round of the hit path
+constexpr int TC_PARK = 4;        // lanes of a warp that share one parking slot of the hit path
+constexpr int TC_BACKLOG = 2;     // parking slots per epilogue warp
+constexpr int TC_PARK_WORDS = TC_PARK * 36 + 4;   // per lane 32 registers + a block bitmap (16-byte rows); then lane mask, first row
 constexpr int TC_BIAS_SLOTS = 12; // K slots of the bias step that carry weight 127 (the 13th carries weight 1)
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------------------
@@ -191,6 +193,59 @@ struct TcArgs {
     int probe;              // measurement aid (cmh_tc_probe): 1 = no tcgen05.mma, 2 = no TMEM drain, 4 = drain without scan
 };
 
+// Working off one parked slice of the hit path (see the epilogue).  Out of line on purpose: ONE copy of this code in
+// the kernel - the epilogue's instruction footprint decides whether the instruction cache holds the pipeline.
+// `mine`: this lane's 32 parked registers + the bitmap of the 8-register blocks whose partial AND showed a flag.
+template <int WORDS>
+__device__ __noinline__ uint32_t tc_work_off(const uint32_t* mine, int64_t row0, int64_t c_end, int thr, int thr0,
+                                             int dot_thr0, int bits, uint64_t* seg, uint32_t pos, uint32_t seg_cap,
+                                             uint32_t* hq, uint32_t index_base, bool store) {
+    constexpr int FIELD = WORDS == 1 ? 8 : 10;
+    constexpr bool PACKED = WORDS == 1;
+    constexpr uint32_t FLAG_LO = 1u << (FIELD - 1), FLAG_HI = 1u << (2 * FIELD - 1);
+    constexpr uint32_t FLAGS = PACKED ? (FLAG_LO | FLAG_HI) * 0x10001u : (FLAG_LO | FLAG_HI);
+    uint32_t blocks = mine[32];
+#pragma unroll 1
+    while (blocks) {
+        const int b = __ffs(blocks) - 1;
+        blocks &= blocks - 1;
+        const uint4 w0 = *reinterpret_cast<const uint4*>(mine + 8 * b);
+        const uint4 w1 = *reinterpret_cast<const uint4*>(mine + 8 * b + 4);
+        uint32_t regs = ((~w0.x & FLAGS) ? 1u : 0u) | ((~w0.y & FLAGS) ? 2u : 0u) | ((~w0.z & FLAGS) ? 4u : 0u) |
+                        ((~w0.w & FLAGS) ? 8u : 0u) | ((~w1.x & FLAGS) ? 16u : 0u) | ((~w1.y & FLAGS) ? 32u : 0u) |
+                        ((~w1.z & FLAGS) ? 64u : 0u) | ((~w1.w & FLAGS) ? 128u : 0u);
+#pragma unroll 1
+        while (regs) {
+            const int r = 8 * b + __ffs(regs) - 1;
+            regs &= regs - 1;
+            const uint32_t xr = mine[r];
+            uint32_t fl = ~xr & FLAGS;
+#pragma unroll 1
+            while (fl) {
+                const int bit = 31 - __clz(fl);
+                fl &= ~(1u << bit);
+                // packed: bit 7 / 15 = column 2r, field 0 / 1; bit 23 / 31 = column 2r + 1, field 0 / 1
+                const int col = PACKED ? 2 * r + (bit >> 4) : r;
+                const int f = PACKED ? ((bit >> 3) & 1) : (bit >= FIELD ? 1 : 0);
+                // acc = e1 + B * e2 with e1 = dot1 - T0, e2 = dot2 - T0 + 1 (no wrap): decode the flagged field
+                const int val = PACKED ? ((bit >> 4) ? (int)xr >> 16 : (int)(xr << 16) >> 16) : (int)xr;
+                const int e1 = (int)((uint32_t)val << (32 - FIELD)) >> (32 - FIELD);
+                const int dot = f ? ((val - e1) >> FIELD) + dot_thr0 - 1 : e1 + dot_thr0;
+                const int dist = (bits - dot) >> 1;
+                const int64_t row = row0 + col + f * TC_NM;
+                if (dist <= thr && row < c_end) {
+                    if (store) {
+                        if (pos < seg_cap) seg[pos] = ((uint64_t)(uint32_t)(2 * dist) << 32) | (index_base + (uint32_t)row);
+                        if (hq != nullptr) atomicAdd(hq + min(thr0 - dist, 3), 1u);
+                    }
+                    ++pos;
+                }
+            }
+        }
+    }
+    return pos;
+}
+
 // smem: [A: T tiles x {+-1, +-S, bias digits}][B: STAGES tiles][bias weights][packed ring][barriers][tmem slot][park]
 template <int WORDS, int T, int TC_STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs a) {
@@ -221,7 +276,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
     uint64_t* r_full = bars + 2 * TC_STAGES + 2 * TC_BUFS;               // [RING] bulk copy -> producers
     uint64_t* r_empty = bars + 2 * TC_STAGES + 2 * TC_BUFS + TC_RING;    // [RING] producers -> bulk copy issuer
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2 * TC_BUFS + 2 * TC_RING);
-    uint32_t* scratch = tmem_slot + 4;           // [EPI_WARPS][TC_PARK][32] parked slices of the hit path (16-byte aligned)
+    uint32_t* scratch = tmem_slot + 4;           // [EPI_WARPS][TC_BACKLOG][TC_PARK_WORDS] parked slices of the hit path
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t q0 = (int64_t)blockIdx.x * (T * TC_M);
@@ -426,55 +481,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
         uint32_t* hq = (a.K > 0 && live) ? a.aux[q].h : nullptr;
         uint32_t pos = 0;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + grp * TC_NM;
-        // The hit path.  A lane whose slice holds a flagged row parks its 32 registers in a small shared-memory slot
-        // and walks them with ONE rolled loop (dynamic index): the code is a few dozen instructions per scan site
-        // instead of 32 unrolled sites, and nothing in it waits - the candidate segment is private to the thread (one
-        // query of one chunk), so the slot is a register counter, the key goes straight to global memory and the
-        // tightening statistics are a fire-and-forget RED.  Up to TC_PARK lanes of a warp per round.
-        uint32_t* park = scratch + ew * (TC_PARK * 32);
-        auto collect = [&](const uint32_t (&v)[32], bool flagged, int64_t row0) {
+        // The hit path, taken out of the pipeline's round trip.  A slice that holds a flagged row is PARKED: the flagged
+        // lanes (up to TC_PARK of a warp) copy their 32 registers and a bitmap of the flagged ones into a
+        // shared-memory slot, and the warp goes on draining.  The backlog (TC_BACKLOG slots per warp) is worked off
+        // while the warp would otherwise wait for its next accumulator tile - the pipeline is bound by that tile's round
+        // trip, so anything done between the drain and the next wait used to delay the release of the next buffer.
+        // Working a slot off is ONE rolled loop over the flagged registers (dynamic index into the slot), and nothing in
+        // it waits: the candidate segment is private to the thread (one query of one chunk), so the position is a
+        // register counter, the key goes straight to global memory and the tightening statistics are a
+        // fire-and-forget RED.
+        uint32_t* park = scratch + ew * (TC_BACKLOG * TC_PARK_WORDS);
+        int n_parked = 0, head = 0;                      // warp-uniform
+        auto work_off = [&]() {                          // the oldest slot
+            const uint32_t* slot = park + head * TC_PARK_WORDS;
+            const uint32_t mask = slot[TC_PARK * 36];
+            const int64_t row0 = (int64_t)(((uint64_t)slot[TC_PARK * 36 + 2] << 32) | slot[TC_PARK * 36 + 1]);
+            if (((mask >> lane) & 1u) && live && !(a.probe & 16))
+                pos = tc_work_off<WORDS>(slot + __popc(mask & lanemask_lt()) * 36, row0, c_end, thr, thr0, dot_thr0, a.bits,
+                                         seg, pos, (uint32_t)a.seg_cap, hq, (uint32_t)a.index_base, !(a.probe & 8));
+            __syncwarp();                                // the slot may be overwritten now
+            head = (head + 1) % TC_BACKLOG;
+            --n_parked;
+        };
+        auto park_slice = [&](const uint32_t (&v)[32], const uint32_t (&ab)[4], bool flagged, int64_t row0) {
             uint32_t pend = __ballot_sync(0xffffffffu, flagged);
-            while (pend) {                       // warp-uniform
-                const int rank = __popc(pend & lanemask_lt());
-                const bool mine = ((pend >> lane) & 1u) && rank < TC_PARK;
-                if (mine) {
-                    uint32_t regs = 0;           // registers of the slice that hold a flagged row
+            if (a.probe & 32) pend = 0;
+            while (pend) {                               // warp-uniform
+                if (n_parked == TC_BACKLOG) work_off();  // backlog full: this one is paid for on the spot
+                uint32_t take = pend;                    // the lowest TC_PARK flagged lanes
 #pragma unroll
-                    for (int r = 0; r < 32; ++r) regs |= ((~v[r] & FLAGS) != 0u ? 1u : 0u) << r;
+                for (int k = 0; k < TC_PARK; ++k) take &= take - 1;
+                take = pend & ~take;
+                uint32_t* slot = park + ((head + n_parked) % TC_BACKLOG) * TC_PARK_WORDS;
+                if ((take >> lane) & 1u) {               // 8 x 16-byte stores: parking must stay cheap, it is on the clock
+                    uint32_t* mine = slot + __popc(take & lanemask_lt()) * 36;
 #pragma unroll
                     for (int r = 0; r < 32; r += 4)
-                        *reinterpret_cast<uint4*>(park + rank * 32 + r) = make_uint4(v[r], v[r + 1], v[r + 2], v[r + 3]);
-#pragma unroll 1
-                    while (regs) {
-                        const int r = __ffs(regs) - 1;
-                        regs &= regs - 1;
-                        const uint32_t xr = park[rank * 32 + r];
-                        uint32_t fl = ~xr & FLAGS;
-#pragma unroll 1
-                        while (fl) {
-                            const int bit = 31 - __clz(fl);
-                            fl &= ~(1u << bit);
-                            // packed: bit 7 / 15 = column 2r, field 0 / 1; bit 23 / 31 = column 2r + 1, field 0 / 1
-                            const int col = PACKED ? 2 * r + (bit >> 4) : r;
-                            const int f = PACKED ? ((bit >> 3) & 1) : (bit >= FIELD ? 1 : 0);
-                            // acc = e1 + B * e2, e1 = dot1 - T0, e2 = dot2 - T0 + 1 (no wrap): decode the flagged field
-                            const int val = PACKED ? ((bit >> 4) ? (int)xr >> 16 : (int)(xr << 16) >> 16) : (int)xr;
-                            const int e1 = (int)((uint32_t)val << (32 - FIELD)) >> (32 - FIELD);
-                            const int dot = f ? ((val - e1) >> FIELD) + dot_thr0 - 1 : e1 + dot_thr0;
-                            const int dist = (a.bits - dot) >> 1;
-                            const int64_t row = row0 + col + f * TC_NM;
-                            if (dist <= thr && row < c_end && live) {
-                                if (pos < (uint32_t)a.seg_cap)
-                                    seg[pos] = ((uint64_t)(uint32_t)(2 * dist) << 32) | (uint32_t)(a.index_base + row);
-                                if (hq != nullptr) atomicAdd(hq + min(thr0 - dist, 3), 1u);
-                                ++pos;
-                            }
-                        }
-                    }
-                }
-                __syncwarp();                    // the slots are reused by the next round
+                        *reinterpret_cast<uint4*>(mine + r) = make_uint4(v[r], v[r + 1], v[r + 2], v[r + 3]);
+                    uint32_t blocks = 0;
 #pragma unroll
-                for (int k = 0; k < TC_PARK; ++k) pend &= pend - 1;
+                    for (int b = 0; b < 4; ++b) blocks |= ((ab[b] & FLAGS) != FLAGS ? 1u : 0u) << b;
+                    mine[32] = blocks;
+                }
+                if (lane == 0) {
+                    slot[TC_PARK * 36] = take;
+                    slot[TC_PARK * 36 + 1] = (uint32_t)row0;
+                    slot[TC_PARK * 36 + 2] = (uint32_t)((uint64_t)row0 >> 32);
+                }
+                __syncwarp();
+                ++n_parked;
+                pend &= ~take;
             }
         };
         // one slice (32 registers: 64 or 128 rows): AND-reduce, one mask test, one vote; the hit path is rare
@@ -492,7 +548,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
                 ab[b] = (v[8 * b] & v[8 * b + 1] & v[8 * b + 2]) & (v[8 * b + 3] & v[8 * b + 4] & v[8 * b + 5]) &
                         (v[8 * b + 6] & v[8 * b + 7]);
             const bool flagged = ((ab[0] & ab[1] & ab[2] & ab[3]) & FLAGS) != FLAGS;
-            if (__any_sync(0xffffffffu, flagged)) collect(v, flagged, r0);
+            if (__any_sync(0xffffffffu, flagged)) park_slice(v, ab, flagged, r0);
         };
         auto release = [&]() {                   // the values are in registers: the buffer goes back to its issuer
             tc_fence_before();
@@ -504,6 +560,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
             const int i = it / T;
             const int64_t row0 = c_begin + (int64_t)i * TC_N;
             if (qrow == 0) TC_TRACE(2 + grp, round, 0);
+            // the backlog of parked hits is worked off in the time this warp would spend waiting for its tile
+            while (n_parked > 0 && !__any_sync(0xffffffffu, mbar_test(&t_full[grp], round & 1))) work_off();
             mbar_wait(&t_full[grp], round & 1);
             tc_fence_after();
             if (qrow == 0) TC_TRACE(2 + grp, round, 1);
@@ -545,6 +603,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
             }
             if (qrow == 0) TC_TRACE(2 + grp, round, 4);
         }
+        while (n_parked > 0) work_off();
         if (live) {
             a.cnt[(int64_t)seg_id * a.nq + q] = pos;
             if (pos > (uint32_t)a.seg_cap) a.aux[q].force_fail = 1u;
@@ -744,7 +803,7 @@ static size_t tc_smem_bytes(int words) {
     const int st = tc_stages(words), T = tc_T(words);
     return (size_t)T * (2 * TC_M * words * 64 + TC_M * 32) + (size_t)st * TC_N * words * 64 + TC_NM * 32 +
            (size_t)TC_RING * TC_N * words * 8 + (2 * st + 2 * TC_BUFS + 2 * TC_RING) * 8 + 16 +
-           (size_t)TC_EPI_WARPS * TC_PARK * 32 * 4;
+           (size_t)TC_EPI_WARPS * TC_BACKLOG * TC_PARK_WORDS * 4;
 }
 
 extern "C" int cmh_tc_supported(int bits, int ternary) {
@@ -826,7 +885,7 @@ extern "C" int cmh_tc_collect(const uint64_t* q_sign, int64_t nq, const uint64_t
 extern "C" int cmh_tc_probe(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits,
                             const int32_t* thr, int seg_total, int seg_cap, uint64_t* cand, uint32_t* cnt, uint32_t* aux,
                             int probe, void* stream) {
-    CMH_REQUIRE(probe >= 0 && probe < 8, CMH_ERR_ARG, "cmh_tc_probe: probe=%d", probe);
+    CMH_REQUIRE(probe >= 0 && probe < 64, CMH_ERR_ARG, "cmh_tc_probe: probe=%d", probe);
     return tc_collect_impl(q_sign, nq, d_sign, nd, bits, 0, thr, 0, 0, seg_total, seg_cap, cand, cnt, aux, probe, stream);
 }
 

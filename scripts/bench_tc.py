@@ -42,7 +42,7 @@ t_static = timed(lambda: collect(0, b.thr))
 c_static = b.cnt.sum(0).cpu().float(); seg_static_max = int(b.cnt.max())
 t_collect = timed(lambda: collect(K, b.thr))
 c = b.cnt.sum(0).cpu().float(); seg_max = int(b.cnt.max())
-t_final = timed(lambda: engine.check(L.cmh_topk_finalize(p(b.cand), p(b.cnt), p(b.aux), p(b.thr), Q, b.seg_total, b.seg_cap, K, D,
+t_final = timed(lambda: engine.check(L.cmh_topk_finalize(p(b.cand), p(b.cnt), p(b.aux), p(b.thr), Q, b.seg_total, b.seg_cap, K, D, 0,
                                                          p(keys), p(b.fail_flags), p(b.fail_count), st)))
 n_fail = int(b.fail_count.item())
 # exact thresholds (the K-th distance itself): the least work the hit path can be given
@@ -66,6 +66,11 @@ if PROBES:
                                                       p(b.cand), p(b.cnt), p(b.aux), mode, st)))
         out[f"probe_{name}_ms"] = t
         out[f"probe_{name}_pairs_per_clk_sm"] = Q * D / (t * 1e-3) / 148 / 1.965e9
+if os.environ.get("HITPROBES", "0") == "1":
+    for name, mode in (("hit_full", 0), ("hit_nostore", 8), ("hit_nowork", 16), ("hit_nopark", 32)):
+        t = timed(lambda: engine.check(L.cmh_tc_probe(p(q.sign), Q, p(db.sign), D, BITS, p(b.thr), b.seg_total, b.seg_cap,
+                                                      p(b.cand), p(b.cnt), p(b.aux), mode, st)))
+        out[f"probe_{name}_ms"] = t
 stats = {}
 t_total = timed(lambda: engine.topk_tc(q, db, K, 0, sample=sample, cap=CAP, stats=stats))
 out["topk_tc_total_ms"] = t_total
