@@ -248,6 +248,9 @@ def pr_curve(qB, rB, query_L, retrieval_L, rank=0):
     return P.cpu(), R.cpu()
 
 
+_TC_MIN_ROWS = 1_000_000
+
+
 def topk_hamming(qB, rB, K: int, rank=0):
     """First ``K`` entries of the stable ascending-distance ranking of every query (`utils/calc_utils.py:30-31`
     truncated).  Returns (dist float32 [Q, K'], index int64 [Q, K']) on the device, K' = min(K, D)."""
@@ -256,6 +259,11 @@ def topk_hamming(qB, rB, K: int, rank=0):
     if kk <= 0 or q.n == 0:
         return (torch.empty((q.n, 0), dtype=torch.float32, device=q.device),
                 torch.empty((q.n, 0), dtype=torch.int64, device=q.device))
-    rp = _e.RankPass(q, d, need_labels=False)
-    keys = rp.topk(kk)
+    if d.n >= _TC_MIN_ROWS and _e.tc_supported(q, d, kk):
+        # +-1 codes of 64 / 128 bits against a large database: int8 tcgen05 GEMM with the fused candidate filter
+        stride = max(1, d.n // 65_536)
+        rows = d.sign[::stride].contiguous()
+        keys = _e.topk_tc(q, d, kk, sample=_e.PackedSet(rows, None, None, rows.shape[0], d.bits))
+    else:
+        keys = _e.RankPass(q, d, need_labels=False).topk(kk)
     return (keys >> 32).to(torch.float32) * 0.5, keys & 0xFFFFFFFF

@@ -407,7 +407,7 @@ class LocalComm:
 def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Optional[PackedSet] = None,
             cap: int = TC_DEFAULT_CAP, stats: Optional[dict] = None, tighten: bool = True,
             seg_cap: Optional[int] = None, pilot: Optional[int] = None, comm=None, nd_total: Optional[int] = None,
-            exact_fallback=None, buffers: Optional[dict] = None) -> torch.Tensor:
+            exact_fallback=None, buffers: Optional[dict] = None, ready=None) -> torch.Tensor:
     """int64 [nq, K] ascending keys, identical to ``RankPass(q, d).topk(K, index_base)`` (to the global stable
     ranking when ``d`` is one shard of a database of ``nd_total`` rows and ``comm`` spans the shards).
 
@@ -419,6 +419,9 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
             every shard filters with the same global thresholds - a shard then contributes only its share of the ~K
             rows below them; the per-shard results are exchanged all-to-all (rank r merges the r-th slice of the
             queries: 1/N of the traffic and of the merge work of an all-gather) and the merged slices all-gathered
+    ready   [(row_end, torch.cuda.Event), ...] in row order: rows below row_end of ``d`` are valid once the event has
+            completed (a database that is still being uploaded on another stream); the scan is cut at those
+            boundaries and every launch waits only for the rows it reads
     buffers a dict the caller keeps between calls: the multi-GB candidate scratch is allocated once per query-chunk
             size instead of per call
     exact_fallback(sub_q) -> keys for the queries whose candidate lists came out short or overflowed (the exact
@@ -445,7 +448,16 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     n_pilot = tc_pilot_rows(d.n) if pilot is None else int(pilot)
     if (sample is None and comm.world == 1) or n_pilot <= 0 or n_pilot >= d.n:
         n_pilot = 0                                  # exact thresholds need no refinement
-    regions = [n_pilot, d.n - n_pilot] if n_pilot else [d.n]
+    cuts = sorted({0, n_pilot, d.n} | {int(e) for e, _ in (ready or ()) if n_pilot < int(e) < d.n})
+    spans = [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]] or [(0, 0)]
+    regions = [hi - lo for lo, hi in spans]
+
+    def wait_rows(hi: int) -> None:
+        for end, ev in (ready or ()):
+            if int(end) >= hi:
+                torch.cuda.current_stream(dev).wait_event(ev)
+                return
+
     bkey = (nq, tuple(regions), q.bits, int(cap), seg_cap, str(dev))
     b = buffers.get(bkey) if buffers is not None else None
     if b is None:
@@ -485,6 +497,7 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
         if n_pilot_all:
             # every shard takes part in the exchange, also one too short for a pilot of its own
             if n_pilot:
+                wait_rows(n_pilot)
                 mark()
                 check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign), n_pilot, q.bits, int(index_base), _ptr(b.thr), 0,
                                        b.seg_base[0], b.seg_total, b.seg_cap, _ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), st),
@@ -500,14 +513,16 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
                                   _ptr(b.thr2), st), "cmh_tc_choose")
             thr_main = b.thr2
             row0 = n_pilot
-        if d.n - row0 > 0:
+        main = [(i, lo, hi) for i, (lo, hi) in enumerate(spans) if lo >= row0 and hi > lo]
+        for i, lo, hi in main:
             # tightening uses this launch's own counts: K rows found locally are K rows found globally
+            wait_rows(hi)
             mark()
-            check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign[row0:]), d.n - row0, q.bits, int(index_base) + row0,
-                                   _ptr(thr_main), K if tighten else 0, b.seg_base[-1], b.seg_total, b.seg_cap,
+            check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign[lo:]), hi - lo, q.bits, int(index_base) + lo,
+                                   _ptr(thr_main), K if tighten else 0, b.seg_base[i], b.seg_total, b.seg_cap,
                                    _ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), st), "cmh_tc_collect")
             mark()
-        else:
+        if not main:
             b.cnt[b.seg_base[-1]:].zero_()
             b.aux.zero_()
         partial = 1 if comm.world > 1 else 0

@@ -31,7 +31,9 @@ class HammingIndex:
     TC_MIN_ROWS = 1_000_000
     SAMPLE_ROWS = 65_536
 
-    def __init__(self, db: PackedSet, index_base: int = 0, group=None, nd_total: Optional[int] = None):
+    def __init__(self, db: PackedSet, index_base: int = 0, group=None, nd_total: Optional[int] = None,
+                 sample: Optional[PackedSet] = None, ready=None):
+        self._ready = ready                      # [(row_end, event)]: an upload still in flight (`from_packed_host`)
         if db.labels is not None:
             db = db.with_labels(None, 0)
         if db.n and db.sign.data_ptr() % 16:
@@ -58,7 +60,9 @@ class HammingIndex:
         self._tc_buffers: dict = {}
         # a strided sample of the shard: first guess of the per-query thresholds of the tensor-core search
         self.sample = None
-        if tc_ok and self.nd_total >= self.TC_MIN_ROWS:
+        if sample is not None:
+            self.sample = sample if tc_ok and self.nd_total >= self.TC_MIN_ROWS else None
+        elif tc_ok and self.nd_total >= self.TC_MIN_ROWS:
             # SAMPLE_ROWS is the budget of the whole database: a shard contributes its share (the histograms are summed)
             share = max(4096, self.SAMPLE_ROWS * max(db.n, 1) // max(self.nd_total, 1))
             stride = max(1, db.n // share)
@@ -82,11 +86,58 @@ class HammingIndex:
         return cls(PackedSet(words.contiguous().view(torch.int64), None, None, words.shape[0], bits), index_base, group,
                    nd_total)
 
+    @classmethod
+    def from_packed_host(cls, words: torch.Tensor, bits: int, index_base: int = 0, group=None,
+                         nd_total: Optional[int] = None, pieces: int = 4, out: Optional[torch.Tensor] = None,
+                         device=None) -> "HammingIndex":
+        """Upload packed +-1 codes from (pinned) host memory WITHOUT waiting for the copy: the rows travel in
+        ``pieces`` ranges on a copy stream, and the first search scans each range as soon as it has landed (the
+        pilot rows first), so the upload of a fresh database hides behind the search that needs it.
+        ``out``: optional device tensor [D, words] to upload into (reused between calls)."""
+        if words.is_cuda:
+            return cls.from_packed(words, bits, index_base, group, nd_total)
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        nwords = (bits + 63) // 64
+        if words.dim() != 2 or words.shape[1] != nwords:
+            raise ValueError(f"packed words must be [D, {nwords}]")
+        n = words.shape[0]
+        dst = torch.empty((n, nwords), dtype=torch.int64, device=dev) if out is None else out
+        if tuple(dst.shape) != (n, nwords) or dst.dtype != torch.int64 or dst.data_ptr() % 16:
+            raise ValueError("out must be a 16-byte aligned int64 [D, words] device tensor")
+        words = words.view(torch.int64)
+        # the threshold sample comes from the host copy (a strided gather of ~64K rows), not from rows in flight
+        total = n if nd_total is None else int(nd_total)
+        share = max(4096, cls.SAMPLE_ROWS * max(n, 1) // max(total, 1))
+        smp_rows = words[::max(1, n // share)].contiguous()
+        sample = PackedSet(smp_rows.to(dev, non_blocking=True), None, None, smp_rows.shape[0], bits)
+        copy_stream = torch.cuda.Stream(dev)
+        copy_stream.wait_stream(torch.cuda.current_stream(dev))      # `out` may still be read by earlier work
+        n_pilot = _e.tc_pilot_rows(n)
+        ends = sorted({e for e in ([n_pilot] if n_pilot else []) +
+                       [n_pilot + (n - n_pilot) * (i + 1) // pieces // 256 * 256 for i in range(pieces - 1)] + [n]
+                       if 0 < e <= n})
+        ready, lo = [], 0
+        with torch.cuda.stream(copy_stream):
+            for hi in ends:
+                dst[lo:hi].copy_(words[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                ready.append((hi, ev))
+                lo = hi
+        return cls(PackedSet(dst, None, None, n, bits), index_base, group, nd_total, sample=sample, ready=ready)
+
+    def _upload_done(self) -> None:
+        if self._ready:
+            torch.cuda.current_stream(self.db.device).wait_event(self._ready[-1][1])
+            self._ready = None
+
     def search_packed(self, q: PackedSet, K: int, stats: Optional[dict] = None) -> torch.Tensor:
         """int64 [Q, K] ascending keys ``(2*dist << 32) | global_row`` (-1 pads rows beyond the database)."""
         if self.sample is not None and q.valid is None and q.bits == self.db.bits and 1 <= int(K) <= _e.TC_MAX_K:
+            ready, self._ready = self._ready, None       # only the first search can overlap the upload
             return _sh.topk_tc_sharded(q, self.db, int(K), self.index_base, self.nd_total, sample=self.sample,
-                                       group=self.group, stats=stats, buffers=self._tc_buffers)
+                                       group=self.group, stats=stats, buffers=self._tc_buffers, ready=ready)
+        self._upload_done()
         return _sh.topk_sharded(q, self.db, int(K), self.index_base, self.group, ternary=None)
 
     def search(self, qB, K: int):
