@@ -259,11 +259,11 @@ def main_native(args):
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):
-        keys = index.search_packed(q_packed, K, stats={"time_collect": True})   # the timed code path, kernels loaded
+        keys = index.search_packed(q_packed, K, stats={"time_collect": True, "time_phases": True})   # the timed code path
     barrier()
     t_region0 = time.perf_counter()
     launches0 = lib.cmh_launch_count()
-    stats = {"time_collect": True}
+    stats = {"time_collect": True, "time_phases": True}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -279,6 +279,11 @@ def main_native(args):
 
     # ---- dominant kernel (tc_collect_kernel: pilot + main launch of every step), timed live by the events the
     # search recorded around its launches on the launching stream ---------------------------------------------
+    phases = {}
+    pe = stats.get("phase_events", [])
+    for (n0, a), (n1, b) in zip(pe, pe[1:]):
+        if n1 != "start":
+            phases[n1] = phases.get(n1, 0.0) + a.elapsed_time(b) / max(1, args.steps)
     ev = stats.get("collect_events", [])
     collect_ms = sum(ev[i].elapsed_time(ev[i + 1]) for i in range(0, len(ev), 2)) / max(1, args.steps)
     n_collect = len(ev) // 2 / max(1, args.steps)
@@ -403,7 +408,7 @@ def main_native(args):
             "peak_source": ("2 x MEASURED_PEAKS.json bf16_tflops (burst)" if bf16 else "fallback 2 x 1500 TFLOP/s") +
                            ": kind::i8 has twice the MAC rate of kind::f16",
             "algorithmic_ops_per_pair": ops_per_pair, "pairs_per_launch_set": pairs_shard,
-            "kernel_ms_per_step": collect_ms,
+            "kernel_ms_per_step": collect_ms, "phase_ms_per_step": phases,
             "in_situ_ceilings_ms": ceilings,
             "note": "the kernel issues 5 K-steps per 4 algorithmic ones (the per-query threshold rides in a bias K-step), "
                     "so 0.8 is the highest fraction this design can reach; mma_only / drain_only / no_hits are the same "

@@ -476,6 +476,10 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
         n_sample_all, n_pilot_all = got
     else:
         n_sample_all, n_pilot_all = smp.n, n_pilot
+    if stats is not None and stats.get("time_phases"):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream(dev))
+        stats.setdefault("phase_events", []).append(("start", e))
     if smp.n:
         h_all, _ = RankPass(q.with_labels(None, 0), smp.with_labels(None, 0), need_labels=False).hist()
     else:
@@ -493,6 +497,14 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
                 e = torch.cuda.Event(enable_timing=True)
                 e.record(torch.cuda.current_stream(dev))
                 stats.setdefault("collect_events", []).append(e)
+
+        def phase(name):
+            if stats is not None and stats.get("time_phases"):
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(torch.cuda.current_stream(dev))
+                stats.setdefault("phase_events", []).append((name, e))
+
+        phase("thresholds_done")
 
         if n_pilot_all:
             # every shard takes part in the exchange, also one too short for a pilot of its own
@@ -513,6 +525,7 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
                                   _ptr(b.thr2), st), "cmh_tc_choose")
             thr_main = b.thr2
             row0 = n_pilot
+        phase("pilot_done")
         main = [(i, lo, hi) for i, (lo, hi) in enumerate(spans) if lo >= row0 and hi > lo]
         for i, lo, hi in main:
             # tightening uses this launch's own counts: K rows found locally are K rows found globally
@@ -525,16 +538,19 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
         if not main:
             b.cnt[b.seg_base[-1]:].zero_()
             b.aux.zero_()
+        phase("main_done")
         partial = 1 if comm.world > 1 else 0
         check(L.cmh_topk_finalize(_ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), _ptr(thr_main), nq, b.seg_total, b.seg_cap, K,
                                   nd_total, partial, _ptr(keys), _ptr(b.fail_flags), _ptr(b.fail_count), st),
               "cmh_topk_finalize")
+        phase("finalize_done")
         if comm.world > 1:
             mine = topk_merge(comm.all_to_all(keys_all.view(comm.world, per_rank, K)), K)     # [per_rank, K]
             keys = comm.all_gather_stack(mine).view(per_rank * comm.world, K)[:nq]
             b.fail_flags = comm.all_reduce_max(b.fail_flags)
             check(L.cmh_topk_verify(_ptr(keys), _ptr(thr_main), nq, K, nd_total, _ptr(b.fail_flags), _ptr(b.fail_count),
                                     st), "cmh_topk_verify")
+    phase("exchange_done")
     n_fail = int(b.fail_count.item())
     if stats is not None:
         stats["n_fail"] = n_fail
