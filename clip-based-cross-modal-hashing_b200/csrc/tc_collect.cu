@@ -636,8 +636,6 @@ __global__ void __launch_bounds__(256) topk_threshold_kernel(const uint32_t* __r
 constexpr int FIN_MAX = 4096;
 constexpr int FIN_BINS = 129;   // bits <= 128 on the tensor path
 constexpr int FIN_THREADS = 512;
-constexpr int FIN_CAP = 6144;   // candidates per query the fast path holds in shared memory (48 KB: 3 CTAs per SM)
-constexpr int FIN_SEGS = 1024;  // segments per query the fast path of the finalize kernel can index
 
 // ---- thresholds from the candidates of a pilot launch ------------------------------------------------------------------
 // The pilot launch scanned n_seen of the nd rows with thresholds thr_in and kept EVERY row at or below them (no
@@ -715,12 +713,10 @@ __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64
                                                                     uint64_t* __restrict__ keys,
                                                                     uint32_t* __restrict__ fail_flags,
                                                                     uint32_t* __restrict__ fail_count) {
-    extern __shared__ __align__(16) uint64_t sk[];   // [FIN_CAP] (the general path uses the first FIN_MAX)
+    __shared__ uint64_t sk[FIN_MAX];
     __shared__ uint32_t hist[FIN_BINS];
-    __shared__ uint32_t whist[(FIN_THREADS / 32) * FIN_BINS];
     __shared__ int s_T, s_keep;
     __shared__ uint32_t s_n, s_total, s_over;
-    __shared__ uint32_t s_off[FIN_SEGS];
     const int64_t q = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NW = FIN_THREADS / 32;
@@ -729,131 +725,6 @@ __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64
     for (int i = threadIdx.x; i < FIN_BINS; i += blockDim.x) hist[i] = 0u;
     if (threadIdx.x == 0) { s_n = 0u; s_total = 0u; s_over = 0u; }
     __syncthreads();
-    // ---- fast path: all the query's candidates fit shared memory (the usual case: a few K of them) -------------------
-    // One round trip for the segment counts, one for the candidates; the K-th bucket, the compaction to the rows at or
-    // below it and the sort (by key = (distance, index), all distinct) happen in shared memory.
-    if (n_chunks <= FIN_SEGS) {
-        for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) {
-            const uint32_t n = cnt[(int64_t)c * nq + q];
-            s_off[c] = n;
-            if (n > (uint32_t)seg_cap) s_over = 1u;
-        }
-        __syncthreads();
-        if (warp == 0) {                                 // exclusive scan of the counts (warp 0, FIN_SEGS / 32 per lane)
-            constexpr int PER = FIN_SEGS / 32;
-            uint32_t local = 0;
-            for (int j = 0; j < PER; ++j) {
-                const int c = lane * PER + j;
-                if (c < n_chunks) local += s_off[c];
-            }
-            uint32_t incl = local;
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += up;
-            }
-            uint32_t run = incl - local;
-            for (int j = 0; j < PER; ++j) {
-                const int c = lane * PER + j;
-                if (c < n_chunks) { const uint32_t n = s_off[c]; s_off[c] = run; run += n; }
-            }
-            if (lane == 31) s_total = incl;
-        }
-        __syncthreads();
-        const uint32_t total = s_total;
-        if (s_over == 0u && total <= (uint32_t)FIN_CAP) {
-            const int64_t want = partial ? min(need, (int64_t)total) : need;
-            bool fail = (int64_t)total < want || aux[q].force_fail != 0u;
-            int keep = 0;
-            if (!fail) {
-                for (int c = warp; c < n_chunks; c += NW) {
-                    const uint32_t off = s_off[c];
-                    const uint32_t n = (c + 1 < n_chunks ? s_off[c + 1] : total) - off;
-                    const uint64_t* seg = mine + (uint64_t)c * seg_cap;
-                    uint32_t i = lane;
-                    for (; i + 96 < n; i += 128) {       // four loads in flight
-                        const uint64_t k0 = seg[i], k1 = seg[i + 32], k2 = seg[i + 64], k3 = seg[i + 96];
-                        sk[off + i] = k0; sk[off + i + 32] = k1; sk[off + i + 64] = k2; sk[off + i + 96] = k3;
-                    }
-                    for (; i < n; i += 32) sk[off + i] = seg[i];
-                }
-                __syncthreads();
-                // this thread's candidates (registers), their buckets into a per-warp histogram
-                constexpr int PT = FIN_CAP / FIN_THREADS;
-                uint64_t mykeys[PT];
-                uint32_t* wh = whist + warp * FIN_BINS;
-                for (int i = lane; i < FIN_BINS; i += 32) wh[i] = 0u;
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < PT; ++j) {           // the candidates sit in 3-4 buckets: one add per bucket per warp
-                    const uint32_t i = threadIdx.x + j * FIN_THREADS;
-                    mykeys[j] = i < total ? sk[i] : ~0ull;
-                    const uint32_t bkt = i < total ? min((uint32_t)(mykeys[j] >> 33), (uint32_t)(FIN_BINS - 1)) : FIN_BINS;
-                    const uint32_t same = __match_any_sync(0xffffffffu, bkt);
-                    if (bkt < FIN_BINS && lane == __ffs(same) - 1) wh[bkt] += __popc(same);
-                    __syncwarp();
-                }
-                __syncthreads();
-                for (int i = threadIdx.x; i < FIN_BINS; i += blockDim.x) {
-                    uint32_t v = 0;
-                    for (int w = 0; w < NW; ++w) v += whist[w * FIN_BINS + i];
-                    hist[i] = v;
-                }
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    int64_t cum = 0;
-                    int T = -1;
-                    for (int b = 0; b < FIN_BINS && cum < want; ++b) { cum += hist[b]; T = b; }
-                    s_T = T;
-                    // buckets above thr_limit may be incomplete (launches with different thresholds): the K-th distance
-                    // must not come from there
-                    s_keep = (cum > FIN_MAX || (thr_limit != nullptr && T > thr_limit[q])) ? -1 : (int)cum;
-                }
-                __syncthreads();
-                keep = s_keep;
-                fail = keep < 0;
-                if (!fail) {
-                    const int T = s_T;
-#pragma unroll
-                    for (int j = 0; j < PT; ++j) {       // every thread holds its keys: the buffer can be overwritten
-                        const bool ok = mykeys[j] != ~0ull && (int)(uint32_t)(mykeys[j] >> 33) <= T;
-                        const uint32_t m = __ballot_sync(0xffffffffu, ok);
-                        uint32_t base = 0;
-                        if (lane == 0 && m) base = atomicAdd(&s_n, (uint32_t)__popc(m));
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        if (ok) sk[base + __popc(m & lanemask_lt())] = mykeys[j];
-                    }
-                    int p2 = 1;
-                    while (p2 < keep) p2 <<= 1;
-                    __syncthreads();
-                    for (int i = keep + threadIdx.x; i < p2; i += blockDim.x) sk[i] = ~0ull;
-                    __syncthreads();
-                    for (int k = 2; k <= p2; k <<= 1) {
-                        for (int j = k >> 1; j > 0; j >>= 1) {
-                            for (int i = threadIdx.x; i < p2; i += blockDim.x) {
-                                const int ixj = i ^ j;
-                                if (ixj > i) {
-                                    const uint64_t x = sk[i], y = sk[ixj];
-                                    const bool up = (i & k) == 0;
-                                    if ((x > y) == up) { sk[i] = y; sk[ixj] = x; }
-                                }
-                            }
-                            __syncthreads();
-                        }
-                    }
-                }
-            }
-            if (threadIdx.x == 0) {
-                fail_flags[q] = fail ? 1u : 0u;
-                if (fail) atomicAdd(fail_count, 1u);
-            }
-            for (int i = threadIdx.x; i < K; i += blockDim.x) keys[q * K + i] = (!fail && i < keep) ? sk[i] : ~0ull;
-            return;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) { s_total = 0u; s_over = 0u; }
-        __syncthreads();
-    }
-    // ---- general path: histogram of the candidates in place, then only those at or below the K-th bucket are sorted ----
     for (int c = warp; c < n_chunks; c += NW) {
         uint32_t n = cnt[(int64_t)c * nq + q];
         if (lane == 0) {
@@ -862,7 +733,12 @@ __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64
         }
         n = min(n, (uint32_t)seg_cap);
         const uint64_t* seg = mine + (uint64_t)c * seg_cap;
-        for (uint32_t i = lane; i < n; i += 32) atomicAdd(&hist[(uint32_t)(seg[i] >> 33)], 1u);
+        for (uint32_t i0 = 0; i0 < n; i0 += 32) {        // the candidates sit in 3-4 buckets: one add per bucket per warp
+            const uint32_t i = i0 + lane;
+            const uint32_t bkt = i < n ? min((uint32_t)(seg[i] >> 33), (uint32_t)(FIN_BINS - 1)) : (uint32_t)FIN_BINS;
+            const uint32_t same = __match_any_sync(0xffffffffu, bkt);
+            if (bkt < (uint32_t)FIN_BINS && lane == __ffs(same) - 1) atomicAdd(&hist[bkt], (uint32_t)__popc(same));
+        }
     }
     __syncthreads();
     // partial (one shard of several): emit what there is, up to K; the K-th key is judged after the merge
@@ -893,9 +769,15 @@ __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64
     for (int c = warp; c < n_chunks; c += NW) {
         const uint32_t n = cnt[(int64_t)c * nq + q];     // <= seg_cap (checked above)
         const uint64_t* seg = mine + (uint64_t)c * seg_cap;
-        for (uint32_t i = lane; i < n; i += 32) {
-            const uint64_t key = seg[i];
-            if ((int)(uint32_t)(key >> 33) <= T) sk[atomicAdd(&s_n, 1u)] = key;
+        for (uint32_t i0 = 0; i0 < n; i0 += 32) {        // one slot reservation per warp
+            const uint32_t i = i0 + lane;
+            const uint64_t key = i < n ? seg[i] : ~0ull;
+            const bool ok = i < n && (int)(uint32_t)(key >> 33) <= T;
+            const uint32_t m = __ballot_sync(0xffffffffu, ok);
+            uint32_t base = 0;
+            if (lane == 0 && m) base = atomicAdd(&s_n, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (ok) sk[base + __popc(m & lanemask_lt())] = key;
         }
     }
     int p2 = 1;
@@ -1086,8 +968,7 @@ extern "C" int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, cons
     CMH_REQUIRE(nq <= 0x7fffffffll, CMH_ERR_UNSUPPORTED, "cmh_topk_finalize: too many queries per call");
     cudaStream_t st = (cudaStream_t)stream;
     CMH_CUDA(cudaMemsetAsync(fail_count, 0, 4, st));
-    CMH_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIN_CAP * 8));
-    topk_finalize_kernel<<<(unsigned)nq, FIN_THREADS, FIN_CAP * 8, st>>>(cand, cnt, reinterpret_cast<const TcAux*>(aux),
+    topk_finalize_kernel<<<(unsigned)nq, FIN_THREADS, 0, st>>>(cand, cnt, reinterpret_cast<const TcAux*>(aux),
                                                               partial ? nullptr : thr_limit, nq, n_chunks, seg_cap, K, nd,
                                                               partial, keys, fail_flags, fail_count);
     CMH_LAUNCH_CHECK("topk_finalize_kernel");
