@@ -298,6 +298,67 @@ def test_tc_topk_against_oracle_and_fallback(dev):
     assert torch.equal(got.cpu(), torch.arange(100).expand(3, 100))
 
 
+def test_tc_unaligned_view_and_clamped_thresholds(dev):
+    """A shard view that is not 16-byte aligned takes the plain-load producer path; thresholds beyond (bits-1)/2 are
+    clamped and the short queries take the exact path - both must still give the stable ranking."""
+    from cmh_b200 import engine
+    D, Q = 70_001, 33
+    db = engine.synth_codes(901, 0, D + 1, 64, dev)
+    q = engine.synth_codes(902, 0, Q, 64, dev)
+    view = db.rows(1, D + 1)                         # 8 bytes past a 16-byte boundary
+    assert view.sign.data_ptr() % 16 == 8
+    want = engine.RankPass(q, view, need_labels=False).topk(200, 5)
+    assert torch.equal(engine.topk_tc(q, view, 200, 5), want)
+    small = db.rows(0, 3000)
+    want = engine.RankPass(q, small, need_labels=False).topk(2500, 0)       # K-th distance > 31: clamp -> fallback
+    st = {}
+    assert torch.equal(engine.topk_tc(q, small, 2500, 0, stats=st), want)
+    assert st["n_fail"] > 0
+
+
+def test_tc_streamed_upload_matches_resident(dev):
+    """`HammingIndex.from_packed_host`: the first search scans the row ranges as they land; same keys as a resident
+    database, and the second search (everything resident) agrees too."""
+    from cmh_b200 import engine
+    from cmh_b200.index import HammingIndex
+    D, Q, K = 9_000_000, 257, 300
+    db = engine.synth_codes(911, 0, D, 64, dev)
+    q = engine.synth_codes(912, 0, Q, 64, dev)
+    want = HammingIndex(db, 11).search_packed(q, K)
+    assert torch.equal(want, engine.RankPass(q, db, need_labels=False).topk(K, 11))
+    host = db.sign.cpu().pin_memory()
+    idx = HammingIndex.from_packed_host(host, 64, 11, pieces=3)
+    assert torch.equal(idx.search_packed(q, K), want)
+    assert torch.equal(idx.search_packed(q, K), want)
+
+
+def test_tc_probe_and_verify(dev):
+    """The measurement aid runs every mode; `cmh_topk_verify` flags pads and keys from incomplete buckets."""
+    import ctypes
+    from cmh_b200 import _cabi, engine
+    L = _cabi.lib()
+    Q, D = 100, 300_000
+    db = engine.synth_codes(921, 0, D, 64, dev)
+    q = engine.synth_codes(922, 0, Q, 64, dev)
+    b = engine.TcBuffers(Q, [D], 64, 4096, dev)
+    thr = torch.full((Q,), 20, dtype=torch.int32, device=dev)
+    for mode in (0, 1, 2, 3, 4, 5, 8, 16, 32):
+        engine.check(L.cmh_tc_probe(engine._ptr(q.sign), Q, engine._ptr(db.sign), D, 64, engine._ptr(thr), b.seg_total,
+                                    b.seg_cap, engine._ptr(b.cand), engine._ptr(b.cnt), engine._ptr(b.aux), mode,
+                                    engine._stream(dev)), "cmh_tc_probe")
+    torch.cuda.synchronize()
+    K = 4
+    keys = torch.tensor([[(2 * 3 << 32) | 1, (2 * 3 << 32) | 9, (2 * 5 << 32) | 2, (2 * 7 << 32) | 4],     # fine
+                         [(2 * 3 << 32) | 1, (2 * 3 << 32) | 9, (2 * 5 << 32) | 2, (2 * 9 << 32) | 4],     # K-th above limit
+                         [(2 * 3 << 32) | 1, (2 * 3 << 32) | 9, -1, -1]], dtype=torch.int64, device=dev)   # short
+    lim = torch.tensor([7, 8, 30], dtype=torch.int32, device=dev)
+    flags = torch.zeros(3, dtype=torch.int32, device=dev)
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    engine.check(L.cmh_topk_verify(engine._ptr(keys), engine._ptr(lim), 3, K, 1000, engine._ptr(flags), engine._ptr(count),
+                                   engine._stream(dev)), "cmh_topk_verify")
+    assert flags.tolist() == [0, 1, 1] and int(count) == 2
+
+
 class _ThreadComm:
     """Test double of `sharded.GroupComm`: the shards of one database are driven by threads on ONE GPU, and the
     exchange steps meet at a barrier (what NCCL does between the ranks of a real box)."""
