@@ -344,7 +344,8 @@ TC_DEFAULT_CAP = 32768      # candidate slots per query, split evenly over its s
 TC_MIN_SEG = 64
 TC_MAX_K = 4096
 TC_PILOT_MIN_ROWS = 8_000_000     # databases at least this long get a pilot launch over their first rows
-TC_PILOT_FRACTION = 64            # ... 1/64 of them (measured optimum: the pilot rows are scanned at the loose thresholds)
+TC_PILOT_FRACTIONS = (64,)        # ... the first 1/64 of the rows (measured optimum; a second stage at 1/8 gains nothing:
+                                  # the main launch tightens by itself), each stage followed by a refinement
 TC_PILOT_SIGMA = 5.0
 
 
@@ -380,10 +381,18 @@ class TcBuffers:
 
 
 def tc_pilot_rows(nd: int) -> int:
-    """Rows of the pilot launch (0 = none): a multiple of the 256-row tile."""
+    """Rows of the first pilot launch (0 = none): a multiple of the 256-row tile."""
     if nd < TC_PILOT_MIN_ROWS:
         return 0
-    return (nd // TC_PILOT_FRACTION) // 256 * 256
+    return (nd // TC_PILOT_FRACTIONS[0]) // 256 * 256
+
+
+def tc_pilot_stages(nd: int, nd_total: int) -> list:
+    """Cumulative row counts (multiples of the 256-row tile, ascending, < nd) after which the thresholds are refined.
+    The NUMBER of stages depends on the whole database only - every shard takes part in every refinement."""
+    if nd_total < TC_PILOT_MIN_ROWS:
+        return []
+    return [(nd // f) // 256 * 256 for f in TC_PILOT_FRACTIONS]
 
 
 class LocalComm:
@@ -413,8 +422,9 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
 
     sample  a subset of the rows of ``d`` (any rows, contiguous in memory) used only to guess the per-query
             thresholds; None = use ``d`` itself (exact thresholds when unsharded, an extra popc pass)
-    pilot   rows of the pilot launch (None = `tc_pilot_rows`): the first ``pilot`` rows of ``d`` are scanned with the
-            sample thresholds, and what they hold refines the thresholds for the rest
+    pilot   cumulative row counts of the pilot launches (None = `tc_pilot_stages`; an int = one stage): the rows up
+            to each count are scanned with the thresholds known so far, and what they hold refines the thresholds
+            for the rest
     comm    exchange steps (`LocalComm`, `sharded.GroupComm`): the sample / pilot histograms are all-reduced so that
             every shard filters with the same global thresholds - a shard then contributes only its share of the ~K
             rows below them; the per-shard results are exchanged all-to-all (rank r merges the r-th slice of the
@@ -445,10 +455,16 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     L = _cabi.lib()
     nb = q.bits + 1
     smp = d if sample is None else sample
-    n_pilot = tc_pilot_rows(d.n) if pilot is None else int(pilot)
-    if (sample is None and comm.world == 1) or n_pilot <= 0 or n_pilot >= d.n:
-        n_pilot = 0                                  # exact thresholds need no refinement
-    cuts = sorted({0, n_pilot, d.n} | {int(e) for e, _ in (ready or ()) if n_pilot < int(e) < d.n})
+    # refinement stages: cumulative local row counts; the same number of stages on every shard
+    if pilot is None:
+        stages = tc_pilot_stages(d.n, nd_total)
+    else:
+        stages = [int(x) for x in (pilot if isinstance(pilot, (list, tuple)) else [pilot]) if int(x) > 0]
+    if sample is None and comm.world == 1:
+        stages = []                                  # exact thresholds need no refinement
+    stages = [min(e, d.n) for e in stages]
+    ends = sorted({e for e in stages if 0 < e < d.n})
+    cuts = sorted({0, d.n} | set(ends) | {int(e) for e, _ in (ready or ()) if 0 < int(e) < d.n})
     spans = [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]] or [(0, 0)]
     regions = [hi - lo for lo, hi in spans]
 
@@ -466,16 +482,16 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
             buffers.clear()                          # one geometry at a time: the scratch is large
             buffers[bkey] = b
     if comm.world > 1:
-        ckey = ("counts", smp.n, n_pilot)
+        ckey = ("counts", smp.n, tuple(stages))
         got = buffers.get(ckey) if buffers is not None else None
         if got is None:
-            counts = comm.all_reduce_sum(torch.tensor([smp.n, n_pilot], dtype=torch.int64, device=dev))
+            counts = comm.all_reduce_sum(torch.tensor([smp.n] + stages, dtype=torch.int64, device=dev))
             got = tuple(int(v) for v in counts.tolist())
             if buffers is not None:
                 buffers[ckey] = got
-        n_sample_all, n_pilot_all = got
+        n_sample_all, stages_all = got[0], list(got[1:])
     else:
-        n_sample_all, n_pilot_all = smp.n, n_pilot
+        n_sample_all, stages_all = smp.n, list(stages)
     if stats is not None and stats.get("time_phases"):
         e = torch.cuda.Event(enable_timing=True)
         e.record(torch.cuda.current_stream(dev))
@@ -488,8 +504,6 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     with torch.cuda.device(dev):
         st = _stream(dev)
         check(L.cmh_topk_threshold(_ptr(h_all), nq, nb, n_sample_all, nd_total, K, _ptr(b.thr), st), "cmh_topk_threshold")
-        thr_main = b.thr
-        row0 = 0
         timed = stats is not None and stats.get("time_collect")
 
         def mark():
@@ -505,39 +519,51 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
                 stats.setdefault("phase_events", []).append((name, e))
 
         phase("thresholds_done")
+        thr_cur, thr_next = b.thr, b.thr2
+        last_stage = stages[-1] if stages else 0
+        si = 0                                       # next stage to close
+        launched = False
 
-        if n_pilot_all:
-            # every shard takes part in the exchange, also one too short for a pilot of its own
-            if n_pilot:
-                wait_rows(n_pilot)
-                mark()
-                check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign), n_pilot, q.bits, int(index_base), _ptr(b.thr), 0,
-                                       b.seg_base[0], b.seg_total, b.seg_cap, _ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), st),
-                      "cmh_tc_collect")
-                mark()
+        def refine_upto(i_stage: int, seg_hi: int):
+            # the candidates of the rows scanned so far (kept at thresholds >= the current ones): exact counts of
+            # every bucket at or below the current threshold; all-reduced over the shards
+            nonlocal thr_cur, thr_next
             ph = torch.zeros((nq, nb), dtype=torch.int32, device=dev)
             over = torch.zeros(nq, dtype=torch.int32, device=dev)
-            if n_pilot:
-                check(L.cmh_tc_cand_hist(_ptr(b.cand), _ptr(b.cnt), nq, b.seg_base[0], b.seg_base[0] + b.n_segs[0],
-                                         b.seg_total, b.seg_cap, nb, _ptr(ph), _ptr(over), st), "cmh_tc_cand_hist")
+            if seg_hi > 0:
+                check(L.cmh_tc_cand_hist(_ptr(b.cand), _ptr(b.cnt), nq, 0, seg_hi, b.seg_total, b.seg_cap, nb, _ptr(ph),
+                                         _ptr(over), st), "cmh_tc_cand_hist")
             ph, over = comm.all_reduce_sum(ph), comm.all_reduce_max(over)
-            check(L.cmh_tc_choose(_ptr(ph), _ptr(over), nq, nb, n_pilot_all, nd_total, K, TC_PILOT_SIGMA, _ptr(b.thr),
-                                  _ptr(b.thr2), st), "cmh_tc_choose")
-            thr_main = b.thr2
-            row0 = n_pilot
-        phase("pilot_done")
-        main = [(i, lo, hi) for i, (lo, hi) in enumerate(spans) if lo >= row0 and hi > lo]
-        for i, lo, hi in main:
-            # tightening uses this launch's own counts: K rows found locally are K rows found globally
+            check(L.cmh_tc_choose(_ptr(ph), _ptr(over), nq, nb, stages_all[i_stage], nd_total, K, TC_PILOT_SIGMA,
+                                  _ptr(thr_cur), _ptr(thr_next), st), "cmh_tc_choose")
+            thr_cur, thr_next = thr_next, thr_cur
+
+        # stages that are empty on this shard (a short shard) still take part in the exchange
+        while si < len(stages) and stages[si] <= 0:
+            if stages_all[si] > 0:
+                refine_upto(si, 0)
+            si += 1
+        for i, (lo, hi) in enumerate(spans):
+            if hi <= lo:
+                continue
+            in_pilot = hi <= last_stage              # pilot spans keep EVERY row at or below the threshold (K = 0)
             wait_rows(hi)
             mark()
+            # tightening (main spans) uses this launch's own counts: K rows found locally are K rows found globally
             check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign[lo:]), hi - lo, q.bits, int(index_base) + lo,
-                                   _ptr(thr_main), K if tighten else 0, b.seg_base[i], b.seg_total, b.seg_cap,
-                                   _ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), st), "cmh_tc_collect")
+                                   _ptr(thr_cur), 0 if in_pilot or not tighten else K, b.seg_base[i], b.seg_total,
+                                   b.seg_cap, _ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), st), "cmh_tc_collect")
             mark()
-        if not main:
-            b.cnt[b.seg_base[-1]:].zero_()
+            launched = True
+            while si < len(stages) and stages[si] <= hi:
+                if stages_all[si] > 0:
+                    refine_upto(si, b.seg_base[i] + b.n_segs[i])
+                si += 1
+                phase("pilot_done")
+        if not launched:
+            b.cnt.zero_()
             b.aux.zero_()
+        thr_main = thr_cur
         phase("main_done")
         partial = 1 if comm.world > 1 else 0
         check(L.cmh_topk_finalize(_ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), _ptr(thr_main), nq, b.seg_total, b.seg_cap, K,
@@ -556,7 +582,7 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
         stats["n_fail"] = n_fail
         stats["candidates"] = b.cnt.sum(0)
         stats["thr"] = thr_main
-        stats["pilot_rows"] = n_pilot
+        stats["pilot_rows"] = stages
     if n_fail:
         rows = torch.nonzero(b.fail_flags, as_tuple=False).squeeze(1)
         sub = PackedSet(q.sign.index_select(0, rows).contiguous(), None, None, int(rows.numel()), q.bits)
