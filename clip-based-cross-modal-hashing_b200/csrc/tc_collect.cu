@@ -14,24 +14,26 @@
 // constant row of weights whose product is  bias_q = B - (B + 1) * T_q  (T_q = the dot product a row needs to qualify).
 // With e1 = dot1 - T and e2 = dot2 - T + 1,  acc = e1 + B * e2  and, F = log2 B,
 //     bit F-1  of acc clear  <=>  e1 >= 0  <=>  row j qualifies
-//     bit 2F-1 of acc clear  <=>  e2 - [e1 < 0] >= 0  <=>  row j+128 qualifies  (or dot2 == T - 1 next to a hit: harmless)
+//     bit 2F-1 of acc clear  <=>  e2 - [e1 < 0] >= 0  <=>  row j+128 qualifies  (e2 is odd: dot products have the parity
+//                                                                              of the code length, so e2 >= 0 <=> e2 >= 1)
 // so the filter is an AND-reduction of the registers and one mask test per slice.  64-bit codes: F = 8, S = 16, acc
 // fits 16 bits and tcgen05.ld packs two columns per register (4 rows per register); 128-bit codes: F = 10, S = 32.
-// The fields cannot wrap (|e| < 2^(F-1) for 1 <= T <= bits), and dot products have the parity of the code length.
+// The fields cannot wrap (|e| < 2^(F-1) for 1 <= T <= bits).
 // The fields of a flagged accumulator decode to the exact distances, which are compared with the query's CURRENT
 // threshold - it tightens while the scan proceeds - before the row is appended.
 //
 // Warp roles (warp-specialised, mbarrier pipelines, no __syncthreads in the main loop):
-//   warps 0-3     MMA issuers, one per accumulator buffer (an elected lane: wait, 2 * KSTEPS tcgen05.mma, commit)
+//   warps 0-3     MMA issuers, one per accumulator buffer (an elected lane: wait, 2 * KSTEPS + 1 tcgen05.mma, commit)
 //   warps 4-7     producers: packed code words arrive through a bulk-copy (cp.async.bulk) ring; every bit is expanded
-//                 to a +-1 / +-32 byte with two integer multiplies per nibble and stored as 8x16 B core matrices
+//                 to a +-1 / +-S byte with two integer multiplies per nibble and stored as 8x16 B core matrices
 //                 (no-swizzle K-major UMMA layout) into a STAGES-deep ring of B tiles
 //   warps 8-23    epilogue: 4 groups of 4 warps, group g drains accumulator buffer g; thread = one query (a TMEM
-//                 lane) for the whole CTA, so its threshold, candidate count and code words live in registers
+//                 lane) for the whole CTA, so its threshold, candidate count and segment pointer live in registers;
+//                 slices with a flagged row are parked in shared memory and worked off while the warp waits
 // TMEM: 4 accumulator buffers x 128 columns (the whole 512-column TMEM, one CTA per SM).
 //
 // Exactness: thresholds only have to be upper bounds of the K-th distance (cmh_topk_threshold derives them from a
-// sample histogram); cmh_topk_finalize sorts the candidates by key - (distance, index), all keys distinct - which IS
+// sample histogram, cmh_tc_cand_hist + cmh_tc_choose refine them from a pilot launch); cmh_topk_finalize sorts the candidates by key - (distance, index), all keys distinct - which IS
 // the stable ranking, and flags any query whose candidate list is short or overflowed for the exact two-pass path.
 #include <algorithm>
 
@@ -190,7 +192,8 @@ struct TcArgs {
     int n_segs, seg_base, seg_cap, bits;   // segments per query in all, first segment of this launch
     int K;                  // > 0: tighten thresholds while scanning (once K rows at dist <= thr0 - j are known)
     long long* trace;       // CMH_TC_TRACE builds only
-    int probe;              // measurement aid (cmh_tc_probe): 1 = no tcgen05.mma, 2 = no TMEM drain, 4 = drain without scan
+    int probe;              // measurement aid (cmh_tc_probe): 1 no tcgen05.mma, 2 no TMEM drain, 4 drain without scan,
+                            // 8 hits decoded but not stored, 16 parked hits dropped, 32 flagged slices not parked
 };
 
 // Working off one parked slice of the hit path (see the epilogue).  Out of line on purpose: ONE copy of this code in

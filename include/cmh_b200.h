@@ -189,7 +189,8 @@ int cmh_tc_collect(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, i
 /* Measurement aid for the roofline of cmh_tc_collect: the same kernel and launch with parts of the pipeline
  * disabled, to time the ceilings in situ.  probe bit 0: no tcgen05.mma is issued (operand expansion + TMEM drain +
  * filter only); bit 1: accumulators are not drained (operand expansion + MMA only = tensor-pipe ceiling);
- * bit 2: accumulators are drained but not scanned.  Outputs are meaningless. */
+ * bit 2: accumulators are drained but not scanned; bits 3-5 switch off stages of the hit path (candidates decoded but
+ * not stored / parked slices dropped / flagged slices not parked).  Outputs are meaningless. */
 int cmh_tc_probe(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits, const int32_t* thr,
                  int seg_total, int seg_cap, uint64_t* cand, uint32_t* cnt, uint32_t* aux, int probe, void* stream);
 /* Thresholds from a pilot launch.  Step 1: hist (device uint32 [nq][nb], bucket = Hamming distance) of the candidates
