@@ -343,26 +343,44 @@ def main_native(args):
             dist.destroy_process_group()
         return
 
-    # ---- secondary: mAP@ALL queries/s at the NUS-WIDE shape (config 2, 64-bit), single GPU ---------------------
+    # ---- secondary: the reference's own evaluation calls at the shapes of configs 1-3, single GPU -----------------
+    # calc_map_k_matrix in both directions (I->T, T->I), p_topK where the config names precision@N, pr_curve where it
+    # names the PR curve: device float codes + labels in, pack + counting passes + host scalar out, cache cleared
+    # before every call (nothing is reused between calls)
     also = None
     if not args.no_also:
         from cmh_b200.synth import CONFIGS, make_case
-        shape = CONFIGS["c2-64"]
-        t = make_case(shape, clustered=True, zero_query_frac=0.01)
-        qB, rB = torch.from_numpy(t["q_img"]).to(dev), torch.from_numpy(t["r_txt"]).to(dev)
-        qL, rL = torch.from_numpy(t["q_lab"]).to(dev), torch.from_numpy(t["r_lab"]).to(dev)
-        for _ in range(3):
-            cu.clear_cache(); m = cu.calc_map_k_matrix(qB, rB, qL, rL, None, local)
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        reps = 10
-        for _ in range(reps):
-            cu.clear_cache(); m = cu.calc_map_k_matrix(qB, rB, qL, rL, None, local)
-        dt = (time.perf_counter() - t0) / reps
-        also = {"workload": "c2: NUS-WIDE shape 2,100 x 193,734, 64-bit, 21 labels, mAP@ALL via calc_map_k_matrix "
-                            "(device float codes in, pack + 2 passes + host scalar out)",
-                "map_queries_per_s": shape.n_query / dt, "ms_per_call": dt * 1e3,
-                "compares_per_s": shape.n_query * shape.n_db / dt, "map": float(m)}
+
+        def per_call_ms(fn, reps=5):
+            for _ in range(2):
+                cu.clear_cache(); out = fn()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                cu.clear_cache(); out = fn()
+            torch.cuda.synchronize(dev)
+            return (time.perf_counter() - t0) / reps * 1e3, out
+
+        also = {}
+        for name in ("c1", "c2-16", "c2-32", "c2-64", "c3"):
+            shape = CONFIGS[name]
+            t = make_case(shape, clustered=True, zero_query_frac=0.01)
+            qi, qt, ri, rt = (torch.from_numpy(t[k]).to(dev) for k in ("q_img", "q_txt", "r_img", "r_txt"))
+            qL, rL = torch.from_numpy(t["q_lab"]).to(dev), torch.from_numpy(t["r_lab"]).to(dev)
+            ms_i2t, m_i2t = per_call_ms(lambda: cu.calc_map_k_matrix(qi, rt, qL, rL, shape.k, local))
+            ms_t2i, m_t2i = per_call_ms(lambda: cu.calc_map_k_matrix(qt, ri, qL, rL, shape.k, local))
+            entry = {"shape": f"{shape.n_query} x {shape.n_db}, {shape.bits}-bit, {shape.n_labels} labels, "
+                              f"mAP@{'ALL' if shape.k is None else shape.k}",
+                     "map_i2t": float(m_i2t), "map_t2i": float(m_t2i), "ms_per_call_i2t": ms_i2t, "ms_per_call_t2i": ms_t2i,
+                     "map_queries_per_s": shape.n_query / (ms_i2t * 1e-3),
+                     "compares_per_s": shape.n_query * shape.n_db / (ms_i2t * 1e-3)}
+            if shape.topn:
+                ms_p, _ = per_call_ms(lambda: cu.p_topK(qi, rt, qL, rL, list(shape.topn), local))
+                entry["p_topK_ms_per_call"] = ms_p
+            if name == "c3":
+                ms_pr, _ = per_call_ms(lambda: cu.pr_curve(qi, rt, qL, rL, local))
+                entry["pr_curve_ms_per_call"] = ms_pr
+            also[name] = entry
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
