@@ -537,21 +537,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
             }
         };
         // one slice (32 registers: 64 or 128 rows): AND-reduce, one mask test, one vote; the hit path is rare
-        auto scan = [&](const uint32_t (&v)[32], int64_t r0) {
+        // two slices (32 registers each: 64 or 128 rows): AND-reduce, one mask test per slice, ONE vote for both; the
+        // hit path is rare
+        auto scan2 = [&](const uint32_t (&v0)[32], int64_t r0, const uint32_t (&v1)[32], int64_t r1) {
             if (no_scan) {
                 uint32_t o = 0;
 #pragma unroll
-                for (int r = 0; r < 32; ++r) o |= v[r];
+                for (int r = 0; r < 32; ++r) o |= v0[r] | v1[r];
                 if (o == 0xdeadbeefu) a.cnt[0] = o;      // keep the loads alive
                 return;
             }
-            uint32_t ab[4];
+            uint32_t ab0[4], ab1[4];
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
-                ab[b] = (v[8 * b] & v[8 * b + 1] & v[8 * b + 2]) & (v[8 * b + 3] & v[8 * b + 4] & v[8 * b + 5]) &
-                        (v[8 * b + 6] & v[8 * b + 7]);
-            const bool flagged = ((ab[0] & ab[1] & ab[2] & ab[3]) & FLAGS) != FLAGS;
-            if (__any_sync(0xffffffffu, flagged)) park_slice(v, ab, flagged, r0);
+            for (int b = 0; b < 4; ++b) {
+                ab0[b] = (v0[8 * b] & v0[8 * b + 1] & v0[8 * b + 2]) & (v0[8 * b + 3] & v0[8 * b + 4] & v0[8 * b + 5]) &
+                         (v0[8 * b + 6] & v0[8 * b + 7]);
+                ab1[b] = (v1[8 * b] & v1[8 * b + 1] & v1[8 * b + 2]) & (v1[8 * b + 3] & v1[8 * b + 4] & v1[8 * b + 5]) &
+                         (v1[8 * b + 6] & v1[8 * b + 7]);
+            }
+            const bool f0 = ((ab0[0] & ab0[1] & ab0[2] & ab0[3]) & FLAGS) != FLAGS;
+            const bool f1 = ((ab1[0] & ab1[1] & ab1[2] & ab1[3]) & FLAGS) != FLAGS;
+            if (__any_sync(0xffffffffu, f0 || f1)) {
+                park_slice(v0, ab0, f0, r0);
+                park_slice(v1, ab1, f1, r1);
+            }
         };
         auto release = [&]() {                   // the values are in registers: the buffer goes back to its issuer
             tc_fence_before();
@@ -588,21 +597,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
                 tmem_ld_wait();
                 if (qrow == 0) TC_TRACE(2 + grp, round, 2);
                 release();                       // before anything is looked at: a hit never holds the buffer
-                scan(va, row0);
-                scan(vb, row0 + 64);
+                scan2(va, row0, vb, row0 + 64);
             } else {
                 tmem_ld32(taddr, va);
                 tmem_ld32(taddr + 32, vb);
                 tmem_ld_wait();
-                scan(va, row0);
-                scan(vb, row0 + 32);
+                scan2(va, row0, vb, row0 + 32);
                 tmem_ld32(taddr + 64, va);
                 tmem_ld32(taddr + 96, vb);
                 tmem_ld_wait();
                 if (qrow == 0) TC_TRACE(2 + grp, round, 2);
                 release();
-                scan(va, row0 + 64);
-                scan(vb, row0 + 96);
+                scan2(va, row0 + 64, vb, row0 + 96);
             }
             if (qrow == 0) TC_TRACE(2 + grp, round, 4);
         }
