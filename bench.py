@@ -58,7 +58,9 @@ def parse_args():
 def config_dict(args, world):
     return {"workload": "c4: 64-bit exact stable top-1000 Hamming retrieval, 100M-row database, one query chunk per step",
             "bits": BITS, "topk": TOPK, "db_rows": args.db_rows, "queries_per_step": args.queries,
-            "sharding": f"database rows split contiguously over {world} GPU(s); queries replicated; all-reduced threshold histograms, NCCL all-gather + merge"
+            "pipelining": "two query chunks in flight (chunk i+1 is enqueued before chunk i is resolved); every chunk is "
+                          "resolved and verified inside the timed region",
+            "sharding": f"database rows split contiguously over {world} GPU(s); queries replicated; all-reduced threshold histograms, NCCL all-to-all by query slice + merge + all-gather"
                         if world > 1 else "single GPU holds the whole database",
             "l2": "per-step working set (packed shard + candidate segments, >1 GB) exceeds the 126 MB L2; no explicit flush",
             "seed": SEED}
@@ -258,16 +260,25 @@ def main_native(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
-        keys = index.search_packed(q_packed, K, stats={"time_collect": True, "time_phases": True})   # the timed code path
+    def run_steps(n, stats):
+        # two query chunks in flight: chunk i+1 is enqueued (on the other of two streams) before chunk i is resolved, so
+        # the small kernels, the exchange and the ragged last wave of one chunk hide behind the scan of the next
+        pending, keys = None, None
+        for _ in range(n):
+            h = index.search_packed_async(q_packed, K, stats=stats)
+            if pending is not None:
+                keys = pending.result()
+            pending = h
+        return pending.result() if pending is not None else keys
+
+    keys = run_steps(args.warmup, {"time_collect": True, "time_phases": True})    # the timed code path, kernels loaded
     barrier()
     t_region0 = time.perf_counter()
     launches0 = lib.cmh_launch_count()
     stats = {"time_collect": True, "time_phases": True}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        keys = index.search_packed(q_packed, K, stats=stats)
+    keys = run_steps(args.steps, stats)
     e1.record()
     barrier()
     launches = lib.cmh_launch_count() - launches0

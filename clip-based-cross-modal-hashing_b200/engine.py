@@ -416,7 +416,7 @@ class LocalComm:
 def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Optional[PackedSet] = None,
             cap: int = TC_DEFAULT_CAP, stats: Optional[dict] = None, tighten: bool = True,
             seg_cap: Optional[int] = None, pilot: Optional[int] = None, comm=None, nd_total: Optional[int] = None,
-            exact_fallback=None, buffers: Optional[dict] = None, ready=None) -> torch.Tensor:
+            exact_fallback=None, buffers: Optional[dict] = None, ready=None, defer: bool = False):
     """int64 [nq, K] ascending keys, identical to ``RankPass(q, d).topk(K, index_base)`` (to the global stable
     ranking when ``d`` is one shard of a database of ``nd_total`` rows and ``comm`` spans the shards).
 
@@ -432,6 +432,8 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     ready   [(row_end, torch.cuda.Event), ...] in row order: rows below row_end of ``d`` are valid once the event has
             completed (a database that is still being uploaded on another stream); the scan is cut at those
             boundaries and every launch waits only for the rows it reads
+    defer   return a callable instead of the keys: everything is enqueued, and calling it reads the verdict (a host
+            sync), redoes failed queries and returns the keys - lets a caller keep two query chunks in flight
     buffers a dict the caller keeps between calls: the multi-GB candidate scratch is allocated once per query-chunk
             size instead of per call
     exact_fallback(sub_q) -> keys for the queries whose candidate lists came out short or overflowed (the exact
@@ -577,20 +579,29 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
             check(L.cmh_topk_verify(_ptr(keys), _ptr(thr_main), nq, K, nd_total, _ptr(b.fail_flags), _ptr(b.fail_count),
                                     st), "cmh_topk_verify")
     phase("exchange_done")
-    n_fail = int(b.fail_count.item())
+    # the verdict is read by `finish`: at once, or - `defer` - when the caller asks for the result, so that the next
+    # query chunk can be enqueued (on another stream) before this one has drained
+    fail_count = b.fail_count.clone() if defer else b.fail_count
+    fail_flags = b.fail_flags.clone() if defer else b.fail_flags
     if stats is not None:
-        stats["n_fail"] = n_fail
         stats["candidates"] = b.cnt.sum(0)
         stats["thr"] = thr_main
         stats["pilot_rows"] = stages
-    if n_fail:
-        rows = torch.nonzero(b.fail_flags, as_tuple=False).squeeze(1)
-        sub = PackedSet(q.sign.index_select(0, rows).contiguous(), None, None, int(rows.numel()), q.bits)
-        if exact_fallback is None:
-            if comm.world > 1:
-                raise RuntimeError("a sharded tensor-core top-K needs exact_fallback")
-            redo = RankPass(sub, d.with_labels(None, 0), need_labels=False).topk(K, index_base)
-        else:
-            redo = exact_fallback(sub)
-        keys.index_copy_(0, rows, redo)
-    return keys
+
+    def finish() -> torch.Tensor:
+        n_fail = int(fail_count.item())
+        if stats is not None:
+            stats["n_fail"] = n_fail
+        if n_fail:
+            rows = torch.nonzero(fail_flags, as_tuple=False).squeeze(1)
+            sub = PackedSet(q.sign.index_select(0, rows).contiguous(), None, None, int(rows.numel()), q.bits)
+            if exact_fallback is None:
+                if comm.world > 1:
+                    raise RuntimeError("a sharded tensor-core top-K needs exact_fallback")
+                redo = RankPass(sub, d.with_labels(None, 0), need_labels=False).topk(K, index_base)
+            else:
+                redo = exact_fallback(sub)
+            keys.index_copy_(0, rows, redo)
+        return keys
+
+    return finish if defer else finish()

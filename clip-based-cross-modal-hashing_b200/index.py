@@ -20,6 +20,27 @@ from . import sharded as _sh
 from .engine import PackedSet
 
 
+class PendingSearch:
+    """Handle of `HammingIndex.search_packed_async`."""
+
+    def __init__(self, finish, sync, keys):
+        self._finish, self._sync, self._keys = finish, sync, keys
+
+    def result(self) -> torch.Tensor:
+        """int64 [Q, K] keys, usable on the caller's current stream."""
+        if self._finish is not None:
+            stream, done = self._sync
+            with torch.cuda.stream(stream):
+                keys = self._finish()                # host sync on the verdict; failed queries redone on that stream
+                redo = torch.cuda.Event()
+                redo.record(stream)
+            cur = torch.cuda.current_stream(keys.device)
+            cur.wait_event(redo)
+            keys.record_stream(cur)
+            self._keys, self._finish = keys, None
+        return self._keys
+
+
 class HammingIndex:
     """Database shard resident on one GPU.
 
@@ -139,6 +160,30 @@ class HammingIndex:
                                        group=self.group, stats=stats, buffers=self._tc_buffers, ready=ready)
         self._upload_done()
         return _sh.topk_sharded(q, self.db, int(K), self.index_base, self.group, ternary=None)
+
+    def search_packed_async(self, q: PackedSet, K: int, stats: Optional[dict] = None) -> "PendingSearch":
+        """`search_packed` without waiting: the search is enqueued on one of two alternating side streams (each with
+        its own scratch) and a handle comes back; `handle.result()` reads the verdict and returns the keys on the
+        caller's stream.  Issuing chunk i+1 before resolving chunk i keeps two chunks in flight: the small
+        kernels, exchanges and ragged last wave of one hide behind the scan of the other.  Handles must be resolved
+        in the order they were issued, at most two outstanding."""
+        dev = self.db.device
+        use_tc = (self.sample is not None and q.valid is None and q.bits == self.db.bits and 1 <= int(K) <= _e.TC_MAX_K)
+        if not use_tc:
+            return PendingSearch(None, None, self.search_packed(q, K, stats))
+        if not hasattr(self, "_lanes"):
+            self._lanes = [(torch.cuda.Stream(dev), {}) for _ in range(2)]
+            self._turn = 0
+        stream, buffers = self._lanes[self._turn % 2]
+        self._turn += 1
+        ready, self._ready = self._ready, None
+        stream.wait_stream(torch.cuda.current_stream(dev))           # the queries (and the database) are ready
+        with torch.cuda.stream(stream):
+            finish = _sh.topk_tc_sharded(q, self.db, int(K), self.index_base, self.nd_total, sample=self.sample,
+                                         group=self.group, stats=stats, buffers=buffers, ready=ready, defer=True)
+            done = torch.cuda.Event()
+            done.record(stream)
+        return PendingSearch(finish, (stream, done), None)
 
     def search(self, qB, K: int):
         """Float query codes in -> (dist float32 [Q, K], index int64 [Q, K]) on the device; pads have index -1."""

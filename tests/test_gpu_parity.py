@@ -572,3 +572,25 @@ def test_sharded_rank_equals_single(dev, name, n_shards):
     single = cu.map_k_detail(T["qB"].to(dev), T["rB"].to(dev), T["qL"], T["rL"], k, 0, topn=topn)
     assert torch.equal(hits, single["hits"])                                       # integer hit counts: exact
     assert abs(float(m.cpu()[0]) - float(single["map"].cpu()[0])) < 1e-7
+
+
+def test_tc_async_two_chunks_in_flight(dev):
+    """`search_packed_async`: chunks enqueued on alternating streams and resolved one step later give the same keys as
+    the blocking search, also when a chunk needs the exact fallback (K-th distance beyond the clamp is impossible
+    here, so the fallback is forced through an absurdly small candidate budget)."""
+    from cmh_b200 import engine
+    from cmh_b200.index import HammingIndex
+    D, K = 5_000_000, 200
+    db = engine.synth_codes(931, 0, D, 64, dev)
+    idx = HammingIndex(db, 3)
+    qs = [engine.synth_codes(940 + i, 0, 100 + 31 * i, 64, dev) for i in range(5)]
+    want = [engine.RankPass(q, db, need_labels=False).topk(K, 3) for q in qs]
+    pending, got = None, []
+    for q in qs:
+        h = idx.search_packed_async(q, K)
+        if pending is not None:
+            got.append(pending.result())
+        pending = h
+    got.append(pending.result())
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
