@@ -100,6 +100,10 @@ def pack_codes(x, device=None, *, binarize: bool = False) -> PackedSet:
     """Sign + bit-pack ``[n, bits]`` codes on the device (kernel K1).  Entries must be in {-1, 0, +1} (what
     `torch.sign` / the argmax heads emit, train/base.py:141-158) unless ``binarize`` is set, in which case the
     sign of any real value is taken (the duplicate API `utils/utils.py:77-78` does that)."""
+    if isinstance(x, PackedSet):                     # already packed (engine level)
+        return x
+    if hasattr(x, "packed") and hasattr(x, "put"):   # codes.CodeBuffer: binarised and packed at the source
+        return x.packed()
     t = _to_tensor(x)
     device = _device_for(device, t)
     owner = x if isinstance(x, torch.Tensor) else None
@@ -152,7 +156,12 @@ def pack_labels(L, device=None) -> Tuple[torch.Tensor, int]:
 
 
 def _prepare(qB, rB, query_L, retrieval_L, rank, binarize=False) -> Tuple[PackedSet, PackedSet]:
-    dev = _device_for(rank, *(x for x in (qB, rB) if isinstance(x, torch.Tensor)))
+    dev = None
+    for x in (qB, rB):                               # packed inputs (PackedSet, CodeBuffer) decide the device
+        if not isinstance(x, torch.Tensor) and isinstance(getattr(x, "device", None), torch.device):
+            dev = x.device
+    if dev is None:
+        dev = _device_for(rank, *(x for x in (qB, rB) if isinstance(x, torch.Tensor)))
     q = pack_codes(qB, dev, binarize=binarize)
     d = pack_codes(rB, dev, binarize=binarize)
     if q.bits != d.bits:

@@ -162,6 +162,51 @@ __global__ void __launch_bounds__(256) pack_rows_generic(const T* __restrict__ x
     warp_count_flush(c0, c1, counters);
 }
 
+// ---- binarise at the source: sign / argmax + pack + scatter by dataset index ---------------------------------------
+// What get_code does per batch (train/base.py:141-146: torch.sign of the encoder output, rows stored at the loader's
+// `index`) and its DCHMT variant (train/base.py:150-158: argmax over [n, bits, 2] logits, class 0 -> -1), written
+// straight into the packed planes: the float [N, bits] buffers never exist.  One warp per row, lane = column.
+//   MODE 0: value x      -> sign bit x > 0, valid bit x != 0 (torch.sign(0) == 0), zeros counted
+//   MODE 1: logits (a,b) -> sign bit b > a (argmax, first maximum wins: a tie is class 0 = -1), valid bit 1
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) pack_scatter_kernel(const T* __restrict__ x, int64_t n, int bits, int64_t ld,
+                                                           const long long* __restrict__ index, int64_t n_out,
+                                                           int w32_out, uint32_t* __restrict__ sign32,
+                                                           uint32_t* __restrict__ valid32,
+                                                           unsigned long long* counters) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long n_zero = 0, n_bad = 0;
+    for (int64_t r = warp; r < n; r += n_warps) {
+        const int64_t dst = index ? (int64_t)index[r] : r;
+        const bool ok = dst >= 0 && dst < n_out;
+        if (!ok) { n_bad += lane == 0; continue; }
+        for (int seg = 0; seg < w32_out; ++seg) {
+            const int col = seg * 32 + lane;
+            const bool live = col < bits;
+            bool pos = false, zero = false;
+            if (live) {
+                if (MODE == 0) {
+                    bool unit;
+                    Cls<T>::get(x[r * ld + col], pos, zero, unit);
+                } else {
+                    const float a = (float)x[r * ld + 2 * (int64_t)col], b = (float)x[r * ld + 2 * (int64_t)col + 1];
+                    pos = b > a;
+                }
+            }
+            const uint32_t sw = __ballot_sync(0xffffffffu, live && pos);
+            const uint32_t vw = __ballot_sync(0xffffffffu, live && !zero);
+            n_zero += live && zero;
+            if (lane == 0) {
+                sign32[dst * w32_out + seg] = sw;
+                if (valid32) valid32[dst * w32_out + seg] = vw;
+            }
+        }
+    }
+    warp_count_flush(n_zero, n_bad, counters);
+}
+
 __device__ __forceinline__ uint64_t splitmix64_dev(uint64_t x) {
     uint64_t z = x + 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -236,6 +281,43 @@ extern "C" int cmh_pack_codes(const void* x, int dtype, int64_t n, int bits, int
     }
     return launch_generic<false>(x, dtype, n, bits, ld, words * 2, (uint32_t*)sign_out, (uint32_t*)valid_out,
                                  counters, st);
+}
+
+extern "C" int cmh_pack_scatter(const void* x, int dtype, int64_t n, int bits, int64_t ld, int mode, const int64_t* index,
+                                int64_t n_out, uint64_t* sign_out, uint64_t* valid_out, unsigned long long* counters,
+                                void* stream) {
+    CMH_REQUIRE(n >= 0 && bits > 0 && n_out >= 0 && (mode == 0 || mode == 1) && ld >= (int64_t)bits * (mode ? 2 : 1),
+                CMH_ERR_ARG, "cmh_pack_scatter: bad shape n=%lld bits=%d ld=%lld mode=%d", (long long)n, bits, (long long)ld, mode);
+    CMH_REQUIRE(bits <= CMH_MAX_BITS, CMH_ERR_UNSUPPORTED, "cmh_pack_scatter: bits=%d > %d", bits, CMH_MAX_BITS);
+    if (n == 0) return CMH_OK;
+    CMH_REQUIRE(x && sign_out, CMH_ERR_ARG, "cmh_pack_scatter: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int w32 = 2 * ((bits + 63) / 64);
+    const int block = 256;
+    int grid = (int)std::min<int64_t>(ceil_div(n * 32, block), (int64_t)sm_count() * 16);
+    if (grid < 1) grid = 1;
+    uint32_t* s32 = reinterpret_cast<uint32_t*>(sign_out);
+    uint32_t* v32 = reinterpret_cast<uint32_t*>(valid_out);
+    const long long* idx = reinterpret_cast<const long long*>(index);
+#define CMH_SCATTER_CASE(DT, T)                                                                                          \
+    case DT:                                                                                                             \
+        if (mode == 0)                                                                                                   \
+            pack_scatter_kernel<T, 0><<<grid, block, 0, st>>>((const T*)x, n, bits, ld, idx, n_out, w32, s32, v32, counters); \
+        else                                                                                                             \
+            pack_scatter_kernel<T, 1><<<grid, block, 0, st>>>((const T*)x, n, bits, ld, idx, n_out, w32, s32, v32, counters); \
+        break;
+    switch (dtype) {
+        CMH_SCATTER_CASE(CMH_F32, float)
+        CMH_SCATTER_CASE(CMH_F16, __half)
+        CMH_SCATTER_CASE(CMH_BF16, __nv_bfloat16)
+        CMH_SCATTER_CASE(CMH_F64, double)
+        default:
+            set_error("cmh_pack_scatter: unsupported dtype %d (floating-point activations only)", dtype);
+            return CMH_ERR_UNSUPPORTED;
+    }
+#undef CMH_SCATTER_CASE
+    CMH_LAUNCH_CHECK("pack_scatter_kernel");
+    return CMH_OK;
 }
 
 extern "C" int cmh_pack_labels(const void* L, int dtype, int64_t n, int nlab, int64_t ld, uint64_t* out,

@@ -95,6 +95,15 @@ int cmh_measure_popc_peak(int iters, int reps, double* popc32_per_s, void* strea
  * {-1, 0, +1}); may be NULL. */
 int cmh_pack_codes(const void* x, int dtype, int64_t n, int bits, int64_t ld,
                    uint64_t* sign_out, uint64_t* valid_out, unsigned long long* counters, void* stream);
+/* Binarise at the source (train/base.py:130-158, get_code / make_hash_code_DCHMT): row i of a batch of encoder
+ * outputs is binarised, packed and written at row index[i] (index == NULL: row i) of the packed planes
+ * sign_out / valid_out (device uint64 [n_out][ceil(bits/64)]; valid_out may be NULL) - the float [N, bits] code
+ * buffers of the reference never exist.
+ *   mode 0: x is [n][bits] (leading dimension ld) of activations: sign bit x > 0, valid bit x != 0 (torch.sign(0) == 0)
+ *   mode 1: x is [n][bits][2] logits (ld >= 2*bits): sign bit = argmax is class 1 (a tie is class 0 = -1), valid bit 1
+ * counters (device uint64 [2], may be NULL) += (#exact zeros, #rows whose index is outside [0, n_out): not written). */
+int cmh_pack_scatter(const void* x, int dtype, int64_t n, int bits, int64_t ld, int mode, const int64_t* index,
+                     int64_t n_out, uint64_t* sign_out, uint64_t* valid_out, unsigned long long* counters, void* stream);
 /* L: device [n][ld] multi-hot (non-negative).  out: device [n][lwords].  neg_counter: device uint64[1],
  * incremented by #entries < 0 (the reference's `dot > 0` predicate is only a set intersection for L >= 0). */
 int cmh_pack_labels(const void* L, int dtype, int64_t n, int nlab, int64_t ld,

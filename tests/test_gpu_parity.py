@@ -594,3 +594,69 @@ def test_tc_async_two_chunks_in_flight(dev):
     got.append(pending.result())
     for g, w in zip(got, want):
         assert torch.equal(g, w)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# binarise at the source: sign / argmax + pack + scatter by dataset index
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bits,dtype", [(64, torch.float32), (16, torch.float32), (100, torch.bfloat16), (128, torch.float16)])
+def test_code_buffer_matches_get_code(dev, bits, dtype):
+    """`CodeBuffer.put` == `torch.sign` + `buffer[index, :] = hash` (train/base.py:141-146) followed by the packer, on
+    shuffled batches of raw activations with exact zeros; `put_argmax` == `make_hash_code_DCHMT` (train/base.py:150-158)."""
+    from cmh_b200 import calc_utils as cu
+    from cmh_b200.codes import CodeBuffer
+    g = torch.Generator().manual_seed(77 + bits)
+    N = 1000
+    acts = torch.randn(N, bits, generator=g)
+    acts[torch.rand(N, bits, generator=g) < 0.02] = 0.0                  # torch.sign(0) == 0: the ternary case
+    acts = acts.to(dtype)
+    perm = torch.randperm(N, generator=g)
+    buf = CodeBuffer(N, bits, dev)
+    ref = torch.empty(N, bits)                                           # the reference's float buffer, :132
+    for lo in range(0, N, 300):                                          # batches of <= 300 like the loaders
+        idx = perm[lo:lo + 300]
+        buf.put(idx.numpy(), acts[idx].to(dev))                          # index arrives as numpy, :139
+        ref[idx, :] = torch.sign(acts[idx].float())                      # :141,145
+    got = buf.packed()
+    want = cu.pack_codes(ref.to(dev))
+    assert torch.equal(got.sign, want.sign)
+    assert (got.valid is None) == (want.valid is None)
+    if got.valid is not None:
+        assert torch.equal(got.valid, want.valid)
+    assert got.n_zero == want.n_zero
+    # DCHMT head: argmax over [n, bits, 2], class 0 -> -1, ties go to class 0
+    logits = torch.randn(N, bits, 2, generator=g)
+    logits[torch.rand(N, bits, generator=g) < 0.05] = 0.25               # exact ties
+    buf2 = CodeBuffer(N, bits, dev)
+    buf2.put_argmax(perm, logits[perm].to(dev))
+    code = torch.argmax(logits, dim=-1)                                  # :154
+    code[code == 0] = -1                                                 # :155
+    want2 = cu.pack_codes(code.float().to(dev))
+    got2 = buf2.packed()
+    assert torch.equal(got2.sign, want2.sign) and got2.valid is None
+    with pytest.raises(IndexError):
+        bad = CodeBuffer(10, bits, dev)
+        bad.put(torch.tensor([3, 10]), acts[:2].to(dev))
+        bad.packed()
+
+
+def test_map_from_code_buffers(dev):
+    """`calc_map_k_matrix` on CodeBuffers == on the float buffers the reference would have filled."""
+    from cmh_b200 import calc_utils as cu
+    from cmh_b200.codes import CodeBuffer
+    from cmh_b200.synth import EvalShape, make_case
+    shape = EvalShape("cb", 150, 4000, 64, 24, 0.15, None, (), 31)
+    t = make_case(shape, clustered=True, zero_query_frac=0.02)
+    qL, rL = torch.from_numpy(t["q_lab"]), torch.from_numpy(t["r_lab"])
+    want = cu.calc_map_k_matrix(torch.from_numpy(t["q_img"]).to(dev), torch.from_numpy(t["r_txt"]).to(dev), qL, rL, None, 0)
+    q, r = CodeBuffer(shape.n_query, 64, dev), CodeBuffer(shape.n_db, 64, dev)
+    g = torch.Generator().manual_seed(5)
+    # raw "activations": the +-1 codes scaled by positive noise keep their signs
+    for buf, codes in ((q, t["q_img"]), (r, t["r_txt"])):
+        x = torch.from_numpy(codes) * (0.1 + torch.rand(codes.shape, generator=g))
+        perm = torch.randperm(x.shape[0], generator=g)
+        for lo in range(0, x.shape[0], 300):
+            idx = perm[lo:lo + 300]
+            buf.put(idx, x[idx].to(dev))
+    got = cu.calc_map_k_matrix(q, r, qL, rL, None, 0)
+    assert abs(float(got) - float(want)) < 1e-7
