@@ -27,7 +27,7 @@ DTYPE_CODES = {"float32": 0, "float16": 1, "bfloat16": 2, "float64": 3, "int8": 
 # every symbol include/cmh_b200.h declares (tests check that the built library exports each of them)
 EXPORTS = (
     "cmh_abi_version", "cmh_last_error", "cmh_device_info", "cmh_launch_count", "cmh_measure_popc_peak",
-    "cmh_pack_codes", "cmh_pack_scatter", "cmh_pack_labels", "cmh_synth_codes",
+    "cmh_pack_codes", "cmh_pack_scatter", "cmh_unpack_codes", "cmh_pack_labels", "cmh_synth_codes",
     "cmh_hamming_dense", "cmh_neighbor_dense",
     "cmh_eval_plan", "cmh_eval_plan_design", "cmh_eval_hist", "cmh_eval_rank",
     "cmh_finalize_map", "cmh_finalize_topn", "cmh_finalize_pr_workspace_bytes", "cmh_finalize_pr",
@@ -114,6 +114,7 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cmh_launch_count.restype = ctypes.c_ulonglong
     L.cmh_measure_popc_peak.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double), vp]
     L.cmh_pack_codes.argtypes = [vp, i32, i64, i32, i64, vp, vp, vp, vp]
+    L.cmh_unpack_codes.argtypes = [vp, vp, i64, i32, vp, i64, vp]
     L.cmh_pack_scatter.argtypes = [vp, i32, i64, i32, i64, i32, vp, i64, vp, vp, vp, vp]
     L.cmh_pack_labels.argtypes = [vp, i32, i64, i32, i64, vp, vp, vp]
     L.cmh_synth_codes.argtypes = [u64, i64, i64, i32, vp, vp]

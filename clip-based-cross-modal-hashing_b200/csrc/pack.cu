@@ -207,6 +207,21 @@ __global__ void __launch_bounds__(256) pack_scatter_kernel(const T* __restrict__
     warp_count_flush(n_zero, n_bad, counters);
 }
 
+// ---- unpack: packed planes -> float32 {-1, 0, +1} codes (the .mat export of train/base.py:307-349 stores float arrays) -----
+__global__ void __launch_bounds__(256) unpack_codes_kernel(const uint32_t* __restrict__ sign32,
+                                                           const uint32_t* __restrict__ valid32, int64_t n, int bits,
+                                                           int w32, float* __restrict__ out, int64_t ld) {
+    const int64_t total = n * (int64_t)bits;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / bits;
+        const int c = (int)(i - r * bits);
+        const uint32_t sw = sign32[r * w32 + (c >> 5)];
+        const uint32_t vw = valid32 ? valid32[r * w32 + (c >> 5)] : 0xffffffffu;
+        const bool v = (vw >> (c & 31)) & 1u, p = (sw >> (c & 31)) & 1u;
+        out[r * ld + c] = v ? (p ? 1.f : -1.f) : 0.f;
+    }
+}
+
 __device__ __forceinline__ uint64_t splitmix64_dev(uint64_t x) {
     uint64_t z = x + 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -317,6 +332,21 @@ extern "C" int cmh_pack_scatter(const void* x, int dtype, int64_t n, int bits, i
     }
 #undef CMH_SCATTER_CASE
     CMH_LAUNCH_CHECK("pack_scatter_kernel");
+    return CMH_OK;
+}
+
+extern "C" int cmh_unpack_codes(const uint64_t* sign, const uint64_t* valid, int64_t n, int bits, float* out, int64_t ld,
+                                void* stream) {
+    CMH_REQUIRE(n >= 0 && bits > 0 && bits <= CMH_MAX_BITS && ld >= bits, CMH_ERR_ARG,
+                "cmh_unpack_codes: bad shape n=%lld bits=%d ld=%lld", (long long)n, bits, (long long)ld);
+    if (n == 0) return CMH_OK;
+    CMH_REQUIRE(sign && out, CMH_ERR_ARG, "cmh_unpack_codes: NULL pointer");
+    const int64_t total = n * (int64_t)bits;
+    const int grid = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
+    unpack_codes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t*>(sign),
+                                                              reinterpret_cast<const uint32_t*>(valid), n, bits,
+                                                              2 * ((bits + 63) / 64), out, ld);
+    CMH_LAUNCH_CHECK("unpack_codes_kernel");
     return CMH_OK;
 }
 

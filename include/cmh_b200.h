@@ -95,6 +95,9 @@ int cmh_measure_popc_peak(int iters, int reps, double* popc32_per_s, void* strea
  * {-1, 0, +1}); may be NULL. */
 int cmh_pack_codes(const void* x, int dtype, int64_t n, int bits, int64_t ld,
                    uint64_t* sign_out, uint64_t* valid_out, unsigned long long* counters, void* stream);
+/* Inverse of cmh_pack_codes: float32 [n][bits] (leading dimension ld) of {-1, 0, +1} from the packed planes (valid may
+ * be NULL: every entry is +-1).  The reference's .mat export (train/base.py:307-349) stores the codes as float arrays. */
+int cmh_unpack_codes(const uint64_t* sign, const uint64_t* valid, int64_t n, int bits, float* out, int64_t ld, void* stream);
 /* Binarise at the source (train/base.py:130-158, get_code / make_hash_code_DCHMT): row i of a batch of encoder
  * outputs is binarised, packed and written at row index[i] (index == NULL: row i) of the packed planes
  * sign_out / valid_out (device uint64 [n_out][ceil(bits/64)]; valid_out may be NULL) - the float [N, bits] code

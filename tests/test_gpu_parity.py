@@ -7,6 +7,7 @@ through the C ABI of include/cmh_b200.h), against
 Bars: rankings / counts / packed words bit-exact; mAP, AP, precision, PR within 1e-6 (BASELINE.json north star).
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -660,3 +661,35 @@ def test_map_from_code_buffers(dev):
             buf.put(idx, x[idx].to(dev))
     got = cu.calc_map_k_matrix(q, r, qL, rL, None, 0)
     assert abs(float(got) - float(want)) < 1e-7
+
+
+def test_mat_export_round_trip(dev, tmp_path):
+    """`export.save_mat` writes the reference's `.mat` schema (train/base.py:328-349) from float or packed codes, and the
+    evaluation of the loaded arrays reproduces the mAP."""
+    import scipy.io as scio
+    from cmh_b200 import calc_utils as cu, export
+    from cmh_b200.codes import CodeBuffer
+    from cmh_b200.synth import EvalShape, make_case
+    shape = EvalShape("mat", 60, 900, 48, 24, 0.15, None, (), 41)
+    t = make_case(shape, clustered=True, ternary_frac=0.01)
+    qL, rL = torch.from_numpy(t["q_lab"]), torch.from_numpy(t["r_lab"])
+    f = {k: torch.from_numpy(t[k]).to(dev) for k in ("q_img", "q_txt", "r_img", "r_txt")}
+    # packed route: buffers filled at the source
+    bufs = {}
+    for k, x in f.items():
+        b = CodeBuffer(x.shape[0], shape.bits, dev)
+        b.put(None, x)
+        bufs[k] = b
+        assert torch.equal(export.unpack_codes(b), torch.sign(x))            # unpack is the inverse of sign + pack
+    p1 = export.save_mat(f["q_img"], f["q_txt"], f["r_img"], f["r_txt"], qL, rL, str(tmp_path / "a"), 48, "flickr", "i2t")
+    p2 = export.save_mat(bufs["q_img"], bufs["q_txt"], bufs["r_img"], bufs["r_txt"], qL, rL, str(tmp_path / "b"), None,
+                         "flickr", "i2t")
+    assert os.path.basename(p1) == "48-ours-flickr-i2t.mat" == os.path.basename(p2)
+    m1, m2 = scio.loadmat(p1), export.load_mat(p2)
+    for k in export.MAT_KEYS:
+        assert m1[k].dtype == np.float32 and np.array_equal(m1[k], m2[k])
+    assert np.array_equal(m1["q_img"], t["q_img"]) and np.array_equal(m1["r_l"], t["r_lab"])
+    want = cu.calc_map_k_matrix(f["q_img"], f["r_txt"], qL, rL, None, 0)
+    got = cu.calc_map_k_matrix(torch.from_numpy(m2["q_img"]).to(dev), torch.from_numpy(m2["r_txt"]).to(dev),
+                               torch.from_numpy(m2["q_l"]), torch.from_numpy(m2["r_l"]), None, 0)
+    assert float(got) == float(want)
