@@ -373,7 +373,7 @@ def main_native(args):
             return (time.perf_counter() - t0) / reps * 1e3, out
 
         also = {}
-        for name in ("c1", "c2-16", "c2-32", "c2-64", "c3"):
+        for name in ("c1", "c2-16", "c2-32", "c2-64", "c3", "c5"):     # c5: the eval stage of config 5
             shape = CONFIGS[name]
             t = make_case(shape, clustered=True, zero_query_frac=0.01)
             qi, qt, ri, rt = (torch.from_numpy(t[k]).to(dev) for k in ("q_img", "q_txt", "r_img", "r_txt"))

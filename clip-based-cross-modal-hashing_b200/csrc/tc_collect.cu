@@ -581,14 +581,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
                 release();
                 continue;
             }
-            if (hq != nullptr && (round & (TC_REFRESH - 1)) == TC_REFRESH - 1) {
-                // tighten: once K rows at dist <= thr0 - j are known, nothing beyond that bucket can be in the top K
-                const uint4 c4 = __ldcg(reinterpret_cast<const uint4*>(hq));
-                const uint32_t K = (uint32_t)a.K;
-                const uint32_t c3 = c4.w, c2 = c3 + c4.z, c1 = c2 + c4.y;
-                const int j = c3 >= K ? 3 : (c2 >= K ? 2 : (c1 >= K ? 1 : 0));
-                thr = thr0 - j;
-            }
             // two slices (register buffers) per trip to TMEM
             uint32_t va[32], vb[32];
             if (PACKED) {
@@ -609,6 +601,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
                 if (qrow == 0) TC_TRACE(2 + grp, round, 2);
                 release();
                 scan2(va, row0 + 64, vb, row0 + 96);
+            }
+            if (hq != nullptr && (round & (TC_REFRESH - 1)) == TC_REFRESH - 1) {
+                // tighten: once K rows at dist <= thr0 - j are known, nothing beyond that bucket can be in the top K.
+                // Here, after the buffer went back, the L2 round trip of the counters costs the pipeline nothing.
+                const uint4 c4 = __ldcg(reinterpret_cast<const uint4*>(hq));
+                const uint32_t K = (uint32_t)a.K;
+                const uint32_t c3 = c4.w, c2 = c3 + c4.z, c1 = c2 + c4.y;
+                const int j = c3 >= K ? 3 : (c2 >= K ? 2 : (c1 >= K ? 1 : 0));
+                thr = thr0 - j;
             }
             if (qrow == 0) TC_TRACE(2 + grp, round, 4);
         }
