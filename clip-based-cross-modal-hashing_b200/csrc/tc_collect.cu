@@ -64,8 +64,8 @@ constexpr int TC_PROD_WARPS = 4;
 constexpr int TC_EPI_WARPS = 16;  // 4 groups of 4 warps; group g drains buffer g
 constexpr int TC_THREADS = (TC_MMA_WARPS + TC_PROD_WARPS + TC_EPI_WARPS) * 32;
 // registers per thread: launched with 80 (768 threads); the issuer and producer warpgroups hand theirs to the 16 epilogue
-// warps, which keep two 32-column slices of accumulators in flight:  24 * 128 + 40 * 128 + 104 * 512 = 80 * 768
-constexpr int TC_REGS_MMA = 24, TC_REGS_PROD = 40, TC_REGS_EPI = 104;
+// warps, which keep two slices of accumulators in flight:  32 * 128 + 32 * 128 + 104 * 512 = 80 * 768
+constexpr int TC_REGS_MMA = 32, TC_REGS_PROD = 32, TC_REGS_EPI = 104;
 static_assert(TC_REGS_MMA * TC_MMA_WARPS * 32 + TC_REGS_PROD * TC_PROD_WARPS * 32 + TC_REGS_EPI * TC_EPI_WARPS * 32 <=
               80 * TC_THREADS, "register budget");
 constexpr int TC_RING = 8;        // packed database tiles in flight (bulk copies)
