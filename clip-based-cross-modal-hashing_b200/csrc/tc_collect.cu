@@ -123,6 +123,18 @@ template <int N>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+// one lane of a converged warp (warp-uniform code around it lets the operands live in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0u;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // 64 consecutive columns, two per register: column 2i in the low half of v[i], column 2i+1 in the high half (the
 // accumulators of 64-bit codes fit 16 bits, so their low halves are the exact values)
@@ -361,41 +373,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
         // for every tile spends ~300 cycles per tile on instruction latency alone (measured), more than the tensor
         // pipe needs for it; four issuers overlap that latency.
         reg_dec<TC_REGS_MMA>();
-        if (lane == 0) {
+        {
+            // The whole warp runs the loop and one elected lane issues: with warp-uniform control flow and a provably
+            // uniform warp index the descriptors live in uniform registers and tcgen05.mma takes them as they are
+            // (under `if (lane == 0)` every operand went through an ELECT / R2UR loop: ~90 instructions per tile on the
+            // pipeline's critical path).
+            const int w = __shfl_sync(0xffffffffu, warp, 0);
             constexpr uint32_t idesc = umma_idesc_i8(TC_M, TC_NM);
             const uint32_t b_addr = smem_u32(sB);
             const bool no_mma = (a.probe & 1) != 0;
-            const uint32_t d_tmem = tmem_base + warp * TC_NM;
-            const uint32_t a_addr = smem_u32(sA) + (warp % T) * A_ALL;           // this issuer's query tile
+            const uint32_t d_tmem = tmem_base + w * TC_NM;
+            const uint32_t a_addr = smem_u32(sA) + (w % T) * A_ALL;              // this issuer's query tile
             const uint64_t bias_a = umma_desc(a_addr + 2 * A_TILE, TC_M * 16, 128);
             const uint64_t bias_b = umma_desc(smem_u32(sW), TC_NM * 16, 128);
             int round = 0;
+            int s = (w / T) % TC_STAGES;                     // stage of this issuer's current iteration
+            uint32_t ph = ((w / T) / TC_STAGES) & 1;
 #pragma unroll 1
-            for (int it = warp; it < n_iters; it += TC_MMA_WARPS, ++round) {
-                const int i = it / T;
-                const int s = i % TC_STAGES;
+            for (int it = w; it < n_iters; it += TC_MMA_WARPS, ++round) {
                 TC_TRACE(0, it, 3);
-                mbar_wait(&b_full[s], (i / TC_STAGES) & 1);
+                mbar_wait(&b_full[s], ph);
                 TC_TRACE(0, it, 0);
-                mbar_wait(&t_empty[warp], (round & 1) ^ 1);
+                mbar_wait(&t_empty[w], (round & 1) ^ 1);
                 tc_fence_after();
                 TC_TRACE(0, it, 1);
-                if (!no_mma) {
-                    umma_i8(d_tmem, bias_a, bias_b, idesc, 0u);      // acc = bias_q
+                if (elect_one()) {
+                    if (!no_mma) {
+                        umma_i8(d_tmem, bias_a, bias_b, idesc, 0u);  // acc = bias_q
 #pragma unroll
-                    for (int f = 0; f < 2; ++f) {            // field 0: rows 0..127 (+-1); field 1: rows 128..255 (+-S)
+                        for (int f = 0; f < 2; ++f)          // field 0: rows 0..127 (+-1); field 1: rows 128..255 (+-S)
 #pragma unroll
-                        for (int k = 0; k < KSTEPS; ++k) {
-                            const uint64_t ad = umma_desc(a_addr + f * A_TILE + k * 2 * (TC_M * 16), TC_M * 16, 128);
-                            const uint64_t bd = umma_desc(
-                                b_addr + s * B_TILE + k * 2 * (TC_N * 16) + f * (TC_NM * 16), TC_N * 16, 128);
-                            umma_i8(d_tmem, ad, bd, idesc, 1u);
-                        }
+                            for (int k = 0; k < KSTEPS; ++k)
+                                umma_i8(d_tmem, umma_desc(a_addr + f * A_TILE + k * 2 * (TC_M * 16), TC_M * 16, 128),
+                                        umma_desc(b_addr + s * B_TILE + k * 2 * (TC_N * 16) + f * (TC_NM * 16), TC_N * 16, 128),
+                                        idesc, 1u);
                     }
+                    umma_commit(&t_full[w]);
+                    umma_commit(&b_empty[s]);
                 }
-                umma_commit(&t_full[warp]);
-                umma_commit(&b_empty[s]);
+                __syncwarp();
                 TC_TRACE(0, it, 2);
+                s += TC_MMA_WARPS / T;                       // next iteration of this issuer: 4 / T tiles further
+                if (s >= TC_STAGES) { s -= TC_STAGES; ph ^= 1; }
             }
         }
     } else if (warp < TC_MMA_WARPS + TC_PROD_WARPS) {
