@@ -58,8 +58,8 @@ def parse_args():
 def config_dict(args, world):
     return {"workload": "c4: 64-bit exact stable top-1000 Hamming retrieval, 100M-row database, one query chunk per step",
             "bits": BITS, "topk": TOPK, "db_rows": args.db_rows, "queries_per_step": args.queries,
-            "pipelining": "two query chunks in flight (chunk i+1 is enqueued before chunk i is resolved); every chunk is "
-                          "resolved and verified inside the timed region",
+            "pipelining": "two query chunks in flight when a wave of the scan is short (1 GPU; >= 8 GPUs), else one; every "
+                          "chunk is resolved and verified inside the timed region",
             "sharding": f"database rows split contiguously over {world} GPU(s); queries replicated; all-reduced threshold histograms, NCCL all-to-all by query slice + merge + all-gather"
                         if world > 1 else "single GPU holds the whole database",
             "l2": "per-step working set (packed shard + candidate segments, >1 GB) exceeds the 126 MB L2; no explicit flush",
@@ -260,11 +260,20 @@ def main_native(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # Two query chunks in flight (chunk i+1 enqueued on the other of two streams before chunk i is resolved) hide the
+    # small kernels and the exchange latency of one chunk behind the scan of the next - but the NCCL kernels of chunk i
+    # then have to find SM slots while the scan of chunk i+1 holds every SM with one long-lived CTA, so they wait for
+    # CTA boundaries.  Measured: +2 % at 8 GPUs (a wave of the scan lasts 1.5 ms), -25 % at 2 GPUs (6 ms waves).  The
+    # bench therefore pipelines only when a wave of the scan is short; a single GPU has no collectives to delay.
+    est_wave_ms = Q * (hi - lo) / 1.6e13 * 1e3 / 4
+    pipelined = world == 1 or est_wave_ms < 2.0
+
     def run_steps(n, stats):
-        # two query chunks in flight: chunk i+1 is enqueued (on the other of two streams) before chunk i is resolved, so
-        # the small kernels, the exchange and the ragged last wave of one chunk hide behind the scan of the next
         pending, keys = None, None
         for _ in range(n):
+            if not pipelined:
+                keys = index.search_packed(q_packed, K, stats=stats)
+                continue
             h = index.search_packed_async(q_packed, K, stats=stats)
             if pending is not None:
                 keys = pending.result()
