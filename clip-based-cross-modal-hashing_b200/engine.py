@@ -448,10 +448,11 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     per_rank = -(-nq // comm.world)                  # queries merged by each rank (the last slice may be padded)
     keys_all = torch.empty((per_rank * comm.world, K), dtype=torch.int64, device=dev)
     keys = keys_all[:nq]
-    if nq == 0:
-        return keys
-    if nd_total == 0:
-        return keys.fill_(-1)
+    if nq == 0 or nd_total == 0:
+        if nq and nd_total == 0:
+            keys.fill_(-1)
+        done = keys
+        return (lambda: done) if defer else done
     if keys_all.shape[0] > nq:
         keys_all[nq:].fill_(-1)
     L = _cabi.lib()

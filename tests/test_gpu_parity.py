@@ -693,3 +693,25 @@ def test_mat_export_round_trip(dev, tmp_path):
     got = cu.calc_map_k_matrix(torch.from_numpy(m2["q_img"]).to(dev), torch.from_numpy(m2["r_txt"]).to(dev),
                                torch.from_numpy(m2["q_l"]), torch.from_numpy(m2["r_l"]), None, 0)
     assert float(got) == float(want)
+
+
+def test_tc_edge_cases(dev):
+    """Empty query sets, K beyond the database, a database shorter than one tile, 128-bit codes through the index."""
+    from cmh_b200 import engine
+    from cmh_b200.index import HammingIndex
+    db = engine.synth_codes(951, 0, 1_200_000, 128, dev)
+    idx = HammingIndex(db, 0)
+    assert idx.sample is not None                                      # tensor-core path
+    q0 = engine.synth_codes(952, 0, 0, 128, dev)
+    assert tuple(idx.search_packed(q0, 10).shape) == (0, 10)
+    assert tuple(idx.search_packed_async(q0, 10).result().shape) == (0, 10)
+    q = engine.synth_codes(953, 0, 70, 128, dev)
+    want = engine.RankPass(q, db, need_labels=False).topk(64, 0)
+    assert torch.equal(idx.search_packed(q, 64), want)
+    assert torch.equal(idx.search_packed_async(q, 64).result(), want)
+    tiny = db.rows(0, 100)
+    got = engine.topk_tc(q, tiny, 300, 0)                               # K > D: pads
+    want = engine.RankPass(q, tiny, need_labels=False).topk(300, 0)
+    assert torch.equal(got, want) and bool((got[:, 100:] == -1).all())
+    big_k = idx.search_packed(q, 5000)                                  # K beyond the tensor path's limit: exact path
+    assert torch.equal(big_k, engine.RankPass(q, db, need_labels=False).topk(5000, 0))
