@@ -697,8 +697,8 @@ __global__ void __launch_bounds__(128) tc_cand_hist_kernel(const uint64_t* __res
 }
 
 __global__ void __launch_bounds__(256) tc_choose_kernel(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ overflow,
-                                                        int64_t nq, int nb, double need, const int32_t* __restrict__ thr_in,
-                                                        int32_t* __restrict__ thr_out) {
+                                                        int64_t nq, int nb, double need, int offset,
+                                                        const int32_t* __restrict__ thr_in, int32_t* __restrict__ thr_out) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     const int t_in = thr_in[q];
@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(256) tc_choose_kernel(const uint32_t* __restri
         double cum = 0.0;
         for (int b = 0; b <= min(t_in, nb - 1); ++b) {
             cum += (double)hist[q * nb + b];
-            if (cum >= need) { t = b; break; }
+            if (cum >= need) { t = min(t_in, b + offset); break; }
         }
     }
     thr_out[q] = t;
@@ -952,7 +952,18 @@ extern "C" int cmh_tc_choose(const uint32_t* hist, const uint32_t* overflow, int
     CMH_REQUIRE(hist && thr_in && thr_out, CMH_ERR_ARG, "cmh_tc_choose: NULL pointer");
     const double kf = (double)K * (double)n_seen / (double)std::max<int64_t>(nd, 1);
     const double need = n_seen >= nd ? (double)std::min<int64_t>(K, nd) : kf + sigma * std::sqrt(kf) + 4.0;
-    tc_choose_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, (cudaStream_t)stream>>>(hist, overflow, nq, nb, need, thr_in, thr_out);
+    tc_choose_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, (cudaStream_t)stream>>>(hist, overflow, nq, nb, need, 0, thr_in, thr_out);
+    CMH_LAUNCH_CHECK("tc_choose_kernel");
+    return CMH_OK;
+}
+
+extern "C" int cmh_tc_choose_prefix(const uint32_t* hist, const uint32_t* overflow, int64_t nq, int nb, int K,
+                                    const int32_t* thr_in, int32_t* thr_out, void* stream) {
+    CMH_REQUIRE(nq >= 0 && nb >= 1 && K >= 1, CMH_ERR_ARG, "cmh_tc_choose_prefix: bad sizes");
+    if (nq == 0) return CMH_OK;
+    CMH_REQUIRE(hist && thr_in && thr_out, CMH_ERR_ARG, "cmh_tc_choose_prefix: NULL pointer");
+    tc_choose_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, (cudaStream_t)stream>>>(hist, overflow, nq, nb, (double)K, -1, thr_in,
+                                                                                   thr_out);
     CMH_LAUNCH_CHECK("tc_choose_kernel");
     return CMH_OK;
 }

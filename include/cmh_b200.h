@@ -215,6 +215,12 @@ int cmh_tc_cand_hist(const uint64_t* cand, const uint32_t* cnt, int64_t nq, int 
  * n_seen = rows behind the histogram), never above thr_in[q]; thr_in[q] when overflow[q] (overflow may be NULL). */
 int cmh_tc_choose(const uint32_t* hist, const uint32_t* overflow, int64_t nq, int nb, int64_t n_seen, int64_t nd, int K,
                   double sigma, const int32_t* thr_in, int32_t* thr_out, void* stream);
+/* The prefix rule (exact, no statistics): hist holds the candidates of rows that ALL precede the rows still to be
+ * scanned in index order.  If K of them lie at dist <= b, a later row at dist >= b ranks after all K (larger or equal
+ * distance, larger index - the stable tie order), so the rest of the database only has to be searched below b:
+ * thr_out[q] = min(thr_in[q], b - 1) for the smallest such b; thr_in[q] when there is none (or overflow[q]). */
+int cmh_tc_choose_prefix(const uint32_t* hist, const uint32_t* overflow, int64_t nq, int nb, int K, const int32_t* thr_in,
+                         int32_t* thr_out, void* stream);
 /* thr[q] from a histogram (cmh_eval_hist, binary mode, nb = bits + 1) over a SAMPLE of n_sample rows of an nd-row
  * shard: smallest bucket whose cumulative sample count reaches K*f + 6*sqrt(K*f) + 8 (f = n_sample / nd), exactly
  * min(K, nd) when n_sample == nd. */
