@@ -58,8 +58,7 @@ def parse_args():
 def config_dict(args, world):
     return {"workload": "c4: 64-bit exact stable top-1000 Hamming retrieval, 100M-row database, one query chunk per step",
             "bits": BITS, "topk": TOPK, "db_rows": args.db_rows, "queries_per_step": args.queries,
-            "pipelining": "two query chunks in flight when a wave of the scan is short (1 GPU; >= 8 GPUs), else one; every "
-                          "chunk is resolved and verified inside the timed region",
+            "pipelining": "none: one query chunk at a time, resolved and verified before the next is enqueued",
             "sharding": f"database rows split contiguously over {world} GPU(s); queries replicated; all-reduced threshold histograms, NCCL all-to-all by query slice + merge + all-gather"
                         if world > 1 else "single GPU holds the whole database",
             "l2": "per-step working set (packed shard + candidate segments, >1 GB) exceeds the 126 MB L2; no explicit flush",
@@ -260,13 +259,11 @@ def main_native(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # Two query chunks in flight (chunk i+1 enqueued on the other of two streams before chunk i is resolved) hide the
-    # small kernels and the exchange latency of one chunk behind the scan of the next - but the NCCL kernels of chunk i
-    # then have to find SM slots while the scan of chunk i+1 holds every SM with one long-lived CTA, so they wait for
-    # CTA boundaries.  Measured: +2 % at 8 GPUs (a wave of the scan lasts 1.5 ms), -25 % at 2 GPUs (6 ms waves).  The
-    # bench therefore pipelines only when a wave of the scan is short; a single GPU has no collectives to delay.
-    est_wave_ms = Q * (hi - lo) / 1.6e13 * 1e3 / 4
-    pipelined = world == 1 or est_wave_ms < 2.0
+    # One query chunk at a time.  `search_packed_async` (two chunks in flight on alternating streams) is available, but
+    # with one long-lived 768-thread CTA per SM the small kernels and the NCCL kernels between the launches of one chunk
+    # only get SM slots at CTA boundaries of the other chunk's scan: measured -25 % at 2 GPUs, and a loss on a single GPU
+    # too once the search became a chain of six launches with refinement kernels in between.
+    pipelined = False
 
     def run_steps(n, stats):
         pending, keys = None, None
@@ -280,7 +277,10 @@ def main_native(args):
             pending = h
         return pending.result() if pending is not None else keys
 
-    keys = run_steps(args.warmup, {"time_collect": True, "time_phases": True})    # the timed code path, kernels loaded
+    # warm-up on the timed code path (kernels loaded).  Its result is not kept: a third live [Q, K] key buffer next to
+    # the two the loop alternates between sends the caching allocator to cudaMalloc in the middle of the timed region
+    # (measured: 1-70 ms in the second timed step, wherever the warm-up ended).
+    run_steps(args.warmup, {"time_collect": True, "time_phases": True})
     barrier()
     t_region0 = time.perf_counter()
     launches0 = lib.cmh_launch_count()
