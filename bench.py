@@ -448,9 +448,14 @@ def main_native(args):
             "algorithmic_ops_per_pair": ops_per_pair, "pairs_per_launch_set": pairs_shard,
             "kernel_ms_per_step": collect_ms, "phase_ms_per_step": phases,
             "in_situ_ceilings_ms": ceilings,
-            "note": "the kernel issues 5 K-steps per 4 algorithmic ones (the per-query threshold rides in a bias K-step), "
-                    "so 0.8 is the highest fraction this design can reach; mma_only / drain_only / no_hits are the same "
-                    "launch over the whole shard with the TMEM drain / the MMAs / the hit path disabled",
+            "note": "the kernel issues 5 K-steps per 4 algorithmic ones (the per-query threshold rides in a bias K-step); "
+                    "mma_only / drain_only / no_hits are the same launch over the whole shard with the TMEM drain / the "
+                    "MMAs / the hit path disabled.  mma_only is the tensor pipe's own ceiling for this instruction "
+                    "stream (its issued rate, 1.25 x algorithmic ops / mma_only time, is above the cuBLAS-bf16-derived "
+                    "peak used here: kind::i8 M128 N128 K32 sustains close to the nominal 4.5 POP/s), so frac is "
+                    "measured against the driver's denominator, not against what the pipe can do",
+            "issued_tops_mma_only": (pairs_shard * ops_per_pair * 1.25 / (ceilings["mma_only_ms"] * 1e-3) / 1e12
+                                     if ceilings.get("mma_only_ms") else None),
             "traffic": traffic,
             "hbm": {"achieved": algo_bytes / (collect_ms * 1e-3) / 1e9 if collect_ms else None, "peak": hbm_peak,
                     "unit": "GB/s", "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",

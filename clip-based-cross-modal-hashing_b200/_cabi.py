@@ -33,7 +33,7 @@ EXPORTS = (
     "cmh_finalize_map", "cmh_finalize_topn", "cmh_finalize_pr_workspace_bytes", "cmh_finalize_pr",
     "cmh_map_k_workspace_bytes", "cmh_map_k",
     "cmh_topk", "cmh_topk_merge",
-    "cmh_tc_supported", "cmh_tc_plan", "cmh_tc_collect", "cmh_tc_probe", "cmh_tc_cand_hist", "cmh_tc_choose", "cmh_tc_choose_prefix",
+    "cmh_tc_supported", "cmh_tc_plan", "cmh_tc_collect", "cmh_tc_probe", "cmh_tc_cand_hist", "cmh_tc_choose", "cmh_tc_choose_prefix", "cmh_tc_choose_seen",
     "cmh_topk_threshold", "cmh_topk_finalize", "cmh_topk_verify",
 )
 
@@ -140,6 +140,7 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cmh_tc_cand_hist.argtypes = [vp, vp, i64, i32, i32, i32, i32, i32, vp, vp, vp]
     L.cmh_tc_choose.argtypes = [vp, vp, i64, i32, i64, i64, i32, ctypes.c_double, vp, vp, vp]
     L.cmh_tc_choose_prefix.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp]
+    L.cmh_tc_choose_seen.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp]
     L.cmh_topk_verify.argtypes = [vp, vp, i64, i32, i64, vp, vp, vp]
     L.cmh_tc_probe.argtypes = [vp, i64, vp, i64, i32, vp, i32, i32, vp, vp, vp, i32, vp]
     L.cmh_topk_threshold.argtypes = [vp, i64, i32, i64, i64, i32, vp, vp]

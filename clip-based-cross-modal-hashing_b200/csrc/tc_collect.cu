@@ -71,9 +71,9 @@ static_assert(TC_REGS_MMA * TC_MMA_WARPS * 32 + TC_REGS_PROD * TC_PROD_WARPS * 3
 constexpr int TC_RING = 8;        // packed database tiles in flight (bulk copies)
 constexpr int TC_MAX_CHUNKS = 1024;  // candidate segments per query (cmh_topk_finalize walks them)
 constexpr int TC_REFRESH = 16;    // tiles (per epilogue group) between threshold refreshes
-constexpr int TC_PARK = 4;        // lanes of a warp that share one parking slot of the hit path
-constexpr int TC_BACKLOG = 2;     // parking slots per epilogue warp
-constexpr int TC_PARK_WORDS = TC_PARK * 36 + 4;   // per lane 32 registers + a block bitmap (16-byte rows); then lane mask, first row
+constexpr int TC_PARK = 4;        // flagged lanes of a warp parked per trip (one __syncwarp)
+constexpr int TC_BACKLOG = 8;     // parked slices an epilogue warp can hold (power of two)
+constexpr int TC_PARK_WORDS = 36; // one parked slice: 32 registers, then owner lane, first row (lo, hi), pad
 constexpr int TC_BIAS_SLOTS = 12; // K slots of the bias step that carry weight 127 (the 13th carries weight 1)
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------------------
@@ -207,59 +207,6 @@ struct TcArgs {
     int probe;              // measurement aid (cmh_tc_probe): 1 no tcgen05.mma, 2 no TMEM drain, 4 drain without scan,
                             // 8 hits decoded but not stored, 16 parked hits dropped, 32 flagged slices not parked
 };
-
-// Working off one parked slice of the hit path (see the epilogue).  Out of line on purpose: ONE copy of this code in
-// the kernel - the epilogue's instruction footprint decides whether the instruction cache holds the pipeline.
-// `mine`: this lane's 32 parked registers + the bitmap of the 8-register blocks whose partial AND showed a flag.
-template <int WORDS>
-__device__ __noinline__ uint32_t tc_work_off(const uint32_t* mine, int64_t row0, int64_t c_end, int thr, int thr0,
-                                             int dot_thr0, int bits, uint64_t* seg, uint32_t pos, uint32_t seg_cap,
-                                             uint32_t* hq, uint32_t index_base, bool store) {
-    constexpr int FIELD = WORDS == 1 ? 8 : 10;
-    constexpr bool PACKED = WORDS == 1;
-    constexpr uint32_t FLAG_LO = 1u << (FIELD - 1), FLAG_HI = 1u << (2 * FIELD - 1);
-    constexpr uint32_t FLAGS = PACKED ? (FLAG_LO | FLAG_HI) * 0x10001u : (FLAG_LO | FLAG_HI);
-    uint32_t blocks = mine[32];
-#pragma unroll 1
-    while (blocks) {
-        const int b = __ffs(blocks) - 1;
-        blocks &= blocks - 1;
-        const uint4 w0 = *reinterpret_cast<const uint4*>(mine + 8 * b);
-        const uint4 w1 = *reinterpret_cast<const uint4*>(mine + 8 * b + 4);
-        uint32_t regs = ((~w0.x & FLAGS) ? 1u : 0u) | ((~w0.y & FLAGS) ? 2u : 0u) | ((~w0.z & FLAGS) ? 4u : 0u) |
-                        ((~w0.w & FLAGS) ? 8u : 0u) | ((~w1.x & FLAGS) ? 16u : 0u) | ((~w1.y & FLAGS) ? 32u : 0u) |
-                        ((~w1.z & FLAGS) ? 64u : 0u) | ((~w1.w & FLAGS) ? 128u : 0u);
-#pragma unroll 1
-        while (regs) {
-            const int r = 8 * b + __ffs(regs) - 1;
-            regs &= regs - 1;
-            const uint32_t xr = mine[r];
-            uint32_t fl = ~xr & FLAGS;
-#pragma unroll 1
-            while (fl) {
-                const int bit = 31 - __clz(fl);
-                fl &= ~(1u << bit);
-                // packed: bit 7 / 15 = column 2r, field 0 / 1; bit 23 / 31 = column 2r + 1, field 0 / 1
-                const int col = PACKED ? 2 * r + (bit >> 4) : r;
-                const int f = PACKED ? ((bit >> 3) & 1) : (bit >= FIELD ? 1 : 0);
-                // acc = e1 + B * e2 with e1 = dot1 - T0, e2 = dot2 - T0 + 1 (no wrap): decode the flagged field
-                const int val = PACKED ? ((bit >> 4) ? (int)xr >> 16 : (int)(xr << 16) >> 16) : (int)xr;
-                const int e1 = (int)((uint32_t)val << (32 - FIELD)) >> (32 - FIELD);
-                const int dot = f ? ((val - e1) >> FIELD) + dot_thr0 - 1 : e1 + dot_thr0;
-                const int dist = (bits - dot) >> 1;
-                const int64_t row = row0 + col + f * TC_NM;
-                if (dist <= thr && row < c_end) {
-                    if (store) {
-                        if (pos < seg_cap) seg[pos] = ((uint64_t)(uint32_t)(2 * dist) << 32) | (index_base + (uint32_t)row);
-                        if (hq != nullptr) atomicAdd(hq + min(thr0 - dist, 3), 1u);
-                    }
-                    ++pos;
-                }
-            }
-        }
-    }
-    return pos;
-}
 
 // smem: [A: T tiles x {+-1, +-S, bias digits}][B: STAGES tiles][bias weights][packed ring][barriers][tmem slot][park]
 template <int WORDS, int T, int TC_STAGES>
@@ -499,60 +446,86 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
         const int dot_thr0 = a.bits - 2 * max(0, thr0);  // T0: the dot product behind the bias K-step of this query
         // with T < 4 a query is drained by 4 / T threads of this CTA (one per group): each owns a segment of its own
         const int seg_id = a.seg_base + blockIdx.y * (TC_BUFS / T) + grp / T;
-        uint64_t* seg = a.cand + ((uint64_t)(live ? q : 0) * a.n_segs + seg_id) * (uint64_t)a.seg_cap;
         uint32_t* hq = (a.K > 0 && live) ? a.aux[q].h : nullptr;
         uint32_t pos = 0;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + grp * TC_NM;
-        // The hit path, taken out of the pipeline's round trip.  A slice that holds a flagged row is PARKED: the flagged
-        // lanes (up to TC_PARK of a warp) copy their 32 registers and a bitmap of the flagged ones into a
-        // shared-memory slot, and the warp goes on draining.  The backlog (TC_BACKLOG slots per warp) is worked off
-        // while the warp would otherwise wait for its next accumulator tile - the pipeline is bound by that tile's round
-        // trip, so anything done between the drain and the next wait used to delay the release of the next buffer.
-        // Working a slot off is ONE rolled loop over the flagged registers (dynamic index into the slot), and nothing in
-        // it waits: the candidate segment is private to the thread (one query of one chunk), so the position is a
-        // register counter, the key goes straight to global memory and the tightening statistics are a
-        // fire-and-forget RED.
+        // The hit path, taken out of the pipeline's round trip.  A slice that holds a flagged row is PARKED: each flagged
+        // lane copies its 32 registers into an entry of the warp's shared-memory queue (TC_BACKLOG entries) and the warp
+        // goes on draining.  The queue is worked off while the warp would otherwise wait for its next accumulator tile,
+        // one entry at a time and with a look at the tile's barrier in between: a buffer that is handed back late stalls
+        // its MMA issuer, and the four buffers of TMEM are all the slack the pipeline has.  An entry is worked off by the
+        // WHOLE warp - lane r decodes register r of the parked slice, the owner's threshold and position travel by
+        // shuffle, the candidate segment is private to (query, chunk, group) so the position is a register counter, the
+        // key goes straight to global memory and the tightening statistics are a fire-and-forget RED.  (A single lane
+        // walking its own slice took ~4x as long: a dependent chain of ~100 instructions at one warp's issue latency.)
         uint32_t* park = scratch + ew * (TC_BACKLOG * TC_PARK_WORDS);
         int n_parked = 0, head = 0;                      // warp-uniform
-        auto work_off = [&]() {                          // the oldest slot
-            const uint32_t* slot = park + head * TC_PARK_WORDS;
-            const uint32_t mask = slot[TC_PARK * 36];
-            const int64_t row0 = (int64_t)(((uint64_t)slot[TC_PARK * 36 + 2] << 32) | slot[TC_PARK * 36 + 1]);
-            if (((mask >> lane) & 1u) && live && !(a.probe & 16))
-                pos = tc_work_off<WORDS>(slot + __popc(mask & lanemask_lt()) * 36, row0, c_end, thr, thr0, dot_thr0, a.bits,
-                                         seg, pos, (uint32_t)a.seg_cap, hq, (uint32_t)a.index_base, !(a.probe & 8));
-            __syncwarp();                                // the slot may be overwritten now
-            head = (head + 1) % TC_BACKLOG;
+        const bool hq_on = a.K > 0, drop = (a.probe & 16) != 0, store = !(a.probe & 8);
+        auto work_off = [&]() {                          // the oldest parked slice, by the whole warp
+            const uint32_t* mine = park + head * TC_PARK_WORDS;
+            const uint32_t xr = mine[lane];              // lane r looks at register r of the slice
+            const int owner = (int)mine[32];
+            const int64_t row0 = (int64_t)(((uint64_t)mine[34] << 32) | mine[33]);
+            const int thr_o = __shfl_sync(0xffffffffu, thr, owner);
+            const int thr0_o = __shfl_sync(0xffffffffu, thr0, owner);
+            uint32_t pos_o = __shfl_sync(0xffffffffu, pos, owner);
+            const int64_t q_o = q - lane + owner;
+            const int dot_thr0_o = a.bits - 2 * max(0, thr0_o);
+            uint32_t fl = (q_o < a.nq && !drop) ? (~xr & FLAGS) : 0u;
+            uint64_t* seg_o = a.cand + ((uint64_t)(q_o < a.nq ? q_o : 0) * a.n_segs + seg_id) * (uint64_t)a.seg_cap;
+            while (__any_sync(0xffffffffu, fl != 0u)) {          // one trip unless a register holds two flagged rows
+                bool pass = false;
+                int dist = 0;
+                int64_t row = 0;
+                if (fl) {
+                    const int bit = 31 - __clz(fl);
+                    fl &= ~(1u << bit);
+                    // packed: bit 7 / 15 = column 2r, field 0 / 1; bit 23 / 31 = column 2r + 1, field 0 / 1
+                    const int col = PACKED ? 2 * lane + (bit >> 4) : lane;
+                    const int f = PACKED ? ((bit >> 3) & 1) : (bit >= FIELD ? 1 : 0);
+                    // acc = e1 + B * e2 with e1 = dot1 - T0, e2 = dot2 - T0 + 1 (no wrap): decode the flagged field
+                    const int val = PACKED ? ((bit >> 4) ? (int)xr >> 16 : (int)(xr << 16) >> 16) : (int)xr;
+                    const int e1 = (int)((uint32_t)val << (32 - FIELD)) >> (32 - FIELD);
+                    const int dot = f ? ((val - e1) >> FIELD) + dot_thr0_o - 1 : e1 + dot_thr0_o;
+                    dist = (a.bits - dot) >> 1;
+                    row = row0 + col + f * TC_NM;
+                    pass = dist <= thr_o && row < c_end;
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, pass);
+                if (pass && store) {
+                    const uint32_t p = pos_o + __popc(m & lanemask_lt());
+                    if (p < (uint32_t)a.seg_cap)
+                        seg_o[p] = ((uint64_t)(uint32_t)(2 * dist) << 32) | ((uint32_t)a.index_base + (uint32_t)row);
+                    if (hq_on) atomicAdd(a.aux[q_o].h + min(thr0_o - dist, 3), 1u);
+                }
+                pos_o += __popc(m);
+            }
+            if (lane == owner) pos = pos_o;
+            __syncwarp();                                // the entry may be overwritten now
+            head = (head + 1) & (TC_BACKLOG - 1);
             --n_parked;
         };
-        auto park_slice = [&](const uint32_t (&v)[32], const uint32_t (&ab)[4], bool flagged, int64_t row0) {
+        auto park_slice = [&](const uint32_t (&v)[32], bool flagged, int64_t row0) {
             uint32_t pend = __ballot_sync(0xffffffffu, flagged);
             if (a.probe & 32) pend = 0;
             while (pend) {                               // warp-uniform
                 if (n_parked == TC_BACKLOG) work_off();  // backlog full: this one is paid for on the spot
-                uint32_t take = pend;                    // the lowest TC_PARK flagged lanes
+                const int room = TC_BACKLOG - n_parked;
+                uint32_t rest = pend;                    // the lowest flagged lanes there is room for, TC_PARK at most
 #pragma unroll
-                for (int k = 0; k < TC_PARK; ++k) take &= take - 1;
-                take = pend & ~take;
-                uint32_t* slot = park + ((head + n_parked) % TC_BACKLOG) * TC_PARK_WORDS;
+                for (int k = 0; k < TC_PARK; ++k)
+                    if (k < room) rest &= rest - 1;
+                const uint32_t take = pend & ~rest;
                 if ((take >> lane) & 1u) {               // 8 x 16-byte stores: parking must stay cheap, it is on the clock
-                    uint32_t* mine = slot + __popc(take & lanemask_lt()) * 36;
+                    uint32_t* mine = park + ((head + n_parked + __popc(take & lanemask_lt())) & (TC_BACKLOG - 1)) * TC_PARK_WORDS;
 #pragma unroll
                     for (int r = 0; r < 32; r += 4)
                         *reinterpret_cast<uint4*>(mine + r) = make_uint4(v[r], v[r + 1], v[r + 2], v[r + 3]);
-                    uint32_t blocks = 0;
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) blocks |= ((ab[b] & FLAGS) != FLAGS ? 1u : 0u) << b;
-                    mine[32] = blocks;
-                }
-                if (lane == 0) {
-                    slot[TC_PARK * 36] = take;
-                    slot[TC_PARK * 36 + 1] = (uint32_t)row0;
-                    slot[TC_PARK * 36 + 2] = (uint32_t)((uint64_t)row0 >> 32);
+                    *reinterpret_cast<uint4*>(mine + 32) = make_uint4((uint32_t)lane, (uint32_t)row0, (uint32_t)((uint64_t)row0 >> 32), 0u);
                 }
                 __syncwarp();
-                ++n_parked;
-                pend &= ~take;
+                n_parked += __popc(take);
+                pend = rest;
             }
         };
         // one slice (32 registers: 64 or 128 rows): AND-reduce, one mask test, one vote; the hit path is rare
@@ -577,8 +550,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
             const bool f0 = ((ab0[0] & ab0[1] & ab0[2] & ab0[3]) & FLAGS) != FLAGS;
             const bool f1 = ((ab1[0] & ab1[1] & ab1[2] & ab1[3]) & FLAGS) != FLAGS;
             if (__any_sync(0xffffffffu, f0 || f1)) {
-                park_slice(v0, ab0, f0, r0);
-                park_slice(v1, ab1, f1, r1);
+                park_slice(v0, f0, r0);
+                park_slice(v1, f1, r1);
             }
         };
         auto release = [&]() {                   // the values are in registers: the buffer goes back to its issuer
@@ -963,6 +936,17 @@ extern "C" int cmh_tc_choose_prefix(const uint32_t* hist, const uint32_t* overfl
     if (nq == 0) return CMH_OK;
     CMH_REQUIRE(hist && thr_in && thr_out, CMH_ERR_ARG, "cmh_tc_choose_prefix: NULL pointer");
     tc_choose_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, (cudaStream_t)stream>>>(hist, overflow, nq, nb, (double)K, -1, thr_in,
+                                                                                   thr_out);
+    CMH_LAUNCH_CHECK("tc_choose_kernel");
+    return CMH_OK;
+}
+
+extern "C" int cmh_tc_choose_seen(const uint32_t* hist, const uint32_t* overflow, int64_t nq, int nb, int K,
+                                  const int32_t* thr_in, int32_t* thr_out, void* stream) {
+    CMH_REQUIRE(nq >= 0 && nb >= 1 && K >= 1, CMH_ERR_ARG, "cmh_tc_choose_seen: bad sizes");
+    if (nq == 0) return CMH_OK;
+    CMH_REQUIRE(hist && thr_in && thr_out, CMH_ERR_ARG, "cmh_tc_choose_seen: NULL pointer");
+    tc_choose_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, (cudaStream_t)stream>>>(hist, overflow, nq, nb, (double)K, 0, thr_in,
                                                                                    thr_out);
     CMH_LAUNCH_CHECK("tc_choose_kernel");
     return CMH_OK;

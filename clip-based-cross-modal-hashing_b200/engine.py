@@ -349,6 +349,7 @@ TC_PILOT_FRACTIONS = (64,)        # ... the first 1/64 of the rows (measured opt
 TC_PILOT_SIGMA = 5.0
 TC_PREFIX_MIN_ROWS = 4_000_000    # shards at least this long apply the prefix rule ...
 TC_PREFIX_FRACTIONS = (0.3, 0.5, 0.7, 0.85)   # ... after these fractions of their rows (swept: 43.1 ms against 50.5 without)
+TC_PREFIX_FRACTIONS_SHARDED = (0.3, 0.6)      # ... of every shard's rows when the database is sharded (each cut is an all-gather)
 
 
 def tc_supported(q: PackedSet, d: PackedSet, K: int = 1) -> bool:
@@ -403,6 +404,7 @@ class LocalComm:
     """The exchange steps of the tensor-core top-K for a database that lives on ONE GPU (no-ops).  `sharded.GroupComm`
     is the `torch.distributed` version for a database sharded over the ranks of a process group."""
     world = 1
+    rank = 0
 
     def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
         return t
@@ -436,7 +438,8 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     ready   [(row_end, torch.cuda.Event), ...] in row order: rows below row_end of ``d`` are valid once the event has
             completed (a database that is still being uploaded on another stream); the scan is cut at those
             boundaries and every launch waits only for the rows it reads
-    prefix  apply the prefix rule (`cmh_tc_choose_prefix`) at `TC_PREFIX_FRACTIONS` of the rows: exact, local
+    prefix  apply the prefix rule (`cmh_tc_choose_prefix` / `cmh_tc_choose_seen`) at `TC_PREFIX_FRACTIONS` of the rows:
+            exact; sharded databases all-gather the candidate histograms of the rows scanned so far at each cut
     defer   return a callable instead of the keys: everything is enqueued, and calling it reads the verdict (a host
             sync), redoes failed queries and returns the keys - lets a caller keep two query chunks in flight
     buffers a dict the caller keeps between calls: the multi-GB candidate scratch is allocated once per query-chunk
@@ -473,10 +476,12 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     stages = [min(e, d.n) for e in stages]
     ends = sorted({e for e in stages if 0 < e < d.n})
     # the prefix rule (exact): after these rows the candidates so far bound what later rows can still contribute
-    prefix_ends = set()
-    if prefix and d.n >= TC_PREFIX_MIN_ROWS:
-        prefix_ends = {int(d.n * f) // 256 * 256 for f in TC_PREFIX_FRACTIONS}
-        prefix_ends = {e for e in prefix_ends if (stages[-1] if stages else 0) < e < d.n}
+    # (every shard takes part in every exchange, so whether and how often is decided from the global sizes alone)
+    prefix_cuts = []
+    if prefix and -(-nd_total // comm.world) >= TC_PREFIX_MIN_ROWS:
+        fractions = TC_PREFIX_FRACTIONS if comm.world == 1 else TC_PREFIX_FRACTIONS_SHARDED
+        prefix_cuts = [min(d.n, int(d.n * f) // 256 * 256) for f in fractions]
+    prefix_ends = {e for e in prefix_cuts if (stages[-1] if stages else 0) < e < d.n}
     cuts = sorted({0, d.n} | set(ends) | prefix_ends | {int(e) for e, _ in (ready or ()) if 0 < int(e) < d.n})
     spans = [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]] or [(0, 0)]
     regions = [hi - lo for lo, hi in spans]
@@ -552,11 +557,47 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
                                   _ptr(thr_cur), _ptr(thr_next), st), "cmh_tc_choose")
             thr_cur, thr_next = thr_next, thr_cur
 
-        # stages that are empty on this shard (a short shard) still take part in the exchange
-        while si < len(stages) and stages[si] <= 0:
-            if stages_all[si] > 0:
-                refine_upto(si, 0)
-            si += 1
+        def prefix_upto(seg_hi: int):
+            # The prefix rule (exact, no statistics).  K candidates at dist <= b among rows of LOWER index than what is
+            # still to be scanned (this shard's rows so far + the same prefix of every lower-ranked shard): later rows
+            # only matter below b.  K candidates at dist <= b ANYWHERE among the rows scanned so far (all shards):
+            # later rows only matter at or below b.  One all-gather of the per-shard histograms serves both.
+            nonlocal thr_cur, thr_limit
+            if thr_limit is None:
+                thr_limit = thr_cur                  # the statistical bound, the same on every shard
+            ph = torch.zeros((nq, nb), dtype=torch.int32, device=dev)
+            over = torch.zeros(nq, dtype=torch.int32, device=dev)
+            if seg_hi > 0:
+                check(L.cmh_tc_cand_hist(_ptr(b.cand), _ptr(b.cnt), nq, 0, seg_hi, b.seg_total, b.seg_cap, nb, _ptr(ph),
+                                         _ptr(over), st), "cmh_tc_cand_hist")
+            out = b.thr3 if thr_cur is not b.thr3 else b.thr4
+            if comm.world > 1:
+                every = comm.all_gather_stack(ph)                                    # [world, nq, nb]
+                lower = every[:comm.rank + 1].sum(0, dtype=torch.int32).contiguous()
+                seen = every.sum(0, dtype=torch.int32).contiguous()
+                check(L.cmh_tc_choose_prefix(_ptr(lower), None, nq, nb, K, _ptr(thr_cur), _ptr(out), st), "cmh_tc_choose_prefix")
+                check(L.cmh_tc_choose_seen(_ptr(seen), None, nq, nb, K, _ptr(out), _ptr(out), st), "cmh_tc_choose_seen")
+            else:
+                check(L.cmh_tc_choose_prefix(_ptr(ph), _ptr(over), nq, nb, K, _ptr(thr_cur), _ptr(out), st), "cmh_tc_choose_prefix")
+            thr_cur = out
+
+        pj = 0                                       # next prefix exchange
+
+        def close(hi: int, seg_hi: int):
+            # exchanges due once the rows below `hi` have been scanned: the pilot stages, then - never before the last
+            # stage, so that the order is the same on every shard - the prefix rule.  A shard that has no rows at a
+            # cut (a short or empty shard) still takes part.
+            nonlocal si, pj
+            while si < len(stages) and stages[si] <= hi:
+                if stages_all[si] > 0:
+                    refine_upto(si, seg_hi)
+                si += 1
+                phase("pilot_done")
+            while si == len(stages) and pj < len(prefix_cuts) and prefix_cuts[pj] <= hi:
+                prefix_upto(seg_hi)
+                pj += 1
+
+        close(0, 0)
         for i, (lo, hi) in enumerate(spans):
             if hi <= lo:
                 continue
@@ -571,21 +612,9 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
                                    b.seg_cap, _ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), st), "cmh_tc_collect")
             mark()
             launched = True
-            while si < len(stages) and stages[si] <= hi:
-                if stages_all[si] > 0:
-                    refine_upto(si, b.seg_base[i] + b.n_segs[i])
-                si += 1
-                phase("pilot_done")
-            if hi in prefix_ends:
-                # K candidates at dist <= b among the rows scanned so far (all of lower index than what follows): later
-                # rows only matter below b.  Local and exact - no exchange, no statistics.
-                ph = torch.zeros((nq, nb), dtype=torch.int32, device=dev)
-                over = torch.zeros(nq, dtype=torch.int32, device=dev)
-                check(L.cmh_tc_cand_hist(_ptr(b.cand), _ptr(b.cnt), nq, 0, b.seg_base[i] + b.n_segs[i], b.seg_total,
-                                         b.seg_cap, nb, _ptr(ph), _ptr(over), st), "cmh_tc_cand_hist")
-                check(L.cmh_tc_choose_prefix(_ptr(ph), _ptr(over), nq, nb, K, _ptr(thr_cur), _ptr(b.thr3 if thr_cur is not b.thr3 else b.thr4), st),
-                      "cmh_tc_choose_prefix")
-                thr_cur = b.thr3 if thr_cur is not b.thr3 else b.thr4
+            if hi < d.n:                             # after the last row there is nothing left to tighten for
+                close(hi, b.seg_base[i] + b.n_segs[i])
+        close(d.n, b.seg_total if launched else 0)
         if not launched:
             b.cnt.zero_()
             b.aux.zero_()
@@ -610,6 +639,7 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     if stats is not None:
         stats["candidates"] = b.cnt.sum(0)
         stats["thr"] = thr_main
+        stats["thr_final"] = thr_cur                 # after the prefix rule (differs between shards)
         stats["pilot_rows"] = stages
 
     def finish() -> torch.Tensor:

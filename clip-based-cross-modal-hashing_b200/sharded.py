@@ -93,7 +93,7 @@ class GroupComm:
 
     def __init__(self, group=None):
         self.group = group
-        self.world = _world(group)[1]
+        self.rank, self.world = _world(group)
 
     def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
         if self.world > 1:

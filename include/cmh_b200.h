@@ -221,6 +221,13 @@ int cmh_tc_choose(const uint32_t* hist, const uint32_t* overflow, int64_t nq, in
  * thr_out[q] = min(thr_in[q], b - 1) for the smallest such b; thr_in[q] when there is none (or overflow[q]). */
 int cmh_tc_choose_prefix(const uint32_t* hist, const uint32_t* overflow, int64_t nq, int nb, int K, const int32_t* thr_in,
                          int32_t* thr_out, void* stream);
+/* The same bound without the index order (a database sharded over several GPUs): hist holds candidates of rows already
+ * scanned ANYWHERE in the database (the all-gathered sum of the shards' prefix histograms).  K of them at dist <= b put
+ * the K-th result at dist <= b, so no row above b is needed - rows AT b still are, their index may be lower:
+ * thr_out[q] = min(thr_in[q], b).  A shard combines both: cmh_tc_choose_prefix on the sum over the shards of lower rank
+ * plus its own prefix, cmh_tc_choose_seen on the sum over all shards. */
+int cmh_tc_choose_seen(const uint32_t* hist, const uint32_t* overflow, int64_t nq, int nb, int K, const int32_t* thr_in,
+                       int32_t* thr_out, void* stream);
 /* thr[q] from a histogram (cmh_eval_hist, binary mode, nb = bits + 1) over a SAMPLE of n_sample rows of an nd-row
  * shard: smallest bucket whose cumulative sample count reaches K*f + 6*sqrt(K*f) + 8 (f = n_sample / nd), exactly
  * min(K, nd) when n_sample == nd. */

@@ -374,6 +374,10 @@ class _ThreadComm:
     def bind(self, rank):
         self.local.rank = rank
 
+    @property
+    def rank(self):
+        return self.local.rank
+
     def _exchange(self, t):
         self.slots[self.local.rank] = t
         self.barrier.wait()
@@ -399,12 +403,19 @@ class _ThreadComm:
         return torch.stack([x[rank] for x in self._exchange(t)])
 
 
-@pytest.mark.parametrize("bits,world,D,K,pilot", [(64, 2, 3_000_001, 1000, 200_000), (64, 3, 2_000_000, 100, 0),
-                                                  (128, 2, 1_500_000, 500, 150_016)])
-def test_tc_topk_sharded_matches_single(dev, bits, world, D, K, pilot):
-    """Shards that filter with all-reduced (global) thresholds + merge + verify == the exact single-shard ranking."""
+@pytest.mark.parametrize("bits,world,D,K,pilot,prefix", [(64, 2, 3_000_001, 1000, 200_000, None), (64, 3, 2_000_000, 100, 0, None),
+                                                         (128, 2, 1_500_000, 500, 150_016, None),
+                                                         (64, 3, 2_400_123, 300, 100_000, (0.2, 0.5, 0.8)),
+                                                         (64, 4, 1_000_000, 1000, 0, (0.25, 0.5, 0.75)),
+                                                         (128, 2, 1_500_000, 500, 150_016, (0.3, 0.6))])
+def test_tc_topk_sharded_matches_single(dev, bits, world, D, K, pilot, prefix, monkeypatch):
+    """Shards that filter with all-reduced (global) thresholds + merge + verify == the exact single-shard ranking;
+    with ``prefix``, the shards also tighten by the cross-shard prefix rule (all-gathered candidate histograms)."""
     import threading
     from cmh_b200 import engine, sharded
+    if prefix is not None:
+        monkeypatch.setattr(engine, "TC_PREFIX_MIN_ROWS", 1000)
+        monkeypatch.setattr(engine, "TC_PREFIX_FRACTIONS_SHARDED", prefix)
     Q = 300
     db = engine.synth_codes(500 + bits, 0, D, bits, dev)
     q = engine.synth_codes(600 + bits, 0, Q, bits, dev)
@@ -438,6 +449,9 @@ def test_tc_topk_sharded_matches_single(dev, bits, world, D, K, pilot):
         assert st["n_fail"] == 0
     # each shard collected only its share of the candidates
     assert sum(int(st["candidates"].sum()) for _, st in out) < 40 * K * Q
+    if prefix is not None:                           # the rule did tighten, and never above the statistical bound
+        assert all(bool((st["thr_final"] <= st["thr"]).all()) for _, st in out)
+        assert any(bool((st["thr_final"] < st["thr"]).any()) for _, st in out)
 
 
 # ---------------------------------------------------------------------------------------------------------------
