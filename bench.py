@@ -420,9 +420,10 @@ def main_native(args):
     # rate (burst figure: the kernel is timed alone, launch by launch)
     bf16 = peaks.get("bf16_tflops")
     i8_peak = 2.0 * bf16 if bf16 else 2.0 * 1500.0
-    traffic = None
+    traffic, traffic_capture = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("tc_collect_kernel")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic, traffic_capture = tj.get("tc_collect_kernel"), tj.get("tc_collect_kernel_capture")
     except Exception:
         pass
     algo_bytes = (hi - lo) * 8 + Q * 8                       # packed shard + packed queries, read once
@@ -456,7 +457,7 @@ def main_native(args):
                     "measured against the driver's denominator, not against what the pipe can do",
             "issued_tops_mma_only": (pairs_shard * ops_per_pair * 1.25 / (ceilings["mma_only_ms"] * 1e-3) / 1e12
                                      if ceilings.get("mma_only_ms") else None),
-            "traffic": traffic,
+            "traffic": traffic, "traffic_capture": traffic_capture,   # ncu dram bytes of ONE captured launch of the set
             "hbm": {"achieved": algo_bytes / (collect_ms * 1e-3) / 1e9 if collect_ms else None, "peak": hbm_peak,
                     "unit": "GB/s", "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                     "algorithmic_bytes_per_launch_set": algo_bytes}},

@@ -646,24 +646,89 @@ constexpr int FIN_THREADS = 512;
 // overflowed.  Sharded databases all-reduce the histograms here.  Step 2 (tc_choose_kernel): thr_out = the smallest
 // bucket whose cumulative count reaches `need`, capped by thr_in; unchanged when a segment overflowed.  As with
 // cmh_topk_threshold any outcome is safe: a threshold that turns out too low is caught after the merge.
-__global__ void __launch_bounds__(128) tc_cand_hist_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt,
-                                                           int64_t nq, int seg_lo, int seg_hi, int seg_total, int seg_cap,
-                                                           int nb, uint32_t* __restrict__ hist_out,
-                                                           uint32_t* __restrict__ overflow) {
+// A query's candidates are spread over many short segments (one per chunk, launch and draining group: a few hundred,
+// ~10 entries each).  Walking them one segment after the other is a chain of dependent L2/HBM round trips (count, then
+// entries); instead a block of segments is INDEXED: every thread loads the counts of SEG_IT segments at once, a block
+// scan turns them into offsets in shared memory, and the candidates are then addressed by their flat position (a binary
+// search in the offsets) - all loads of a pass are in flight together.
+constexpr int SEG_IT = 4;         // segments per thread and block of segments
+
+// offsets of the segments [c0, c0 + THREADS * SEG_IT) (those beyond c1 are empty) into s_off[THREADS * SEG_IT + 1];
+// returns the number of (clamped) entries.  raw / over accumulate per thread.
+template <int THREADS>
+__device__ __forceinline__ uint32_t seg_block_offsets(const uint32_t* __restrict__ cnt, int64_t nq, int64_t q, int c0, int c1,
+                                                      uint32_t seg_cap, uint32_t* s_off, uint32_t* s_warp, uint32_t& raw,
+                                                      uint32_t& over) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t v[SEG_IT], sum = 0;
+#pragma unroll
+    for (int k = 0; k < SEG_IT; ++k) {
+        const int c = c0 + tid * SEG_IT + k;
+        uint32_t n = c < c1 ? cnt[(int64_t)c * nq + q] : 0u;
+        raw += n;
+        if (n > seg_cap) { over = 1u; n = seg_cap; }
+        v[k] = n;
+        sum += n;
+    }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += y;
+    }
+    __syncthreads();                             // the previous block's walk is over: s_off / s_warp may be rewritten
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t ex = inc - sum;
+    for (int w = 0; w < warp; ++w) ex += s_warp[w];
+#pragma unroll
+    for (int k = 0; k < SEG_IT; ++k) {
+        s_off[tid * SEG_IT + k] = ex;
+        ex += v[k];
+    }
+    if (tid == THREADS - 1) s_off[THREADS * SEG_IT] = ex;
+    __syncthreads();
+    return s_off[THREADS * SEG_IT];
+}
+
+// the key at flat position i (< s_off[n_off]) of the indexed block: segment = the last one whose offset is <= i
+__device__ __forceinline__ uint64_t seg_flat_load(const uint64_t* __restrict__ block_base, const uint32_t* s_off, int n_off,
+                                                  uint32_t seg_cap, uint32_t i) {
+    int lo = 0, hi = n_off;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    return block_base[(uint64_t)lo * seg_cap + (i - s_off[lo])];
+}
+
+constexpr int CH_THREADS = 256;
+__global__ void __launch_bounds__(CH_THREADS) tc_cand_hist_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt,
+                                                                  int64_t nq, int seg_lo, int seg_hi, int seg_total, int seg_cap,
+                                                                  int nb, uint32_t* __restrict__ hist_out,
+                                                                  uint32_t* __restrict__ overflow) {
+    constexpr int BLOCK = CH_THREADS * SEG_IT;
     __shared__ uint32_t hist[FIN_BINS];
+    __shared__ uint32_t s_off[BLOCK + 1], s_warp[CH_THREADS / 32];
     __shared__ uint32_t s_over;
     const int64_t q = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < FIN_BINS; i += blockDim.x) hist[i] = 0u;
     if (threadIdx.x == 0) s_over = 0u;
-    __syncthreads();
     const uint64_t* __restrict__ mine = cand + (uint64_t)q * seg_total * (uint64_t)seg_cap;
-    for (int c = seg_lo + warp; c < seg_hi; c += 4) {
-        uint32_t n = cnt[(int64_t)c * nq + q];
-        if (n > (uint32_t)seg_cap) { s_over = 1u; n = (uint32_t)seg_cap; }
-        const uint64_t* seg = mine + (uint64_t)c * seg_cap;
-        for (uint32_t i = lane; i < n; i += 32) atomicAdd(&hist[min((uint32_t)(seg[i] >> 33), (uint32_t)(FIN_BINS - 1))], 1u);
+    uint32_t raw = 0, over = 0;
+    for (int c0 = seg_lo; c0 < seg_hi; c0 += BLOCK) {
+        const uint32_t total = seg_block_offsets<CH_THREADS>(cnt, nq, q, c0, seg_hi, (uint32_t)seg_cap, s_off, s_warp, raw, over);
+        const uint64_t* base = mine + (uint64_t)c0 * seg_cap;
+        for (uint32_t i0 = threadIdx.x - lane; i0 < total; i0 += CH_THREADS) {   // warp-uniform trip count
+            const uint32_t i = i0 + lane;
+            const uint32_t bkt = i < total ? min((uint32_t)(seg_flat_load(base, s_off, BLOCK, (uint32_t)seg_cap, i) >> 33),
+                                                 (uint32_t)(FIN_BINS - 1)) : (uint32_t)FIN_BINS;
+            const uint32_t same = __match_any_sync(0xffffffffu, bkt);
+            if (bkt < (uint32_t)FIN_BINS && lane == __ffs(same) - 1) atomicAdd(&hist[bkt], (uint32_t)__popc(same));
+        }
     }
+    if (over) s_over = 1u;
     __syncthreads();
     for (int i = threadIdx.x; i < nb; i += blockDim.x) hist_out[q * nb + i] = i < FIN_BINS ? hist[i] : 0u;
     if (threadIdx.x == 0) overflow[q] = s_over;
@@ -715,33 +780,35 @@ __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64
                                                                     uint64_t* __restrict__ keys,
                                                                     uint32_t* __restrict__ fail_flags,
                                                                     uint32_t* __restrict__ fail_count) {
+    constexpr int BLOCK = FIN_THREADS * SEG_IT;
     __shared__ uint64_t sk[FIN_MAX];
     __shared__ uint32_t hist[FIN_BINS];
+    __shared__ uint32_t s_off[BLOCK + 1], s_warp[FIN_THREADS / 32];
+    __shared__ uint32_t s_wc[FIN_THREADS / 32][8], s_base[8];
     __shared__ int s_T, s_keep;
-    __shared__ uint32_t s_n, s_total, s_over;
+    __shared__ uint32_t s_total, s_over;
     const int64_t q = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int NW = FIN_THREADS / 32;
+    const int lane = threadIdx.x & 31;
     const int64_t need = nd < (int64_t)K ? nd : (int64_t)K;
     const uint64_t* __restrict__ mine = cand + (uint64_t)q * n_chunks * (uint64_t)seg_cap;
     for (int i = threadIdx.x; i < FIN_BINS; i += blockDim.x) hist[i] = 0u;
-    if (threadIdx.x == 0) { s_n = 0u; s_total = 0u; s_over = 0u; }
-    __syncthreads();
-    for (int c = warp; c < n_chunks; c += NW) {
-        uint32_t n = cnt[(int64_t)c * nq + q];
-        if (lane == 0) {
-            atomicAdd(&s_total, n);
-            if (n > (uint32_t)seg_cap) s_over = 1u;
-        }
-        n = min(n, (uint32_t)seg_cap);
-        const uint64_t* seg = mine + (uint64_t)c * seg_cap;
-        for (uint32_t i0 = 0; i0 < n; i0 += 32) {        // the candidates sit in 3-4 buckets: one add per bucket per warp
+    if (threadIdx.x == 0) { s_total = 0u; s_over = 0u; }
+    // pass 1: the candidates' histogram (they sit in 3-4 buckets: one add per bucket per warp)
+    uint32_t raw = 0, over = 0;
+    for (int c0 = 0; c0 < n_chunks; c0 += BLOCK) {
+        const uint32_t total = seg_block_offsets<FIN_THREADS>(cnt, nq, q, c0, n_chunks, (uint32_t)seg_cap, s_off, s_warp, raw, over);
+        const uint64_t* base = mine + (uint64_t)c0 * seg_cap;
+        for (uint32_t i0 = threadIdx.x - lane; i0 < total; i0 += FIN_THREADS) {  // warp-uniform trip count
             const uint32_t i = i0 + lane;
-            const uint32_t bkt = i < n ? min((uint32_t)(seg[i] >> 33), (uint32_t)(FIN_BINS - 1)) : (uint32_t)FIN_BINS;
+            const uint32_t bkt = i < total ? min((uint32_t)(seg_flat_load(base, s_off, BLOCK, (uint32_t)seg_cap, i) >> 33),
+                                                 (uint32_t)(FIN_BINS - 1)) : (uint32_t)FIN_BINS;
             const uint32_t same = __match_any_sync(0xffffffffu, bkt);
             if (bkt < (uint32_t)FIN_BINS && lane == __ffs(same) - 1) atomicAdd(&hist[bkt], (uint32_t)__popc(same));
         }
     }
+    raw = __reduce_add_sync(0xffffffffu, raw);
+    if (lane == 0 && raw) atomicAdd(&s_total, raw);
+    if (over) s_over = 1u;
     __syncthreads();
     // partial (one shard of several): emit what there is, up to K; the K-th key is judged after the merge
     const int64_t want = partial ? min(need, (int64_t)s_total) : need;
@@ -767,37 +834,71 @@ __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64
         for (int i = threadIdx.x; i < K; i += blockDim.x) keys[q * K + i] = ~0ull;
         return;
     }
+    // pass 2: place the candidates at or below the K-th bucket, bucket by bucket and - inside a bucket - in the order
+    // they are stored.  That order is ascending in the row index (segments follow the chunks and launches, a segment
+    // is appended to tile after tile) except inside one 256-row tile and between the two groups that share a query
+    // tile of 128-bit codes, so the result is usually sorted already: it is checked, and only an unsorted one goes
+    // through the bitonic network (which was 90 % of this kernel's instructions).
+    // Classes: slot s = T - bucket for the 7 highest buckets, slot 7 = everything below (rarely populated).
     const int T = s_T, keep = s_keep;
-    for (int c = warp; c < n_chunks; c += NW) {
-        const uint32_t n = cnt[(int64_t)c * nq + q];     // <= seg_cap (checked above)
-        const uint64_t* seg = mine + (uint64_t)c * seg_cap;
-        for (uint32_t i0 = 0; i0 < n; i0 += 32) {        // one slot reservation per warp
-            const uint32_t i = i0 + lane;
-            const uint64_t key = i < n ? seg[i] : ~0ull;
-            const bool ok = i < n && (int)(uint32_t)(key >> 33) <= T;
-            const uint32_t m = __ballot_sync(0xffffffffu, ok);
-            uint32_t base = 0;
-            if (lane == 0 && m) base = atomicAdd(&s_n, (uint32_t)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (ok) sk[base + __popc(m & lanemask_lt())] = key;
-        }
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x < 8) {
+        const int b_lo = threadIdx.x == 7 ? 0 : T - (int)threadIdx.x;     // first bucket of the class
+        uint32_t below = 0;
+        for (int b = 0; b < b_lo && b < FIN_BINS; ++b) below += hist[b];
+        s_base[threadIdx.x] = b_lo < 0 ? 0u : below;
     }
-    int p2 = 1;
-    while (p2 < keep) p2 <<= 1;
-    __syncthreads();
-    for (int i = keep + threadIdx.x; i < p2; i += blockDim.x) sk[i] = ~0ull;
-    __syncthreads();
-    for (int k = 2; k <= p2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < p2; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const uint64_t x = sk[i], y = sk[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((x > y) == up) { sk[i] = y; sk[ixj] = x; }
-                }
+    for (int c0 = 0; c0 < n_chunks; c0 += BLOCK) {
+        // (with a single block of segments - the usual case - the offsets of pass 1 are still in place)
+        const uint32_t total = n_chunks <= BLOCK ? s_off[BLOCK]
+                                                 : seg_block_offsets<FIN_THREADS>(cnt, nq, q, c0, n_chunks, (uint32_t)seg_cap, s_off, s_warp, raw, over);
+        const uint64_t* base = mine + (uint64_t)c0 * seg_cap;
+        for (uint32_t i0 = 0; i0 < total; i0 += FIN_THREADS) {          // block-uniform trip count
+            const uint32_t i = i0 + threadIdx.x;
+            const uint64_t key = i < total ? seg_flat_load(base, s_off, BLOCK, (uint32_t)seg_cap, i) : ~0ull;
+            const int bkt = (int)(uint32_t)(key >> 33);
+            const int cls = (i < total && bkt <= T) ? min(T - bkt, 7) : 8;
+            if (threadIdx.x < (FIN_THREADS / 32) * 8) s_wc[threadIdx.x >> 3][threadIdx.x & 7] = 0u;
+            __syncthreads();
+            const uint32_t same = __match_any_sync(0xffffffffu, cls);
+            if (cls < 8 && lane == __ffs(same) - 1) s_wc[warp][cls] = (uint32_t)__popc(same);
+            __syncthreads();
+            if (cls < 8) {
+                uint32_t pos = s_base[cls] + (uint32_t)__popc(same & lanemask_lt());
+                for (int w = 0; w < warp; ++w) pos += s_wc[w][cls];
+                if (pos < (uint32_t)FIN_MAX) sk[pos] = key;
             }
             __syncthreads();
+            if (threadIdx.x < 8) {
+                uint32_t tot = 0;
+#pragma unroll
+                for (int w = 0; w < FIN_THREADS / 32; ++w) tot += s_wc[w][threadIdx.x];
+                s_base[threadIdx.x] += tot;
+            }
+            __syncthreads();                     // s_wc is zeroed again by the next trip
+        }
+    }
+    __syncthreads();
+    bool unsorted = false;
+    for (int i = threadIdx.x; i + 1 < keep; i += blockDim.x) unsorted |= sk[i] > sk[i + 1];
+    if (__syncthreads_or(unsorted)) {
+        int p2 = 1;
+        while (p2 < keep) p2 <<= 1;
+        __syncthreads();
+        for (int i = keep + threadIdx.x; i < p2; i += blockDim.x) sk[i] = ~0ull;
+        __syncthreads();
+        for (int k = 2; k <= p2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < p2; i += blockDim.x) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const uint64_t x = sk[i], y = sk[ixj];
+                        const bool up = (i & k) == 0;
+                        if ((x > y) == up) { sk[i] = y; sk[ixj] = x; }
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
     for (int i = threadIdx.x; i < K; i += blockDim.x) keys[q * K + i] = i < keep ? sk[i] : ~0ull;
@@ -911,7 +1012,7 @@ extern "C" int cmh_tc_cand_hist(const uint64_t* cand, const uint32_t* cnt, int64
     if (nq == 0) return CMH_OK;
     CMH_REQUIRE(cand && cnt && hist && overflow, CMH_ERR_ARG, "cmh_tc_cand_hist: NULL pointer");
     CMH_REQUIRE(nq <= 0x7fffffffll, CMH_ERR_UNSUPPORTED, "cmh_tc_cand_hist: too many queries per call");
-    tc_cand_hist_kernel<<<(unsigned)nq, 128, 0, (cudaStream_t)stream>>>(cand, cnt, nq, seg_lo, seg_hi, seg_total, seg_cap, nb,
+    tc_cand_hist_kernel<<<(unsigned)nq, CH_THREADS, 0, (cudaStream_t)stream>>>(cand, cnt, nq, seg_lo, seg_hi, seg_total, seg_cap, nb,
                                                                        hist, overflow);
     CMH_LAUNCH_CHECK("tc_cand_hist_kernel");
     return CMH_OK;

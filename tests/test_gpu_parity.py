@@ -729,3 +729,50 @@ def test_tc_edge_cases(dev):
     assert torch.equal(got, want) and bool((got[:, 100:] == -1).all())
     big_k = idx.search_packed(q, 5000)                                  # K beyond the tensor path's limit: exact path
     assert torch.equal(big_k, engine.RankPass(q, db, need_labels=False).topk(5000, 0))
+
+
+@pytest.mark.parametrize("n_segs,seg_cap,nq,K", [(7, 64, 9, 50), (2500, 4, 6, 300), (5000, 3, 4, 1000)])
+def test_finalize_and_cand_hist_over_many_segments(dev, n_segs, seg_cap, nq, K):
+    """`cmh_tc_cand_hist` / `cmh_topk_finalize` index a query's candidate segments in blocks (1024 / 2048 segments): a
+    synthetic candidate store with more segments than one block, empty segments and one overflowed query, against a
+    sort of the same entries."""
+    from cmh_b200 import _cabi, engine
+    L = _cabi.lib()
+    g = torch.Generator().manual_seed(n_segs)
+    nb = 65
+    cnt = torch.randint(0, seg_cap + 1, (n_segs, nq), generator=g, dtype=torch.int32)
+    cnt[torch.rand(n_segs, nq, generator=g) < 0.5] = 0
+    over_q = nq - 1
+    cnt[n_segs // 2, over_q] = seg_cap + 3                       # lost entries: the query must fail
+    dist = torch.randint(10, 14, (nq, n_segs, seg_cap), generator=g, dtype=torch.int64)
+    row = torch.randperm(nq * n_segs * seg_cap, generator=g).reshape(nq, n_segs, seg_cap)
+    cand = ((2 * dist) << 32) | row
+    cand_d, cnt_d = cand.to(dev), cnt.to(dev)
+    aux = torch.zeros((nq, 8), dtype=torch.int32, device=dev)
+    st, p = engine._stream(dev), engine._ptr
+    # histogram of a sub-range of the segments
+    lo, hi = n_segs // 5, n_segs
+    ph = torch.zeros((nq, nb), dtype=torch.int32, device=dev)
+    ov = torch.zeros(nq, dtype=torch.int32, device=dev)
+    engine.check(L.cmh_tc_cand_hist(p(cand_d), p(cnt_d), nq, lo, hi, n_segs, seg_cap, nb, p(ph), p(ov), st), "cmh_tc_cand_hist")
+    keys = torch.empty((nq, K), dtype=torch.int64, device=dev)
+    flags = torch.zeros(nq, dtype=torch.int32, device=dev)
+    nfail = torch.zeros(1, dtype=torch.int32, device=dev)
+    thr = torch.full((nq,), 20, dtype=torch.int32, device=dev)
+    engine.check(L.cmh_topk_finalize(p(cand_d), p(cnt_d), p(aux), p(thr), nq, n_segs, seg_cap, K, 10**9, 0, p(keys), p(flags),
+                                     p(nfail), st), "cmh_topk_finalize")
+    ph, ov, keys, flags = ph.cpu(), ov.cpu(), keys.cpu(), flags.cpu()
+    n_fail = 0
+    for q in range(nq):
+        n = cnt[:, q].clamp(max=seg_cap)
+        ent = [cand[q, c, :int(n[c])] for c in range(n_segs)]
+        sub = torch.cat(ent[lo:hi]) if hi > lo else torch.empty(0, dtype=torch.int64)
+        assert torch.equal(ph[q].to(torch.int64), torch.bincount(sub >> 33, minlength=nb)[:nb])
+        assert int(ov[q]) == (1 if q == over_q else 0)
+        every = torch.sort(torch.cat(ent)).values
+        if q == over_q or every.numel() < K:
+            assert int(flags[q]) == 1 and bool((keys[q] == -1).all())
+            n_fail += 1
+        else:
+            assert int(flags[q]) == 0 and torch.equal(keys[q], every[:K])
+    assert int(nfail.item()) == n_fail
