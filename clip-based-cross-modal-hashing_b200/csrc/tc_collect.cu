@@ -73,7 +73,7 @@ constexpr int TC_MAX_CHUNKS = 1024;  // candidate segments per query (cmh_topk_f
 constexpr int TC_REFRESH = 16;    // tiles (per epilogue group) between threshold refreshes
 constexpr int TC_PARK = 4;        // flagged lanes of a warp parked per trip (one __syncwarp)
 constexpr int TC_BACKLOG = 8;     // parked slices an epilogue warp can hold (power of two)
-constexpr int TC_PARK_WORDS = 36; // one parked slice: 32 registers, then owner lane, first row (lo, hi), pad
+constexpr int TC_PARK_WORDS = 36; // one parked slice: 32 registers, then owner lane, first row (relative to the chunk), pad
 constexpr int TC_BIAS_SLOTS = 12; // K slots of the bias step that carry weight 127 (the 13th carries weight 1)
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------------------
@@ -205,7 +205,8 @@ struct TcArgs {
     int K;                  // > 0: tighten thresholds while scanning (once K rows at dist <= thr0 - j are known)
     long long* trace;       // CMH_TC_TRACE builds only
     int probe;              // measurement aid (cmh_tc_probe): 1 no tcgen05.mma, 2 no TMEM drain, 4 drain without scan,
-                            // 8 hits decoded but not stored, 16 parked hits dropped, 32 flagged slices not parked
+                            // 8 hits decoded but not stored, 16 parked hits dropped, 32 flagged slices not parked,
+                            // 64 parked slices also worked off in the rounds that parked them
 };
 
 // smem: [A: T tiles x {+-1, +-S, bias digits}][B: STAGES tiles][bias weights][packed ring][barriers][tmem slot][park]
@@ -448,6 +449,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
         const int seg_id = a.seg_base + blockIdx.y * (TC_BUFS / T) + grp / T;
         uint32_t* hq = (a.K > 0 && live) ? a.aux[q].h : nullptr;
         uint32_t pos = 0;
+        // what the hit path needs of ANOTHER lane's query is derived from this lane's by pointer arithmetic (adjacent lanes
+        // are adjacent queries): nothing is recomputed from the launch parameters while a parked slice is worked off
+        uint64_t* const seg_mine = a.cand + ((uint64_t)q * a.n_segs + seg_id) * (uint64_t)a.seg_cap;   // not dereferenced unless live
+        uint32_t* const hq_mine = a.aux[q].h;
+        const int seg_stride = a.n_segs * a.seg_cap;     // keys between the segments of adjacent queries (< 2^31, host-checked)
+        const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
+        const uint32_t row_base = (uint32_t)a.index_base + (uint32_t)c_begin;   // global index of the chunk's first row
+        const uint32_t chunk_len = (uint32_t)(c_end - c_begin);
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + grp * TC_NM;
         // The hit path, taken out of the pipeline's round trip.  A slice that holds a flagged row is PARKED: each flagged
         // lane copies its 32 registers into an entry of the warp's shared-memory queue (TC_BACKLOG entries) and the warp
@@ -460,23 +469,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
         // walking its own slice took ~4x as long: a dependent chain of ~100 instructions at one warp's issue latency.)
         uint32_t* park = scratch + ew * (TC_BACKLOG * TC_PARK_WORDS);
         int n_parked = 0, head = 0;                      // warp-uniform
+        bool parked_now = false;                         // ... this round's scan parked a slice
         const bool hq_on = a.K > 0, drop = (a.probe & 16) != 0, store = !(a.probe & 8);
         auto work_off = [&]() {                          // the oldest parked slice, by the whole warp
             const uint32_t* mine = park + head * TC_PARK_WORDS;
             const uint32_t xr = mine[lane];              // lane r looks at register r of the slice
-            const int owner = (int)mine[32];
-            const int64_t row0 = (int64_t)(((uint64_t)mine[34] << 32) | mine[33]);
+            const uint2 hdr = *reinterpret_cast<const uint2*>(mine + 32);    // owner lane, first row (relative to the chunk)
+            const int owner = (int)hdr.x;
             const int thr_o = __shfl_sync(0xffffffffu, thr, owner);
             const int thr0_o = __shfl_sync(0xffffffffu, thr0, owner);
             uint32_t pos_o = __shfl_sync(0xffffffffu, pos, owner);
-            const int64_t q_o = q - lane + owner;
             const int dot_thr0_o = a.bits - 2 * max(0, thr0_o);
-            uint32_t fl = (q_o < a.nq && !drop) ? (~xr & FLAGS) : 0u;
-            uint64_t* seg_o = a.cand + ((uint64_t)(q_o < a.nq ? q_o : 0) * a.n_segs + seg_id) * (uint64_t)a.seg_cap;
-            while (__any_sync(0xffffffffu, fl != 0u)) {          // one trip unless a register holds two flagged rows
+            uint32_t fl = (((live_mask >> owner) & 1u) && !drop) ? (~xr & FLAGS) : 0u;
+            uint64_t* const seg_o = seg_mine + (int64_t)(owner - lane) * seg_stride;
+            do {                                         // one trip unless a register holds two flagged rows
                 bool pass = false;
                 int dist = 0;
-                int64_t row = 0;
+                uint32_t rel = 0;
                 if (fl) {
                     const int bit = 31 - __clz(fl);
                     fl &= ~(1u << bit);
@@ -488,18 +497,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
                     const int e1 = (int)((uint32_t)val << (32 - FIELD)) >> (32 - FIELD);
                     const int dot = f ? ((val - e1) >> FIELD) + dot_thr0_o - 1 : e1 + dot_thr0_o;
                     dist = (a.bits - dot) >> 1;
-                    row = row0 + col + f * TC_NM;
-                    pass = dist <= thr_o && row < c_end;
+                    rel = hdr.y + (uint32_t)(col + f * TC_NM);
+                    pass = dist <= thr_o && rel < chunk_len;
                 }
                 const uint32_t m = __ballot_sync(0xffffffffu, pass);
                 if (pass && store) {
                     const uint32_t p = pos_o + __popc(m & lanemask_lt());
-                    if (p < (uint32_t)a.seg_cap)
-                        seg_o[p] = ((uint64_t)(uint32_t)(2 * dist) << 32) | ((uint32_t)a.index_base + (uint32_t)row);
-                    if (hq_on) atomicAdd(a.aux[q_o].h + min(thr0_o - dist, 3), 1u);
+                    if (p < (uint32_t)a.seg_cap) seg_o[p] = ((uint64_t)(uint32_t)(2 * dist) << 32) | (row_base + rel);
+                    if (hq_on) atomicAdd(hq_mine + (owner - lane) * 8 + min(thr0_o - dist, 3), 1u);
                 }
                 pos_o += __popc(m);
-            }
+            } while (__any_sync(0xffffffffu, fl != 0u));
             if (lane == owner) pos = pos_o;
             __syncwarp();                                // the entry may be overwritten now
             head = (head + 1) & (TC_BACKLOG - 1);
@@ -521,7 +529,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
 #pragma unroll
                     for (int r = 0; r < 32; r += 4)
                         *reinterpret_cast<uint4*>(mine + r) = make_uint4(v[r], v[r + 1], v[r + 2], v[r + 3]);
-                    *reinterpret_cast<uint4*>(mine + 32) = make_uint4((uint32_t)lane, (uint32_t)row0, (uint32_t)((uint64_t)row0 >> 32), 0u);
+                    *reinterpret_cast<uint2*>(mine + 32) = make_uint2((uint32_t)lane, (uint32_t)(row0 - c_begin));
                 }
                 __syncwarp();
                 n_parked += __popc(take);
@@ -552,6 +560,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
             if (__any_sync(0xffffffffu, f0 || f1)) {
                 park_slice(v0, f0, r0);
                 park_slice(v1, f1, r1);
+                parked_now = true;
             }
         };
         auto release = [&]() {                   // the values are in registers: the buffer goes back to its issuer
@@ -564,8 +573,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
             const int i = it / T;
             const int64_t row0 = c_begin + (int64_t)i * TC_N;
             if (qrow == 0) TC_TRACE(2 + grp, round, 0);
-            // the backlog of parked hits is worked off in the time this warp would spend waiting for its tile
-            while (n_parked > 0 && !__any_sync(0xffffffffu, mbar_test(&t_full[grp], round & 1))) work_off();
+            // The backlog of parked hits is worked off in the time this warp would spend waiting for its tile - but not
+            // in a round that has just parked: scan + parking + one work-off is about as long as the wait, and a warp
+            // that is late for its tile holds the whole group's buffer back (the tensor pipe has no slack to catch up).
+            const bool busy_round = parked_now && !(a.probe & 64);
+            parked_now = false;
+            if (!busy_round)
+                while (n_parked > 0 && !__any_sync(0xffffffffu, mbar_test(&t_full[grp], round & 1))) work_off();
             mbar_wait(&t_full[grp], round & 1);
             tc_fence_after();
             if (qrow == 0) TC_TRACE(2 + grp, round, 1);
@@ -966,6 +980,8 @@ static int tc_collect_impl(const uint64_t* q_sign, int64_t nq, const uint64_t* d
     CMH_REQUIRE(seg_base >= 0 && seg_base + n_segs <= seg_total, CMH_ERR_ARG,
                 "cmh_tc_collect: segments [%d, %d) do not fit seg_total=%d (see cmh_tc_plan)", seg_base, seg_base + n_segs,
                 seg_total);
+    CMH_REQUIRE((int64_t)seg_total * seg_cap < (1ll << 31), CMH_ERR_UNSUPPORTED,
+                "cmh_tc_collect: seg_total * seg_cap = %lld keys per query (must stay below 2^31)", (long long)seg_total * seg_cap);
     CMH_REQUIRE(q_sign && thr && cand && cnt && aux, CMH_ERR_ARG, "cmh_tc_collect: NULL pointer");
     static_assert(sizeof(TcAux) == 32, "cmh_tc_collect: aux is uint32 [nq][8]");
     CMH_CUDA(cudaMemsetAsync(cnt + (size_t)seg_base * nq, 0, (size_t)n_segs * nq * 4, st));
@@ -1001,7 +1017,7 @@ extern "C" int cmh_tc_collect(const uint64_t* q_sign, int64_t nq, const uint64_t
 extern "C" int cmh_tc_probe(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits,
                             const int32_t* thr, int seg_total, int seg_cap, uint64_t* cand, uint32_t* cnt, uint32_t* aux,
                             int probe, void* stream) {
-    CMH_REQUIRE(probe >= 0 && probe < 64, CMH_ERR_ARG, "cmh_tc_probe: probe=%d", probe);
+    CMH_REQUIRE(probe >= 0 && probe < 128, CMH_ERR_ARG, "cmh_tc_probe: probe=%d", probe);
     return tc_collect_impl(q_sign, nq, d_sign, nd, bits, 0, thr, 0, 0, seg_total, seg_cap, cand, cnt, aux, probe, stream);
 }
 

@@ -11,7 +11,7 @@ L = _cabi.lib(); st = engine._stream(dev); p = engine._ptr
 db = engine.synth_codes(4000, 0, D, BITS, dev); q = engine.synth_codes(4001, 0, Q, BITS, dev)
 b = engine.TcBuffers(Q, [D], BITS, 32768, dev)
 
-def timed(fn, reps=3):
+def timed(fn, reps=6):
     fn(); torch.cuda.synchronize(); ts = []
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -19,10 +19,10 @@ def timed(fn, reps=3):
     return min(ts)
 
 base = None
-for thr in (-1, 14, 15, 16, 17):
+for thr in (-1, 15, 16, 17, -1, 15, 16):
     thr0 = torch.full((Q,), thr, dtype=torch.int32, device=dev)
     row = []
-    for mode in (32, 16, 8, 0):
+    for mode in (32, 16, 64, 0):
         t = timed(lambda: engine.check(L.cmh_tc_probe(p(q.sign), Q, p(db.sign), D, BITS, p(thr0), b.seg_total, b.seg_cap, p(b.cand), p(b.cnt), p(b.aux), mode, st)))
         row.append(t)
     cand = float(b.cnt.sum(0).float().mean())
@@ -32,5 +32,5 @@ for thr in (-1, 14, 15, 16, 17):
     t_real = timed(real); cand_real = float(b.cnt.sum(0).float().mean())
     if base is None: base = row[-1]
     cyc = lambda t, c: (t - base) * 1e-3 * 148 * 1.965e9 / max(1.0, c * Q)
-    print(f"thr {thr:3d}: no-park {row[0]:.2f}  no-work {row[1]:.2f}  no-store {row[2]:.2f}  full {row[3]:.2f} ms  cand/q {cand:.0f}  -> {cyc(row[3], cand):.0f} SM-cycles/candidate;"
+    print(f"thr {thr:3d}: no-park {row[0]:.2f}  no-work {row[1]:.2f}  eager {row[2]:.2f}  full {row[3]:.2f} ms  cand/q {cand:.0f}  -> {cyc(row[3], cand):.0f} SM-cycles/candidate;"
           f"  K>0: {t_real:.2f} ms cand/q {cand_real:.0f}", flush=True)
