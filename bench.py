@@ -59,7 +59,7 @@ def config_dict(args, world):
     return {"workload": "c4: 64-bit exact stable top-1000 Hamming retrieval, 100M-row database, one query chunk per step",
             "bits": BITS, "topk": TOPK, "db_rows": args.db_rows, "queries_per_step": args.queries,
             "pipelining": "none: one query chunk at a time, resolved and verified before the next is enqueued",
-            "sharding": f"database rows split contiguously over {world} GPU(s); queries replicated; all-reduced threshold histograms, NCCL all-to-all by query slice + merge + all-gather"
+            "sharding": f"database rows over {world} GPUs in lockstep stripes (3 global stripes x {world} contiguous pieces, rank r holds piece r of each); queries replicated; all-reduced threshold / prefix-rule histograms, NCCL all-to-all by query slice + merge + all-gather"
                         if world > 1 else "single GPU holds the whole database",
             "l2": "per-step working set (packed shard + candidate segments, >1 GB) exceeds the 126 MB L2; no explicit flush",
             "seed": SEED}
@@ -248,10 +248,22 @@ def main_native(args):
         return float(t.item())
 
     Q, D, K = args.queries, args.db_rows, TOPK
-    lo, hi = sharded.shard_bounds(D, world, rank)
-    db = engine.synth_codes(SEED, lo, hi - lo, BITS, dev)
+    # One GPU holds the rows 0..D-1.  N GPUs hold them in LOCKSTEP STRIPES (`sharded.lockstep_stripes`): three global
+    # stripes, each cut into N contiguous pieces, rank r holding piece r of every stripe - all shards walk the database
+    # front to back together, so the exact prefix rule tightens as early as on one GPU.  (One contiguous range per
+    # shard is supported too - `HammingIndex(db, index_base)` - but shard 0 then never benefits from the rule.)
+    if world > 1:
+        ranges, stripes = sharded.lockstep_stripes(D, world, rank)
+        parts = [engine.synth_codes(SEED, a, b - a, BITS, dev) for a, b in ranges]
+        rows = torch.cat([p.sign for p in parts])
+        db = engine.PackedSet(rows, None, None, rows.shape[0], BITS)
+        del parts
+    else:
+        ranges, stripes = [(0, D)], None
+        db = engine.synth_codes(SEED, 0, D, BITS, dev)
+    lo, hi = ranges[0][0], ranges[0][0] + db.n          # hi - lo = rows of this shard
     q_packed = engine.synth_codes(SEED + 1, 0, Q, BITS, dev)
-    index = HammingIndex(db, lo, nd_total=D)
+    index = HammingIndex(db, lo, nd_total=D, stripes=stripes)
 
     # ---- device-resident timing ("value") ------------------------------------------------------------------
     # nvidia-smi is started before the warm-up: its NVML start-up takes driver locks and must not land in the timed
@@ -341,7 +353,7 @@ def main_native(args):
         # the queries go first (H2D copies share one engine: behind the shard they would wait for all of it); the
         # packed shard is uploaded in row ranges on a copy stream and the search scans each range as it lands
         qp = cu.pack_codes(q_host.to(dev, non_blocking=True), dev)
-        idx = HammingIndex.from_packed_host(db_host, BITS, lo, nd_total=D, out=db_dev, pieces=3)
+        idx = HammingIndex.from_packed_host(db_host, BITS, lo, nd_total=D, out=db_dev, pieces=3, stripes=stripes)
         k = idx.search_packed(qp, K)
         keys_host.copy_(k, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()

@@ -336,6 +336,35 @@ def topk_merge(keys_in: torch.Tensor, K: int) -> torch.Tensor:
     return out
 
 
+def check_stripes(stripes, n_rows: int, index_base: int = 0) -> list:
+    """Normalise the stripes of a shard: ``[(local_row, global_index), ...]`` - the local rows from ``local_row`` up to
+    the next stripe (or the end of the shard) are the database rows ``global_index, global_index + 1, ...``.  A shard
+    that is one contiguous row range is the single stripe ``[(0, index_base)]``."""
+    if not stripes:
+        return [(0, int(index_base))]
+    out = [(int(lo), int(g)) for lo, g in stripes]
+    if out[0][0] != 0 or any(b[0] < a[0] for a, b in zip(out, out[1:])) or out[-1][0] > max(int(n_rows), 0):
+        raise ValueError("stripes must start at local row 0 and ascend within the shard")
+    return out
+
+
+def stripe_ranges(stripes: list, n_rows: int) -> list:
+    """[(local_lo, local_hi, global_index of local_lo), ...] of the non-empty stripes."""
+    ends = [lo for lo, _ in stripes[1:]] + [int(n_rows)]
+    return [(lo, hi, g) for (lo, g), hi in zip(stripes, ends) if hi > lo]
+
+
+def topk_exact(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, stripes=None, ternary=None) -> torch.Tensor:
+    """The exact two-pass (popc) top-K keys of one shard, stripe by stripe + merge when the shard has several."""
+    parts = stripe_ranges(check_stripes(stripes, d.n, index_base), d.n)
+    if len(parts) <= 1:
+        base = parts[0][2] if parts else int(index_base)
+        return RankPass(q, d.with_labels(None, 0), need_labels=False, ternary=ternary).topk(K, base)
+    lists = [RankPass(q, d.rows(lo, hi).with_labels(None, 0), need_labels=False, ternary=ternary).topk(K, g)
+             for lo, hi, g in parts]
+    return topk_merge(torch.stack(lists), K)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # top-K on the tensor cores (tcgen05 / TMEM): sample histogram -> thresholds -> fused GEMM + candidate filter ->
 # per-query sort; queries whose candidate list came out short or overflowed are redone by the exact two-pass path
@@ -422,7 +451,8 @@ class LocalComm:
 def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Optional[PackedSet] = None,
             cap: int = TC_DEFAULT_CAP, stats: Optional[dict] = None, tighten: bool = True,
             seg_cap: Optional[int] = None, pilot: Optional[int] = None, comm=None, nd_total: Optional[int] = None,
-            exact_fallback=None, buffers: Optional[dict] = None, ready=None, defer: bool = False, prefix: bool = True):
+            exact_fallback=None, buffers: Optional[dict] = None, ready=None, defer: bool = False, prefix: bool = True,
+            stripes=None):
     """int64 [nq, K] ascending keys, identical to ``RankPass(q, d).topk(K, index_base)`` (to the global stable
     ranking when ``d`` is one shard of a database of ``nd_total`` rows and ``comm`` spans the shards).
 
@@ -440,6 +470,11 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
             boundaries and every launch waits only for the rows it reads
     prefix  apply the prefix rule (`cmh_tc_choose_prefix` / `cmh_tc_choose_seen`) at `TC_PREFIX_FRACTIONS` of the rows:
             exact; sharded databases all-gather the candidate histograms of the rows scanned so far at each cut
+    stripes ``[(local_row, global_index), ...]`` (`check_stripes`): the shard is several row ranges of the database
+            instead of one (``index_base`` is then ignored).  With ``comm`` spanning several shards the stripes must be
+            LOCKSTEP stripes - the same number on every shard, stripe j of every shard below stripe j+1 of every shard
+            in global index: the prefix rule is then applied at the stripe boundaries on the all-reduced histograms,
+            with everything scanned so far (on any shard) of lower index than everything still to come, as on one GPU
     defer   return a callable instead of the keys: everything is enqueued, and calling it reads the verdict (a host
             sync), redoes failed queries and returns the keys - lets a caller keep two query chunks in flight
     buffers a dict the caller keeps between calls: the multi-GB candidate scratch is allocated once per query-chunk
@@ -477,12 +512,23 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     ends = sorted({e for e in stages if 0 < e < d.n})
     # the prefix rule (exact): after these rows the candidates so far bound what later rows can still contribute
     # (every shard takes part in every exchange, so whether and how often is decided from the global sizes alone)
+    stripes = check_stripes(stripes, d.n, index_base)
+    lockstep = comm.world > 1 and len(stripes) > 1
+    ascending = all(b[1] >= a[1] + (b[0] - a[0]) for a, b in zip(stripes, stripes[1:]))
     prefix_cuts = []
-    if prefix and -(-nd_total // comm.world) >= TC_PREFIX_MIN_ROWS:
+    if lockstep:
+        if prefix:
+            prefix_cuts = [lo for lo, _ in stripes[1:]]
+    elif prefix and ascending and -(-nd_total // comm.world) >= TC_PREFIX_MIN_ROWS:
         fractions = TC_PREFIX_FRACTIONS if comm.world == 1 else TC_PREFIX_FRACTIONS_SHARDED
         prefix_cuts = [min(d.n, int(d.n * f) // 256 * 256) for f in fractions]
     prefix_ends = {e for e in prefix_cuts if (stages[-1] if stages else 0) < e < d.n}
-    cuts = sorted({0, d.n} | set(ends) | prefix_ends | {int(e) for e, _ in (ready or ()) if 0 < int(e) < d.n})
+    cuts = sorted({0, d.n} | set(ends) | prefix_ends | {int(e) for e, _ in (ready or ()) if 0 < int(e) < d.n} |
+                  {lo for lo, _ in stripes if 0 < lo < d.n})
+
+    def global_index(row: int) -> int:               # of a local row (spans never straddle a stripe boundary)
+        lo, g = [st_ for st_ in stripes if st_[0] <= row][-1]
+        return g + (row - lo)
     spans = [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]] or [(0, 0)]
     regions = [hi - lo for lo, hi in spans]
 
@@ -571,7 +617,11 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
                 check(L.cmh_tc_cand_hist(_ptr(b.cand), _ptr(b.cnt), nq, 0, seg_hi, b.seg_total, b.seg_cap, nb, _ptr(ph),
                                          _ptr(over), st), "cmh_tc_cand_hist")
             out = b.thr3 if thr_cur is not b.thr3 else b.thr4
-            if comm.world > 1:
+            if lockstep:
+                # lockstep stripes: whatever any shard has scanned lies below whatever any shard has still to scan
+                ph = comm.all_reduce_sum(ph)
+                check(L.cmh_tc_choose_prefix(_ptr(ph), None, nq, nb, K, _ptr(thr_cur), _ptr(out), st), "cmh_tc_choose_prefix")
+            elif comm.world > 1:
                 every = comm.all_gather_stack(ph)                                    # [world, nq, nb]
                 lower = every[:comm.rank + 1].sum(0, dtype=torch.int32).contiguous()
                 seen = every.sum(0, dtype=torch.int32).contiguous()
@@ -607,7 +657,7 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
             wait_rows(hi)
             mark()
             # tightening (main spans) uses this launch's own counts: K rows found locally are K rows found globally
-            check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign[lo:]), hi - lo, q.bits, int(index_base) + lo,
+            check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign[lo:]), hi - lo, q.bits, global_index(lo),
                                    _ptr(thr_cur), 0 if in_pilot or not tighten else K, b.seg_base[i], b.seg_total,
                                    b.seg_cap, _ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), st), "cmh_tc_collect")
             mark()
@@ -652,7 +702,7 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
             if exact_fallback is None:
                 if comm.world > 1:
                     raise RuntimeError("a sharded tensor-core top-K needs exact_fallback")
-                redo = RankPass(sub, d.with_labels(None, 0), need_labels=False).topk(K, index_base)
+                redo = topk_exact(sub, d, K, index_base, stripes)
             else:
                 redo = exact_fallback(sub)
             keys.index_copy_(0, rows, redo)

@@ -53,8 +53,10 @@ class HammingIndex:
     SAMPLE_ROWS = 65_536
 
     def __init__(self, db: PackedSet, index_base: int = 0, group=None, nd_total: Optional[int] = None,
-                 sample: Optional[PackedSet] = None, ready=None):
+                 sample: Optional[PackedSet] = None, ready=None, stripes=None):
         self._ready = ready                      # [(row_end, event)]: an upload still in flight (`from_packed_host`)
+        # a shard made of several row ranges of the database (`sharded.lockstep_stripes`): [(local_row, global_index)]
+        self.stripes = _e.check_stripes(stripes, db.n, index_base) if stripes else None
         if db.labels is not None:
             db = db.with_labels(None, 0)
         if db.n and db.sign.data_ptr() % 16:
@@ -97,7 +99,7 @@ class HammingIndex:
 
     @classmethod
     def from_packed(cls, words: torch.Tensor, bits: int, index_base: int = 0, group=None,
-                    nd_total: Optional[int] = None) -> "HammingIndex":
+                    nd_total: Optional[int] = None, stripes=None) -> "HammingIndex":
         """Adopt already packed +-1 codes: int64 / uint64-bit-pattern tensor ``[D, ceil(bits/64)]`` on a GPU,
         padding bits zero."""
         if words.dim() != 2 or words.shape[1] != (bits + 63) // 64:
@@ -105,18 +107,18 @@ class HammingIndex:
         if not words.is_cuda:
             raise RuntimeError("packed database must be on a CUDA device")
         return cls(PackedSet(words.contiguous().view(torch.int64), None, None, words.shape[0], bits), index_base, group,
-                   nd_total)
+                   nd_total, stripes=stripes)
 
     @classmethod
     def from_packed_host(cls, words: torch.Tensor, bits: int, index_base: int = 0, group=None,
                          nd_total: Optional[int] = None, pieces: int = 4, out: Optional[torch.Tensor] = None,
-                         device=None) -> "HammingIndex":
+                         device=None, stripes=None) -> "HammingIndex":
         """Upload packed +-1 codes from (pinned) host memory WITHOUT waiting for the copy: the rows travel in
         ``pieces`` ranges on a copy stream, and the first search scans each range as soon as it has landed (the
         pilot rows first), so the upload of a fresh database hides behind the search that needs it.
         ``out``: optional device tensor [D, words] to upload into (reused between calls)."""
         if words.is_cuda:
-            return cls.from_packed(words, bits, index_base, group, nd_total)
+            return cls.from_packed(words, bits, index_base, group, nd_total, stripes)
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         nwords = (bits + 63) // 64
         if words.dim() != 2 or words.shape[1] != nwords:
@@ -145,7 +147,8 @@ class HammingIndex:
                 ev.record(copy_stream)
                 ready.append((hi, ev))
                 lo = hi
-        return cls(PackedSet(dst, None, None, n, bits), index_base, group, nd_total, sample=sample, ready=ready)
+        return cls(PackedSet(dst, None, None, n, bits), index_base, group, nd_total, sample=sample, ready=ready,
+                   stripes=stripes)
 
     def _upload_done(self) -> None:
         if self._ready:
@@ -157,9 +160,10 @@ class HammingIndex:
         if self.sample is not None and q.valid is None and q.bits == self.db.bits and 1 <= int(K) <= _e.TC_MAX_K:
             ready, self._ready = self._ready, None       # only the first search can overlap the upload
             return _sh.topk_tc_sharded(q, self.db, int(K), self.index_base, self.nd_total, sample=self.sample,
-                                       group=self.group, stats=stats, buffers=self._tc_buffers, ready=ready)
+                                       group=self.group, stats=stats, buffers=self._tc_buffers, ready=ready,
+                                       stripes=self.stripes)
         self._upload_done()
-        return _sh.topk_sharded(q, self.db, int(K), self.index_base, self.group, ternary=None)
+        return _sh.topk_sharded(q, self.db, int(K), self.index_base, self.group, ternary=None, stripes=self.stripes)
 
     def search_packed_async(self, q: PackedSet, K: int, stats: Optional[dict] = None) -> "PendingSearch":
         """`search_packed` without waiting: the search is enqueued on one of two alternating side streams (each with
@@ -180,7 +184,8 @@ class HammingIndex:
         stream.wait_stream(torch.cuda.current_stream(dev))           # the queries (and the database) are ready
         with torch.cuda.stream(stream):
             finish = _sh.topk_tc_sharded(q, self.db, int(K), self.index_base, self.nd_total, sample=self.sample,
-                                         group=self.group, stats=stats, buffers=buffers, ready=ready, defer=True)
+                                         group=self.group, stats=stats, buffers=buffers, ready=ready, defer=True,
+                                         stripes=self.stripes)
             done = torch.cuda.Event()
             done.record(stream)
         return PendingSearch(finish, (stream, done), None)

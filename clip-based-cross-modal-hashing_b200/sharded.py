@@ -33,6 +33,28 @@ def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+LOCKSTEP_FRACTIONS = (0.3, 0.6)   # stripe boundaries of a database sharded in lockstep stripes (= the prefix-rule cuts)
+
+
+def lockstep_stripes(n_rows: int, world: int, rank: int, fractions=LOCKSTEP_FRACTIONS, align: int = 256):
+    """Split a database of ``n_rows`` into ``len(fractions) + 1`` global stripes and every stripe into ``world``
+    contiguous pieces: rank r holds piece r of every stripe.  All shards then walk the database front to back in
+    lockstep - after stripe j everything any shard has scanned has a lower index than everything still to come - so the
+    exact prefix rule of the tensor-core top-K tightens as early on 8 GPUs as on one (with one contiguous range per
+    shard, shard 0 never sees a lower-index row outside its own prefix).
+    Returns ``(ranges, stripes)``: the global row ranges ``[(lo, hi), ...]`` this rank holds, in local order, and the
+    ``[(local_row, global_index), ...]`` description `engine.topk_tc` / `HammingIndex` take."""
+    unit = max(1, int(align)) * int(world)
+    edges = [0] + [min(int(n_rows), int(n_rows * f) // unit * unit) for f in fractions] + [int(n_rows)]
+    ranges, stripes, local = [], [], 0
+    for a, b in zip(edges, edges[1:]):
+        lo, hi = shard_bounds(b - a, world, rank)
+        ranges.append((a + lo, a + hi))
+        stripes.append((local, a + lo))
+        local += hi - lo
+    return ranges, stripes
+
+
 def _world(group) -> Tuple[int, int]:
     if not dist.is_available() or not dist.is_initialized():
         return 0, 1
@@ -124,12 +146,16 @@ class GroupComm:
 
 
 def topk_sharded(q, d_shard, K: int, index_base: int, group=None, eng=_engine,
-                 ternary: Optional[bool] = None) -> torch.Tensor:
+                 ternary: Optional[bool] = None, stripes=None) -> torch.Tensor:
     """Global top-``K`` keys int64 [Q, K] (ascending, ``-1`` pads) - identical on every rank.
-    ``index_base`` is the global index of this shard's first row.  The exact two-pass (popc) path: every rank
-    selects its local top-K, one all-gather, K-way merge."""
-    rp = eng.RankPass(q, d_shard, need_labels=False, ternary=ternary)
-    local = rp.topk(K, index_base)
+    ``index_base`` is the global index of this shard's first row (``stripes``: `engine.check_stripes`, a shard made
+    of several row ranges).  The exact two-pass (popc) path: every rank selects its local top-K, one all-gather,
+    K-way merge."""
+    if stripes and len(stripes) > 1:
+        local = eng.topk_exact(q, d_shard, K, index_base, stripes, ternary=ternary)
+    else:
+        rp = eng.RankPass(q, d_shard, need_labels=False, ternary=ternary)
+        local = rp.topk(K, index_base)
     _, world = _world(group)
     if world == 1:
         return local
@@ -143,5 +169,7 @@ def topk_tc_sharded(q, d_shard, K: int, index_base: int, nd_total: int, sample=N
     share of the ~K rows below them; the per-shard results are all-gathered and merged, and the merged K-th key is
     verified against the thresholds.  Queries that fail the check are redone by `topk_sharded` on every rank."""
     comm = GroupComm(group)
+    stripes = kw.get("stripes")
     return eng.topk_tc(q, d_shard, K, index_base, sample=sample, comm=comm, nd_total=nd_total, stats=stats,
-                       exact_fallback=lambda sub: topk_sharded(sub, d_shard, K, index_base, group, eng), **kw)
+                       exact_fallback=lambda sub: topk_sharded(sub, d_shard, K, index_base, group, eng, stripes=stripes),
+                       **kw)

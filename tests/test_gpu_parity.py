@@ -407,12 +407,20 @@ class _ThreadComm:
                                                          (128, 2, 1_500_000, 500, 150_016, None),
                                                          (64, 3, 2_400_123, 300, 100_000, (0.2, 0.5, 0.8)),
                                                          (64, 4, 1_000_000, 1000, 0, (0.25, 0.5, 0.75)),
-                                                         (128, 2, 1_500_000, 500, 150_016, (0.3, 0.6))])
+                                                         (128, 2, 1_500_000, 500, 150_016, (0.3, 0.6)),
+                                                         (64, 3, 2_400_123, 300, 100_000, "lockstep"),
+                                                         (64, 4, 1_000_001, 1000, 0, "lockstep"),
+                                                         (128, 2, 1_500_000, 500, 150_016, "lockstep")])
 def test_tc_topk_sharded_matches_single(dev, bits, world, D, K, pilot, prefix, monkeypatch):
     """Shards that filter with all-reduced (global) thresholds + merge + verify == the exact single-shard ranking;
-    with ``prefix``, the shards also tighten by the cross-shard prefix rule (all-gathered candidate histograms)."""
+    with ``prefix``, the shards also tighten by the cross-shard prefix rule (all-gathered candidate histograms);
+    "lockstep": every shard holds one piece of each of three global stripes (`sharded.lockstep_stripes`) and the
+    prefix rule runs on the all-reduced histograms at the stripe boundaries."""
     import threading
     from cmh_b200 import engine, sharded
+    lockstep = prefix == "lockstep"
+    if lockstep:
+        prefix = None
     if prefix is not None:
         monkeypatch.setattr(engine, "TC_PREFIX_MIN_ROWS", 1000)
         monkeypatch.setattr(engine, "TC_PREFIX_FRACTIONS_SHARDED", prefix)
@@ -428,12 +436,20 @@ def test_tc_topk_sharded_matches_single(dev, bits, world, D, K, pilot, prefix, m
             comm.bind(rank)
             torch.cuda.set_device(dev)
             lo, hi = sharded.shard_bounds(D, world, rank)
-            shard = db.rows(lo, hi)
+            stripes = None
+            if lockstep:
+                ranges, stripes = sharded.lockstep_stripes(D, world, rank, (0.25, 0.6), align=64)
+                rows = torch.cat([db.sign[a:b] for a, b in ranges])
+                shard = engine.PackedSet(rows, None, None, rows.shape[0], bits)
+                assert sum(b - a for a, b in ranges) == shard.n and stripes[0] == (0, ranges[0][0])
+            else:
+                shard = db.rows(lo, hi)
             if shard.sign.data_ptr() % 16:
                 shard = engine.PackedSet(shard.sign.clone(), None, None, shard.n, shard.bits)
             smp = engine.PackedSet(shard.sign[::97].contiguous(), None, None, (shard.n + 96) // 97, bits)
             st = {}
             out[rank] = (engine.topk_tc(q, shard, K, lo, sample=smp, comm=comm, nd_total=D, stats=st, pilot=pilot,
+                                        stripes=stripes,
                                         exact_fallback=lambda sub: engine.RankPass(sub, db, need_labels=False).topk(K, 0)),
                          st)
         except Exception as e:  # noqa: BLE001
@@ -449,9 +465,12 @@ def test_tc_topk_sharded_matches_single(dev, bits, world, D, K, pilot, prefix, m
         assert st["n_fail"] == 0
     # each shard collected only its share of the candidates
     assert sum(int(st["candidates"].sum()) for _, st in out) < 40 * K * Q
-    if prefix is not None:                           # the rule did tighten, and never above the statistical bound
+    if prefix is not None or lockstep:               # the rule did tighten, and never above the statistical bound
         assert all(bool((st["thr_final"] <= st["thr"]).all()) for _, st in out)
         assert any(bool((st["thr_final"] < st["thr"]).any()) for _, st in out)
+    if lockstep:                                     # ... on EVERY shard, the first one included, and all alike
+        assert bool((out[0][1]["thr_final"] < out[0][1]["thr"]).any())
+        assert all(torch.equal(st["thr_final"], out[0][1]["thr_final"]) for _, st in out)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -776,3 +795,33 @@ def test_finalize_and_cand_hist_over_many_segments(dev, n_segs, seg_cap, nq, K):
         else:
             assert int(flags[q]) == 0 and torch.equal(keys[q], every[:K])
     assert int(nfail.item()) == n_fail
+
+
+def test_stripes_single_gpu_and_exact_path(dev):
+    """A shard made of several row ranges with their own global indices (`engine.check_stripes`): the tensor-core
+    search, the exact path and `HammingIndex` number the rows by their stripes."""
+    from cmh_b200 import engine
+    from cmh_b200.index import HammingIndex
+    D, Q, K = 1_200_000, 200, 300
+    full = engine.synth_codes(31, 0, 3 * D, 64, dev)
+    # local rows = global [2D, 2D + D/2) then [D/2, D): descending stripes (no prefix rule), a gap in between
+    pieces = [(2 * D, 2 * D + D // 2), (D // 2, D)]
+    rows = torch.cat([full.sign[a:b] for a, b in pieces])
+    shard = engine.PackedSet(rows, None, None, rows.shape[0], 64)
+    stripes = [(0, 2 * D), (D // 2, D // 2)]
+    q = engine.synth_codes(32, 0, Q, 64, dev)
+    lists = [engine.RankPass(q, full.rows(a, b), need_labels=False).topk(K, a) for a, b in pieces]
+    want = engine.topk_merge(torch.stack(lists), K)
+    assert torch.equal(engine.topk_exact(q, shard, K, 0, stripes), want)
+    assert torch.equal(engine.topk_tc(q, shard, K, 0, sample=None, stripes=stripes), want)
+    idx = HammingIndex(shard, stripes=stripes)
+    assert torch.equal(idx.search_packed(q, K), want)
+    # ascending stripes: the prefix rule stays on
+    pieces = [(D // 2, D), (2 * D, 2 * D + D // 2)]
+    rows = torch.cat([full.sign[a:b] for a, b in pieces])
+    shard = engine.PackedSet(rows, None, None, rows.shape[0], 64)
+    stripes = [(0, D // 2), (D // 2, 2 * D)]
+    lists = [engine.RankPass(q, full.rows(a, b), need_labels=False).topk(K, a) for a, b in pieces]
+    want = engine.topk_merge(torch.stack(lists), K)
+    smp = engine.PackedSet(shard.sign[::53].contiguous(), None, None, (shard.n + 52) // 53, 64)
+    assert torch.equal(engine.topk_tc(q, shard, K, 0, sample=smp, stripes=stripes), want)

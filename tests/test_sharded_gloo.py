@@ -140,3 +140,30 @@ def test_shard_bounds_cover_rows():
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("n,world", [(100_000_000, 8), (1_000_003, 3), (5, 4), (0, 2)])
+def test_lockstep_stripes_cover_rows_in_order(n, world):
+    """Every row belongs to exactly one (rank, stripe) piece; stripe j of every rank lies below stripe j+1 of every
+    rank; the stripe descriptions number the local rows by their global index."""
+    from cmh_b200 import engine, sharded
+    per_rank = [sharded.lockstep_stripes(n, world, r) for r in range(world)]
+    n_stripes = len(sharded.LOCKSTEP_FRACTIONS) + 1
+    covered = 0
+    for j in range(n_stripes):
+        pieces = [per_rank[r][0][j] for r in range(world)]
+        assert all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))            # contiguous across the ranks
+        if j + 1 < n_stripes:
+            assert pieces[-1][1] == per_rank[0][0][j + 1][0]                     # ... and across the stripes
+        covered += sum(hi - lo for lo, hi in pieces)
+    assert covered == n and per_rank[0][0][0][0] == 0 and per_rank[-1][0][-1][1] == n
+    for ranges, stripes in per_rank:
+        local = 0
+        for (lo, hi), (row, g) in zip(ranges, stripes):
+            assert (row, g) == (local, lo)
+            local += hi - lo
+        norm = engine.check_stripes(stripes, local)
+        assert [(a, b, g) for a, b, g in engine.stripe_ranges(norm, local)] == \
+               [(r, r + hi - lo, lo) for (lo, hi), (r, _) in zip(ranges, stripes) if hi > lo]
+    with pytest.raises(ValueError):
+        engine.check_stripes([(1, 0)], 10)
