@@ -43,7 +43,8 @@ def run(label, n_it=5, **kw):
     print(f"{label:24s} {e0.elapsed_time(e1) / n_it:.3f} ms/step  " + " ".join(f"{k[:-5]}={v:.2f}" for k, v in ph.items()) +
           "  collect " + "+".join(f"{c:.2f}" for c in col) + f" = {sum(col):.2f}  cand/q {float(stats['candidates'].float().mean()):.0f}", flush=True)
 
-run("no prefix", prefix=False)
-for fr in ((0.3, 0.6), (0.3,), (0.2, 0.5), (0.25,), (0.4,), (0.3, 0.5, 0.7, 0.85)):
-    engine.TC_PREFIX_FRACTIONS_SHARDED = fr
-    run(f"prefix {fr}")
+run("contiguous shard", n_it=8)
+ranges, stripes = __import__("cmh_b200.sharded", fromlist=["x"]).lockstep_stripes(D, WORLD, RANK)
+rows = torch.cat([engine.synth_codes(4000, a, b - a, 64, dev).sign for a, b in ranges])
+db = engine.PackedSet(rows, None, None, rows.shape[0], 64)
+run("lockstep stripes", n_it=8, stripes=stripes)
