@@ -373,8 +373,11 @@ TC_DEFAULT_CAP = 16384      # candidate slots per query and launch, split evenly
 TC_MIN_SEG = 64
 TC_MAX_K = 4096
 TC_PILOT_MIN_ROWS = 8_000_000     # databases at least this long get a pilot launch over their first rows
-TC_PILOT_FRACTIONS = (64,)        # ... the first 1/64 of the rows (measured optimum; a second stage at 1/8 gains nothing:
-                                  # the main launch tightens by itself), each stage followed by a refinement
+TC_PILOT_FRACTIONS = (64,)        # ... the first 1/64 of the rows, followed by a refinement of the thresholds (measured
+                                  # optimum; a further stage at 1/8 gains nothing: the main launches tighten by themselves)
+TC_PILOT_EARLY = 512              # shards of at least TC_PILOT_EARLY_MIN_ROWS refine once more, after 1/512 of their rows:
+TC_PILOT_EARLY_MIN_ROWS = 64_000_000   # the sample's thresholds are loose (K f < 1 sample rows at the K-th distance) and
+                                  # the 1/64 pilot at those costs 1.8 ms per 8192 queries on 100M rows; two stages 1.2 ms
 TC_PILOT_SIGMA = 5.0
 TC_PREFIX_MIN_ROWS = 4_000_000    # shards at least this long apply the prefix rule ...
 TC_PREFIX_FRACTIONS = (0.3, 0.5, 0.7, 0.85)   # ... after these fractions of their rows (swept: 43.1 ms against 50.5 without)
@@ -415,18 +418,22 @@ class TcBuffers:
 
 
 def tc_pilot_rows(nd: int) -> int:
-    """Rows of the first pilot launch (0 = none): a multiple of the 256-row tile."""
+    """Rows scanned by the pilot launches (0 = none): a multiple of the 256-row tile."""
     if nd < TC_PILOT_MIN_ROWS:
         return 0
-    return (nd // TC_PILOT_FRACTIONS[0]) // 256 * 256
+    return (nd // TC_PILOT_FRACTIONS[-1]) // 256 * 256
 
 
-def tc_pilot_stages(nd: int, nd_total: int) -> list:
+def tc_pilot_stages(nd: int, nd_total: int, world: int = 1) -> list:
     """Cumulative row counts (multiples of the 256-row tile, ascending, < nd) after which the thresholds are refined.
-    The NUMBER of stages depends on the whole database only - every shard takes part in every refinement."""
+    The NUMBER of stages depends on the whole database and the number of shards only - every shard takes part in
+    every refinement."""
     if nd_total < TC_PILOT_MIN_ROWS:
         return []
-    return [(nd // f) // 256 * 256 for f in TC_PILOT_FRACTIONS]
+    fractions = TC_PILOT_FRACTIONS
+    if nd_total // max(1, int(world)) >= TC_PILOT_EARLY_MIN_ROWS:
+        fractions = (TC_PILOT_EARLY,) + tuple(fractions)
+    return [(nd // f) // 256 * 256 for f in fractions]
 
 
 class LocalComm:
@@ -503,7 +510,7 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     smp = d if sample is None else sample
     # refinement stages: cumulative local row counts; the same number of stages on every shard
     if pilot is None:
-        stages = tc_pilot_stages(d.n, nd_total)
+        stages = tc_pilot_stages(d.n, nd_total, comm.world)
     else:
         stages = [int(x) for x in (pilot if isinstance(pilot, (list, tuple)) else [pilot]) if int(x) > 0]
     if sample is None and comm.world == 1:

@@ -1,11 +1,11 @@
 #!/bin/bash
 # Run on the GPU box (via gpurun): launch list + full ncu captures of kernels of the bench step.
 # Usage: scripts/gpu_profile.sh <tag> [kernel-regex:skip ...]
-#   tc_collect_kernel is launched 6 times per step (pilot + 5 spans); after 3 warm-up steps, skip 19 = the first main span
+#   tc_collect_kernel is launched 7 times per step (2 pilot stages + 5 spans); after 3 warm-up steps, skip 23 = the first main span
 #   of the timed step, skip 3 = the 4th topk_finalize_kernel (the timed step's)
 set -u
 TAG=${1:-r01}; shift
-PAIRS=${@:-tc_collect_kernel:19 topk_finalize_kernel:3}
+PAIRS=${@:-tc_collect_kernel:23 topk_finalize_kernel:3}
 CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-also"
 OUT=gpurun_out
 $CMD > $OUT/${TAG}_plain.log 2>&1 || { echo "plain run failed"; tail -20 $OUT/${TAG}_plain.log; exit 1; }
