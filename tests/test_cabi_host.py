@@ -108,3 +108,19 @@ def test_pack_cache_is_keyed_on_live_tensor_objects():
     assert c.get(u, "codes", dev) is None       # a different object never hits, whatever its address
     del t
     assert len(c._entries) == 0                 # entry dies with the tensor
+
+
+def test_pilot_stages_depend_on_global_sizes_only():
+    """Every shard takes part in every threshold refinement: the NUMBER of pilot stages may depend on the database
+    and the number of shards, never on a shard's own length."""
+    from cmh_b200 import engine
+    assert engine.tc_pilot_stages(1_000_000, 1_000_000) == []                     # small database: no pilot
+    one = engine.tc_pilot_stages(100_000_000, 100_000_000, 1)
+    assert one == [100_000_000 // 512 // 256 * 256, 100_000_000 // 64 // 256 * 256]
+    assert engine.tc_pilot_rows(100_000_000) == one[-1]
+    for world in (2, 4, 8):                                                       # shards below 64M rows: one stage
+        lens = {len(engine.tc_pilot_stages(n, 100_000_000, world)) for n in (0, 5, 12_500_000, 50_000_000)}
+        assert lens == {1}
+    lens = {len(engine.tc_pilot_stages(n, 1_000_000_000, 8)) for n in (0, 1000, 125_000_000)}
+    assert lens == {2}
+    assert all(s % 256 == 0 for s in engine.tc_pilot_stages(123_456_789, 1_000_000_000, 8))
