@@ -167,3 +167,100 @@ def test_lockstep_stripes_cover_rows_in_order(n, world):
                [(r, r + hi - lo, lo) for (lo, hi), (r, _) in zip(ranges, stripes) if hi > lo]
     with pytest.raises(ValueError):
         engine.check_stripes([(1, 0)], 10)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the prefix rule across shards: a numpy restatement of what `engine.topk_tc` does between its launches (candidate
+# histograms of the rows scanned so far -> exchange -> `tc_choose_kernel`), driven through the real `GroupComm`
+# over gloo.  The property under test is the rule's exactness - no row of the true stable top-K is ever excluded,
+# ties included - for contiguous shards (all-gather: lower ranks + own prefix at b - 1, everything seen at b) and for
+# lockstep stripes (all-reduce, b - 1 on every shard).
+# ---------------------------------------------------------------------------------------------------------------
+def _choose(hist, need, offset, thr_in):
+    """`tc_choose_kernel` (csrc/tc_collect.cu): smallest bucket whose cumulative count reaches `need`, + offset,
+    never above thr_in; only buckets <= thr_in are looked at."""
+    out = thr_in.copy()
+    for q in range(hist.shape[0]):
+        cum = 0
+        for b in range(0, min(int(thr_in[q]), hist.shape[1] - 1) + 1):
+            cum += int(hist[q, b])
+            if cum >= need:
+                out[q] = min(int(thr_in[q]), b + offset)
+                break
+    return out
+
+
+def _prefix_worker(rank, world, port, layout, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cmh_b200 import sharded
+        rng = np.random.default_rng(5)
+        D, Q, K, bits = 24_000, 24, 40, 16                     # 16-bit codes: every bucket is full of ties
+        db = rng.integers(0, 2, (D, bits), dtype=np.int8)
+        qs = rng.integers(0, 2, (Q, bits), dtype=np.int8)
+        dist_all = (qs[:, None, :] != db[None, :, :]).sum(2).astype(np.int64)          # [Q, D]
+        kth = np.sort(dist_all, axis=1, kind="stable")[:, K - 1]
+        thr_stat = (kth + 2).astype(np.int64)                   # a loose statistical bound, the same on every shard
+        comm = sharded.GroupComm(None)
+        fractions = (0.25, 0.6)
+        if layout == "lockstep":
+            ranges, _ = sharded.lockstep_stripes(D, world, rank, fractions, align=8)
+        else:
+            lo, hi = sharded.shard_bounds(D, world, rank)
+            cuts = [lo] + [lo + int((hi - lo) * f) for f in fractions] + [hi]
+            ranges = list(zip(cuts, cuts[1:]))
+        nb = bits + 1
+        thr = thr_stat.copy()
+        cand = [[] for _ in range(Q)]                            # (dist, global row) of the rows kept so far
+        for j, (a, b) in enumerate(ranges):
+            for q in range(Q):
+                rows = np.nonzero(dist_all[q, a:b] <= thr[q])[0] + a
+                cand[q] += [(int(dist_all[q, r]), int(r)) for r in rows]
+            if j + 1 == len(ranges):
+                break
+            hist = np.zeros((Q, nb), dtype=np.int64)
+            for q in range(Q):
+                for dd, _ in cand[q]:
+                    hist[q, dd] += 1
+            h = torch.from_numpy(hist)
+            if layout == "lockstep":
+                thr = _choose(comm.all_reduce_sum(h).numpy(), K, -1, thr)
+            else:
+                every = comm.all_gather_stack(h).numpy()
+                thr = _choose(every[:rank + 1].sum(0), K, -1, thr)
+                thr = _choose(every.sum(0), K, 0, thr)
+        # what the shards kept, merged: must contain the exact stable top-K
+        keys = np.full((Q, K), -1, dtype=np.int64)
+        for q in range(Q):
+            ks = sorted((dd << 33) | r for dd, r in cand[q])[:K]
+            keys[q, :len(ks)] = ks
+        merged = comm.all_gather_stack(torch.from_numpy(keys)).numpy()                 # [world, Q, K]
+        np.savez(os.path.join(out_dir, f"p{rank}.npz"), merged=merged, thr=thr, thr_stat=thr_stat, dist_all=dist_all)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,layout", [(2, "contiguous"), (3, "contiguous"), (2, "lockstep"), (3, "lockstep")])
+def test_prefix_rule_across_shards_is_exact(tmp_path, world, layout):
+    port = _free_port()
+    mp.spawn(_prefix_worker, args=(world, port, layout, str(tmp_path)), nprocs=world, join=True)
+    z = [np.load(os.path.join(str(tmp_path), f"p{r}.npz")) for r in range(world)]
+    dist_all = z[0]["dist_all"]
+    Q, D = dist_all.shape
+    K = z[0]["merged"].shape[2]
+    order = np.argsort(dist_all, axis=1, kind="stable")[:, :K]
+    want = (np.take_along_axis(dist_all, order, 1) << 33) | order
+    for r in range(world):
+        lists = z[r]["merged"]
+        got = np.sort(np.where(lists < 0, np.iinfo(np.int64).max, lists).transpose(1, 0, 2).reshape(Q, -1), axis=1)[:, :K]
+        assert np.array_equal(got, want)                                               # nothing of the top K was excluded
+        assert np.all(z[r]["thr"] <= z[r]["thr_stat"])
+    tightened = [bool(np.any(z[r]["thr"] < z[r]["thr_stat"])) for r in range(world)]
+    assert any(tightened)
+    if layout == "lockstep":                                                           # every shard, and all alike
+        assert all(tightened) and all(np.array_equal(z[r]["thr"], z[0]["thr"]) for r in range(world))
