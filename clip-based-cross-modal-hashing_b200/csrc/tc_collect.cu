@@ -68,6 +68,16 @@ constexpr int TC_THREADS = (TC_MMA_WARPS + TC_PROD_WARPS + TC_EPI_WARPS) * 32;
 constexpr int TC_REGS_MMA = 32, TC_REGS_PROD = 32, TC_REGS_EPI = 104;
 static_assert(TC_REGS_MMA * TC_MMA_WARPS * 32 + TC_REGS_PROD * TC_PROD_WARPS * 32 + TC_REGS_EPI * TC_EPI_WARPS * 32 <=
               80 * TC_THREADS, "register budget");
+// Experimental variant (template flag WK, CMH_TC_WORKERS=1): four more warps, one HIT WORKER per epilogue group, take
+// the parked slices off the draining warps' queues.  896 threads are launched with 72 registers; issuers 32, producers
+// 32, epilogue 96, workers 56:  32 * 256 + 96 * 512 + 56 * 128 = 72 * 896.
+constexpr int TC_WORK_WARPS = 4;
+constexpr int TC_THREADS_WK = TC_THREADS + TC_WORK_WARPS * 32;
+constexpr int TC_REGS_EPI_WK = 96, TC_REGS_WORK = 56;
+static_assert(TC_REGS_MMA * TC_MMA_WARPS * 32 + TC_REGS_PROD * TC_PROD_WARPS * 32 + TC_REGS_EPI_WK * TC_EPI_WARPS * 32 +
+              TC_REGS_WORK * TC_WORK_WARPS * 32 <= 72 * TC_THREADS_WK, "register budget (worker variant)");
+constexpr int TC_WK_WORDS = 3 * TC_BUFS * TC_M + 3 * TC_EPI_WARPS;   // per-query position / threshold / initial threshold
+                                                                     // of every group; tail, head, done of every queue
 constexpr int TC_RING = 8;        // packed database tiles in flight (bulk copies)
 constexpr int TC_MAX_CHUNKS = 1024;  // candidate segments per query (cmh_topk_finalize walks them)
 constexpr int TC_REFRESH = 16;    // tiles (per epilogue group) between threshold refreshes
@@ -210,8 +220,9 @@ struct TcArgs {
 };
 
 // smem: [A: T tiles x {+-1, +-S, bias digits}][B: STAGES tiles][bias weights][packed ring][barriers][tmem slot][park]
-template <int WORDS, int T, int TC_STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs a) {
+template <int WORDS, int T, int TC_STAGES, bool WK = false>
+__global__ void __launch_bounds__(WK ? TC_THREADS_WK : TC_THREADS, 1) tc_collect_kernel(const TcArgs a) {
+    constexpr int NTHREADS = WK ? TC_THREADS_WK : TC_THREADS;
     constexpr int KBYTES = WORDS * 64;           // int8 elements (= bytes) per row
     constexpr int KSTEPS = KBYTES / 32;          // tcgen05.mma kind::i8 has K = 32
     constexpr int CHUNKS = KBYTES / 16;          // 16-byte K chunks per row
@@ -240,6 +251,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
     uint64_t* r_empty = bars + 2 * TC_STAGES + 2 * TC_BUFS + TC_RING;    // [RING] producers -> bulk copy issuer
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2 * TC_BUFS + 2 * TC_RING);
     uint32_t* scratch = tmem_slot + 4;           // [EPI_WARPS][TC_BACKLOG][TC_PARK_WORDS] parked slices of the hit path
+    // worker variant: [BUFS][128] positions, [BUFS][128] thresholds, [BUFS][128] initial thresholds, then per queue
+    // (= epilogue warp) tail (written by its producer), head (by the worker), done
+    uint32_t* wk_pos = scratch + TC_EPI_WARPS * TC_BACKLOG * TC_PARK_WORDS;
+    int* wk_thr = reinterpret_cast<int*>(wk_pos + TC_BUFS * TC_M);
+    int* wk_thr0 = wk_thr + TC_BUFS * TC_M;
+    volatile uint32_t* wk_tail = reinterpret_cast<volatile uint32_t*>(wk_thr0 + TC_BUFS * TC_M);
+    volatile uint32_t* wk_head = wk_tail + TC_EPI_WARPS;
+    volatile uint32_t* wk_done = wk_head + TC_EPI_WARPS;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t q0 = (int64_t)blockIdx.x * (T * TC_M);
@@ -266,10 +285,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
             mbar_init(&r_empty[r], TC_PROD_WARPS * 32);
         }
         mbar_fence_init();
+        if (WK)
+            for (int i = 0; i < 3 * TC_EPI_WARPS; ++i) wk_tail[i] = 0u;
     }
     // A operand: T x 128 query rows at both scales, expanded by everyone (rows beyond nq are all -1 / -S; their
     // threshold never fires)
-    for (int i = tid; i < T * TC_M * CHUNKS; i += TC_THREADS) {
+    for (int i = tid; i < T * TC_M * CHUNKS; i += NTHREADS) {
         const int c = i % CHUNKS;                // 16-byte chunk of the row
         const int r = (i / CHUNKS) % TC_M;
         const int t = i / (CHUNKS * TC_M);
@@ -281,7 +302,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
         *reinterpret_cast<uint4*>(dst + A_TILE) = expand16<SCALE>(b16);
     }
     // bias K-step: digits of  bias_q = B - (B + 1) * T_q  against the weights (127 x TC_BIAS_SLOTS, 1, 0 ...)
-    for (int i = tid; i < T * TC_M; i += TC_THREADS) {
+    for (int i = tid; i < T * TC_M; i += NTHREADS) {
         const int r = i % TC_M, t = i / TC_M;
         const int64_t q = q0 + i;
         // padding queries (all -1) get the tightest valid threshold; whatever they flag is dropped by the hit path
@@ -300,7 +321,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
         *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
         *reinterpret_cast<uint4*>(dst + TC_M * 16) = make_uint4(w[4], w[5], w[6], w[7]);
     }
-    for (int i = tid; i < TC_NM * 2; i += TC_THREADS) {          // weights: row i % 128, 16-byte chunk i / 128
+    for (int i = tid; i < TC_NM * 2; i += NTHREADS) {          // weights: row i % 128, 16-byte chunk i / 128
         uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int k = 0; k < TC_BIAS_SLOTS; ++k) w[k >> 2] |= 127u << (8 * (k & 3));
         w[TC_BIAS_SLOTS >> 2] |= 1u << (8 * (TC_BIAS_SLOTS & 3));
@@ -430,9 +451,116 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
             mbar_arrive(&b_full[s]);
             if (pt == 0) TC_TRACE(1, i, 6);
         }
+    } else if (WK && warp >= TC_MMA_WARPS + TC_PROD_WARPS + TC_EPI_WARPS) {
+        // ================= hit workers (experimental variant): one warp per epilogue group =================
+        // The draining warps of group g only park flagged slices; this warp takes them off their four queues and owns
+        // the group's per-query state (position in the candidate segment, current threshold) in shared memory - nobody
+        // else touches it, so there are no atomics, and nothing the draining warps do depends on how long this takes.
+        reg_dec<TC_REGS_WORK>();
+        const int g = warp - (TC_MMA_WARPS + TC_PROD_WARPS + TC_EPI_WARPS);
+        const int t = g % T;
+        const int seg_id = a.seg_base + blockIdx.y * (TC_BUFS / T) + g / T;
+        const bool hq_on = a.K > 0, drop = (a.probe & 16) != 0, store = !(a.probe & 8);
+        const uint32_t row_base = (uint32_t)a.index_base + (uint32_t)c_begin;
+        const uint32_t chunk_len = (uint32_t)(c_end - c_begin);
+        uint32_t* pos_s = wk_pos + g * TC_M;
+        int* thr_s = wk_thr + g * TC_M;
+        int* thr0_s = wk_thr0 + g * TC_M;
+        for (int i = lane; i < TC_M; i += 32) {
+            const int64_t q = q0 + t * TC_M + i;
+            const int t0 = q < a.nq ? min(a.thr[q], thr_max) : -1;
+            pos_s[i] = 0u;
+            thr_s[i] = t0;
+            thr0_s[i] = t0;
+        }
+        __syncwarp();
+        uint32_t heads[4] = {0u, 0u, 0u, 0u};             // warp-uniform
+        for (;;) {
+            bool progressed = false;
+            int n_done = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                 // queue k = the group's warp that drains TMEM lanes 32k..32k+31
+                const int ew = g * 4 + k;
+                uint32_t dn = 0u, tail = 0u;
+                if (lane == 0) {
+                    dn = wk_done[ew];                     // done first: a tail read after it is final
+                    __threadfence_block();
+                    tail = wk_tail[ew];
+                }
+                dn = __shfl_sync(0xffffffffu, dn, 0);
+                tail = __shfl_sync(0xffffffffu, tail, 0);
+                __threadfence_block();                    // the entries below the tail are visible
+                while (heads[k] != tail) {
+                    const uint32_t* mine = scratch + (ew * TC_BACKLOG + (heads[k] & (TC_BACKLOG - 1))) * TC_PARK_WORDS;
+                    const uint32_t xr = mine[lane];       // lane r looks at register r of the slice
+                    const uint2 hdr = *reinterpret_cast<const uint2*>(mine + 32);   // owner lane, first row (rel.)
+                    const int qrow_o = k * 32 + (int)hdr.x;
+                    const int thr_o = thr_s[qrow_o], thr0_o = thr0_s[qrow_o];
+                    const uint32_t pos_in = pos_s[qrow_o];
+                    uint32_t pos_o = pos_in;
+                    const int64_t q_o = q0 + t * TC_M + qrow_o;
+                    const int dot_thr0_o = a.bits - 2 * max(0, thr0_o);
+                    uint32_t fl = (q_o < a.nq && !drop) ? (~xr & FLAGS) : 0u;
+                    uint64_t* const seg_o = a.cand + ((uint64_t)(q_o < a.nq ? q_o : 0) * a.n_segs + seg_id) * (uint64_t)a.seg_cap;
+                    uint32_t* const hq_o = a.aux[q_o < a.nq ? q_o : 0].h;
+                    do {                                  // one trip unless a register holds two flagged rows
+                        bool pass = false;
+                        int dist = 0;
+                        uint32_t rel = 0;
+                        if (fl) {
+                            const int bit = 31 - __clz(fl);
+                            fl &= ~(1u << bit);
+                            const int col = PACKED ? 2 * lane + (bit >> 4) : lane;
+                            const int f = PACKED ? ((bit >> 3) & 1) : (bit >= FIELD ? 1 : 0);
+                            const int val = PACKED ? ((bit >> 4) ? (int)xr >> 16 : (int)(xr << 16) >> 16) : (int)xr;
+                            const int e1 = (int)((uint32_t)val << (32 - FIELD)) >> (32 - FIELD);
+                            const int dot = f ? ((val - e1) >> FIELD) + dot_thr0_o - 1 : e1 + dot_thr0_o;
+                            dist = (a.bits - dot) >> 1;
+                            rel = hdr.y + (uint32_t)(col + f * TC_NM);
+                            pass = dist <= thr_o && rel < chunk_len;
+                        }
+                        const uint32_t m = __ballot_sync(0xffffffffu, pass);
+                        if (pass && store) {
+                            const uint32_t p = pos_o + __popc(m & lanemask_lt());
+                            if (p < (uint32_t)a.seg_cap) seg_o[p] = ((uint64_t)(uint32_t)(2 * dist) << 32) | (row_base + rel);
+                            if (hq_on) atomicAdd(hq_o + min(thr0_o - dist, 3), 1u);
+                        }
+                        pos_o += __popc(m);
+                    } while (__any_sync(0xffffffffu, fl != 0u));
+                    if (lane == 0) {
+                        pos_s[qrow_o] = pos_o;
+                        if (hq_on && ((pos_in ^ pos_o) >> 4)) {
+                            // tighten (every 16 candidates of a query): once K rows at dist <= thr0 - j are known,
+                            // nothing beyond that bucket can be in the top K
+                            const uint4 c4 = __ldcg(reinterpret_cast<const uint4*>(hq_o));
+                            const uint32_t K = (uint32_t)a.K;
+                            const uint32_t c3 = c4.w, c2 = c3 + c4.z, c1 = c2 + c4.y;
+                            thr_s[qrow_o] = thr0_o - (c3 >= K ? 3 : (c2 >= K ? 2 : (c1 >= K ? 1 : 0)));
+                        }
+                    }
+                    __syncwarp();                         // everyone has read the entry; the state is written
+                    ++heads[k];
+                    if (lane == 0) {
+                        __threadfence_block();
+                        wk_head[ew] = heads[k];           // the producer may reuse the entry
+                    }
+                    progressed = true;
+                }
+                n_done += dn ? 1 : 0;
+            }
+            if (n_done == 4) break;                       // all four producers had finished before their tails were read
+            if (!progressed) __nanosleep(200);
+        }
+        for (int i = lane; i < TC_M; i += 32) {
+            const int64_t q = q0 + t * TC_M + i;
+            if (q < a.nq) {
+                a.cnt[(int64_t)seg_id * a.nq + q] = pos_s[i];
+                if (pos_s[i] > (uint32_t)a.seg_cap) a.aux[q].force_fail = 1u;
+            }
+        }
     } else {
         // ================= epilogue: flag filter on the packed dot products =================
-        reg_inc<TC_REGS_EPI>();
+        reg_inc<(WK ? TC_REGS_EPI_WK : TC_REGS_EPI)>();
         const int ew = warp - (TC_MMA_WARPS + TC_PROD_WARPS);   // 0 .. 15
         const int grp = ew >> 2;                          // accumulator buffer this warp drains
         const int quarter = warp & 3;                     // TMEM lanes this warp may touch: 32 * (warp % 4)
@@ -536,6 +664,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
                 pend = rest;
             }
         };
+        // worker variant: the queue is drained by the group's hit worker; this warp only appends (and waits when it is full)
+        uint32_t tail_l = 0u, head_seen = 0u;            // warp-uniform
+        auto park_slice_wk = [&](const uint32_t (&v)[32], bool flagged, int64_t row0) {
+            uint32_t pend = __ballot_sync(0xffffffffu, flagged);
+            if (a.probe & 32) pend = 0;
+            while (pend) {                               // warp-uniform
+                while (tail_l - head_seen >= (uint32_t)TC_BACKLOG) {
+                    uint32_t h = 0u;
+                    if (lane == 0) h = wk_head[ew];
+                    head_seen = __shfl_sync(0xffffffffu, h, 0);
+                    if (tail_l - head_seen >= (uint32_t)TC_BACKLOG) __nanosleep(64);
+                }
+                const int room = TC_BACKLOG - (int)(tail_l - head_seen);
+                uint32_t rest = pend;
+#pragma unroll
+                for (int k = 0; k < TC_PARK; ++k)
+                    if (k < room) rest &= rest - 1;
+                const uint32_t take = pend & ~rest;
+                if ((take >> lane) & 1u) {
+                    uint32_t* mine = park + ((tail_l + __popc(take & lanemask_lt())) & (TC_BACKLOG - 1)) * TC_PARK_WORDS;
+#pragma unroll
+                    for (int r = 0; r < 32; r += 4)
+                        *reinterpret_cast<uint4*>(mine + r) = make_uint4(v[r], v[r + 1], v[r + 2], v[r + 3]);
+                    *reinterpret_cast<uint2*>(mine + 32) = make_uint2((uint32_t)lane, (uint32_t)(row0 - c_begin));
+                }
+                __syncwarp();
+                tail_l += (uint32_t)__popc(take);
+                if (lane == 0) {
+                    __threadfence_block();               // the entries before the tail
+                    wk_tail[ew] = tail_l;
+                }
+                pend = rest;
+            }
+        };
         // one slice (32 registers: 64 or 128 rows): AND-reduce, one mask test, one vote; the hit path is rare
         // two slices (32 registers each: 64 or 128 rows): AND-reduce, one mask test per slice, ONE vote for both; the
         // hit path is rare
@@ -558,9 +720,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
             const bool f0 = ((ab0[0] & ab0[1] & ab0[2] & ab0[3]) & FLAGS) != FLAGS;
             const bool f1 = ((ab1[0] & ab1[1] & ab1[2] & ab1[3]) & FLAGS) != FLAGS;
             if (__any_sync(0xffffffffu, f0 || f1)) {
-                park_slice(v0, f0, r0);
-                park_slice(v1, f1, r1);
-                parked_now = true;
+                if (WK) {
+                    park_slice_wk(v0, f0, r0);
+                    park_slice_wk(v1, f1, r1);
+                } else {
+                    park_slice(v0, f0, r0);
+                    park_slice(v1, f1, r1);
+                    parked_now = true;
+                }
             }
         };
         auto release = [&]() {                   // the values are in registers: the buffer goes back to its issuer
@@ -578,7 +745,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
             // that is late for its tile holds the whole group's buffer back (the tensor pipe has no slack to catch up).
             const bool busy_round = parked_now && !(a.probe & 64);
             parked_now = false;
-            if (!busy_round)
+            if (!WK && !busy_round)
                 while (n_parked > 0 && !__any_sync(0xffffffffu, mbar_test(&t_full[grp], round & 1))) work_off();
             mbar_wait(&t_full[grp], round & 1);
             tc_fence_after();
@@ -608,7 +775,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
                 release();
                 scan2(va, row0 + 64, vb, row0 + 96);
             }
-            if (hq != nullptr && (round & (TC_REFRESH - 1)) == TC_REFRESH - 1) {
+            if (!WK && hq != nullptr && (round & (TC_REFRESH - 1)) == TC_REFRESH - 1) {
                 // tighten: once K rows at dist <= thr0 - j are known, nothing beyond that bucket can be in the top K.
                 // Here, after the buffer went back, the L2 round trip of the counters costs the pipeline nothing.
                 const uint4 c4 = __ldcg(reinterpret_cast<const uint4*>(hq));
@@ -619,10 +786,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_collect_kernel(const TcArgs 
             }
             if (qrow == 0) TC_TRACE(2 + grp, round, 4);
         }
-        while (n_parked > 0) work_off();
-        if (live) {
-            a.cnt[(int64_t)seg_id * a.nq + q] = pos;
-            if (pos > (uint32_t)a.seg_cap) a.aux[q].force_fail = 1u;
+        if (WK) {
+            __syncwarp();
+            if (lane == 0) {                             // this queue gets no more entries (the tail is final)
+                __threadfence_block();
+                wk_done[ew] = 1u;
+            }
+        } else {
+            while (n_parked > 0) work_off();
+            if (live) {
+                a.cnt[(int64_t)seg_id * a.nq + q] = pos;
+                if (pos > (uint32_t)a.seg_cap) a.aux[q].force_fail = 1u;
+            }
         }
     }
     // ---- teardown -----------------------------------------------------------------------------------------------
@@ -927,6 +1102,10 @@ using namespace cmh;
 // so exactly one CTA - which owns the whole TMEM - is resident per SM.
 static int tc_T(int words) { return words == 1 ? 4 : 2; }
 static int tc_stages(int words) { return words == 1 ? 6 : 3; }
+static bool tc_workers() {       // experimental hit-worker variant of the kernel (CMH_TC_WORKERS=1); off by default
+    static const bool on = [] { const char* e = getenv("CMH_TC_WORKERS"); return e && e[0] == '1'; }();
+    return on;
+}
 static size_t tc_smem_bytes(int words) {
     const int st = tc_stages(words), T = tc_T(words);
     return (size_t)T * (2 * TC_M * words * 64 + TC_M * 32) + (size_t)st * TC_N * words * 64 + TC_NM * 32 +
@@ -994,9 +1173,15 @@ static int tc_collect_impl(const uint64_t* q_sign, int64_t nq, const uint64_t* d
     a.q = q_sign; a.d = d_sign; a.thr = thr; a.cand = cand; a.cnt = cnt; a.aux = reinterpret_cast<TcAux*>(aux);
     a.nq = nq; a.nd = nd; a.index_base = index_base; a.chunk_rows = (int)chunk_rows; a.n_segs = seg_total;
     a.seg_base = seg_base; a.seg_cap = seg_cap; a.bits = bits; a.K = K; a.probe = probe; a.trace = g_tc_trace;
-    const size_t smem = tc_smem_bytes(words);
+    const size_t smem = tc_smem_bytes(words) + (tc_workers() ? (size_t)TC_WK_WORDS * 4 : 0);
     const dim3 grid((unsigned)n_qgroups, (unsigned)n_chunks);
-    if (words == 1) {
+    if (tc_workers() && words == 1) {
+        CMH_CUDA(cudaFuncSetAttribute(tc_collect_kernel<1, 4, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_collect_kernel<1, 4, 6, true><<<grid, TC_THREADS_WK, smem, st>>>(a);
+    } else if (tc_workers()) {
+        CMH_CUDA(cudaFuncSetAttribute(tc_collect_kernel<2, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_collect_kernel<2, 2, 3, true><<<grid, TC_THREADS_WK, smem, st>>>(a);
+    } else if (words == 1) {
         CMH_CUDA(cudaFuncSetAttribute(tc_collect_kernel<1, 4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_collect_kernel<1, 4, 6><<<grid, TC_THREADS, smem, st>>>(a);
     } else {
