@@ -29,12 +29,16 @@
 //                 (no-swizzle K-major UMMA layout) into a STAGES-deep ring of B tiles
 //   warps 8-23    epilogue: 4 groups of 4 warps, group g drains accumulator buffer g; thread = one query (a TMEM
 //                 lane) for the whole CTA, so its threshold, candidate count and segment pointer live in registers;
-//                 slices with a flagged row are parked in shared memory and worked off while the warp waits
+//                 slices with a flagged row are parked in a per-warp shared-memory queue and worked off - by the whole
+//                 warp, one entry at a time - while the warp waits for its next tile
+//   warps 24-27   (experimental variant WK only) hit workers: take the parked slices off the queues instead
 // TMEM: 4 accumulator buffers x 128 columns (the whole 512-column TMEM, one CTA per SM).
 //
 // Exactness: thresholds only have to be upper bounds of the K-th distance (cmh_topk_threshold derives them from a
-// sample histogram, cmh_tc_cand_hist + cmh_tc_choose refine them from a pilot launch); cmh_topk_finalize sorts the candidates by key - (distance, index), all keys distinct - which IS
-// the stable ranking, and flags any query whose candidate list is short or overflowed for the exact two-pass path.
+// sample histogram, cmh_tc_cand_hist + cmh_tc_choose refine them from the pilot launches, cmh_tc_choose_prefix /
+// cmh_tc_choose_seen tighten them - exactly - from the candidates of the rows already scanned); cmh_topk_finalize
+// orders the candidates by key - (distance, index), all keys distinct - which IS the stable ranking, and flags any
+// query whose candidate list is short or overflowed for the exact two-pass path.
 #include <algorithm>
 
 #include "common.cuh"
