@@ -274,7 +274,7 @@ def main_native(args):
     # One query chunk at a time.  `search_packed_async` (two chunks in flight on alternating streams) is available, but
     # with one long-lived 768-thread CTA per SM the small kernels and the NCCL kernels between the launches of one chunk
     # only get SM slots at CTA boundaries of the other chunk's scan: measured -25 % at 2 GPUs, and a loss on a single GPU
-    # too once the search became a chain of six launches with refinement kernels in between.
+    # too once the search became a chain of six to seven launches with refinement kernels in between.
     pipelined = False
 
     def run_steps(n, stats):
