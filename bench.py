@@ -58,8 +58,9 @@ def parse_args():
 def config_dict(args, world):
     return {"workload": "c4: 64-bit exact stable top-1000 Hamming retrieval, 100M-row database, one query chunk per step",
             "bits": BITS, "topk": TOPK, "db_rows": args.db_rows, "queries_per_step": args.queries,
+            "queries": "a different chunk of the config's 1M queries every step (chunk i = query rows i*Q..(i+1)*Q)",
             "pipelining": "none: one query chunk at a time, resolved and verified before the next is enqueued",
-            "sharding": f"database rows over {world} GPUs in lockstep stripes (3 global stripes x {world} contiguous pieces, rank r holds piece r of each); queries replicated; all-reduced threshold / prefix-rule histograms, NCCL all-to-all by query slice + merge + all-gather"
+            "sharding": f"database rows over {world} GPUs in lockstep stripes (3 global stripes x {world} contiguous pieces, rank r holds piece r of each); queries replicated; all-reduced threshold / prefix-rule histograms, NCCL all-to-all by query slice + merge + verify; results stay sharded by query slice (rank r keeps slice r)"
                         if world > 1 else "single GPU holds the whole database",
             "l2": "per-step working set (packed shard + candidate segments, >1 GB) exceeds the 126 MB L2; no explicit flush",
             "seed": SEED}
@@ -203,10 +204,16 @@ def main_reference(args):
         return
     nq, nd = 8, 2_000_000
     value, dt = run_reference_sample(nq, nd, args.steps, max(1, args.warmup))
+    cfg = config_dict(args, 1)
+    cfg.update({"queries_timed_per_step": nq, "db_rows_timed": nd,
+                "extrapolation": "the CPU arm ranks a bounded sample of the workload (8 queries x 2M rows per step); its "
+                                 "compares/s is per pair - a full sort is O(D log D), so the per-pair cost at 100M rows is "
+                                 "higher than what is measured here (the reported value flatters the CPU)",
+                "sort": "stable (the contract); the shipped reference calls torch.sort with the default flag"})
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args, 1),
+            "config": cfg,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": f"per step {nq} queries x {nd} database rows of the same synthetic codes: float "
                                        "distance row + full stable sort per query (utils/calc_utils.py:30-31), torch CPU, "
@@ -218,6 +225,179 @@ def main_reference(args):
 # ---------------------------------------------------------------------------------------------------------------
 # native arm
 # ---------------------------------------------------------------------------------------------------------------
+def map_cpu_baseline(t, shape, n_queries):
+    """The reference's own `calc_map_k_matrix` (utils/calc_utils.py:16-39; op-for-op oracle port, torch CPU, all host
+    threads) on a query prefix: per-query cost is independent across queries, so queries/s extrapolates linearly."""
+    from oracle import cmh_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    qB, rB = torch.from_numpy(t["q_img"][:n_queries]), torch.from_numpy(t["r_txt"])
+    qL, rL = torch.from_numpy(t["q_lab"][:n_queries]), torch.from_numpy(t["r_lab"])
+    out = {}
+    for tag, stable in (("stable_sort", True), ("as_shipped_unstable_sort", False)):
+        orc.ap_per_query_sorted(qB[:2], rB, qL[:2], rL, shape.k, stable=stable)
+        t0 = time.perf_counter()
+        orc.ap_per_query_sorted(qB, rB, qL, rL, shape.k, stable=stable)
+        out[tag] = n_queries / (time.perf_counter() - t0)
+    return {"value": out["stable_sort"], "unit": "queries/s", "as_shipped_value": out["as_shipped_unstable_sort"],
+            "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"first {n_queries} of {shape.n_query} queries against all {shape.n_db} rows (same synthetic codes and "
+                      "labels), one repetition per sort flavour; per-query cost is independent across queries: linear "
+                      "extrapolation to the whole query set"}
+
+
+def bench_also(dev, local, hbm_peak, cpu=True):
+    """Single-GPU secondary legs.  The reference's own calls (calc_map_k_matrix both directions, p_topK, pr_curve) at the
+    shapes of configs 1-3 and the eval stage of config 5: device float codes + labels in, pack + two counting passes +
+    host scalar out, pack cache cleared before every call.  Each with its roofline (the XOR+POPC compare against the
+    integer-pipe peak measured live by `cmh_measure_popc_peak`) and the reference's CPU time beside it."""
+    import ctypes
+    from cmh_b200 import _cabi, calc_utils as cu, engine
+    from cmh_b200.index import HammingIndex
+    from cmh_b200.synth import CONFIGS, make_case
+    lib = _cabi.lib()
+    peak = ctypes.c_double(0.0)
+    _cabi.check(lib.cmh_measure_popc_peak(4096, 5, ctypes.byref(peak), engine._stream(dev)), "cmh_measure_popc_peak")
+    popc_peak = float(peak.value)
+
+    def per_call_ms(fn, reps=5):
+        for _ in range(2):
+            cu.clear_cache(); out = fn()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            cu.clear_cache(); out = fn()
+        torch.cuda.synchronize(dev)
+        return (time.perf_counter() - t0) / reps * 1e3, out
+
+    also = {"popc32_peak_per_s": popc_peak}
+    cpu_queries = {"c1": 48, "c2-16": 16, "c2-32": 16, "c2-64": 24, "c3": 24, "c5": 24}
+    for name in ("c1", "c2-16", "c2-32", "c2-64", "c3", "c5"):     # c5: the eval stage of config 5
+        shape = CONFIGS[name]
+        t = make_case(shape, clustered=True, zero_query_frac=0.01)
+        qi, qt, ri, rt = (torch.from_numpy(t[k]).to(dev) for k in ("q_img", "q_txt", "r_img", "r_txt"))
+        qL, rL = torch.from_numpy(t["q_lab"]).to(dev), torch.from_numpy(t["r_lab"]).to(dev)
+        ms_i2t, m_i2t = per_call_ms(lambda: cu.calc_map_k_matrix(qi, rt, qL, rL, shape.k, local))
+        ms_t2i, m_t2i = per_call_ms(lambda: cu.calc_map_k_matrix(qt, ri, qL, rL, shape.k, local))
+        pairs = shape.n_query * shape.n_db
+        popc = pairs * ((shape.bits + 31) // 32) * 2            # two counting passes recompute every distance
+        entry = {"shape": f"{shape.n_query} x {shape.n_db}, {shape.bits}-bit, {shape.n_labels} labels, "
+                          f"mAP@{'ALL' if shape.k is None else shape.k}",
+                 "map_i2t": float(m_i2t), "map_t2i": float(m_t2i), "ms_per_call_i2t": ms_i2t, "ms_per_call_t2i": ms_t2i,
+                 "map_queries_per_s": shape.n_query / (ms_i2t * 1e-3),
+                 "compares_per_s": pairs / (ms_i2t * 1e-3),
+                 "roofline": {"bound": "integer pipe (XOR+POPC)", "achieved": popc / (ms_i2t * 1e-3), "peak": popc_peak,
+                              "unit": "POPC32/s", "frac": popc / (ms_i2t * 1e-3) / popc_peak if popc_peak else None,
+                              "algorithmic": "ceil(bits/32) POPC32 per pair x 2 passes; whole call incl. pack, scan, "
+                                             "finalize and the host read of the scalar"}}
+        if shape.topn:
+            ms_p, _ = per_call_ms(lambda: cu.p_topK(qi, rt, qL, rL, list(shape.topn), local))
+            entry["p_topK_ms_per_call"] = ms_p
+        if name == "c3":
+            ms_pr, _ = per_call_ms(lambda: cu.pr_curve(qi, rt, qL, rL, local))
+            entry["pr_curve_ms_per_call"] = ms_pr
+        if cpu:
+            entry["cpu_baseline"] = map_cpu_baseline(t, shape, cpu_queries[name])
+        also[name] = entry
+        del qi, qt, ri, rt, qL, rL
+
+    # K1 at HBM scale: float32 codes [8M, 64] (2 GB) -> packed planes, float32 labels [8M, 24] -> masks
+    n_rows = 8_000_000
+    x = torch.randint(0, 2, (n_rows, 64), device=dev, dtype=torch.int8).float() * 2 - 1
+    lab = (torch.rand((n_rows, 24), device=dev) < 0.15).float()
+    cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    neg = torch.zeros(1, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    pack = {}
+    for pname, fn, rd, wr in (("pack_codes", lambda: engine.pack_codes_device(x, cnt), n_rows * 64 * 4, 2 * n_rows * 8),
+                              ("pack_labels", lambda: engine.pack_labels_device(lab, neg), n_rows * 24 * 4, n_rows * 8)):
+        ts = []
+        for _ in range(6):
+            flush.zero_()                                        # L2 flush between launches
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b))
+        ms = min(ts[2:])
+        pack[pname] = {"rows": n_rows, "ms": ms, "algorithmic_bytes": rd + wr,
+                       "roofline": {"bound": "hbm", "achieved": (rd + wr) / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                                    "frac": (rd + wr) / ms / 1e6 / hbm_peak}}
+    also["pack"] = pack
+    del x, lab, flush
+
+    # the 128-bit tensor path (config 3's code length at retrieval scale): 8192 x 50M, top-1000, device-resident
+    try:
+        D128, Q128 = 50_000_000, 8192
+        db = engine.synth_codes(SEED + 128, 0, D128, 128, dev)
+        idx = HammingIndex(db, 0, nd_total=D128, assume_binary=True)
+        qs = [engine.synth_codes(SEED + 129, i * Q128, Q128, 128, dev) for i in range(4)]
+        st = {}
+        idx.search_packed(qs[0], TOPK)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(1, 4):
+            idx.search_packed(qs[i], TOPK, stats=st)
+        b.record(); torch.cuda.synchronize(dev)
+        ms = a.elapsed_time(b) / 3
+        also["bits128"] = {"shape": f"{Q128} x {D128}, 128-bit, top-{TOPK}", "ms_per_step": ms, "n_fail": st.get("n_fail"),
+                           "compares_per_s": Q128 * D128 / (ms * 1e-3),
+                           "int8_tops": Q128 * D128 * 256 / (ms * 1e-3) / 1e12}
+        del db, idx, qs
+    except Exception as e:  # noqa: BLE001 - a secondary leg must not take the headline down
+        also["bits128"] = {"error": repr(e)}
+    return also
+
+
+def bench_sharded_map(dev, rank, world, max_over_ranks, barrier):
+    """N > 1: calc_map_k_matrix + precision@N + PR curve with the database sharded by contiguous row ranges
+    (`cmh_map_k_sharded` over the library's NCCL transport) at a scaled NUS-WIDE shape, against the same call on ONE GPU
+    (rank 0 ranks the whole database alone): per-query AP must agree within 1e-7."""
+    from cmh_b200 import engine, sharded
+    nq, nd, bits, nlab, topn = 2100, 20_000_000, 64, 21, (1, 100, 1000)
+
+    def labels(seed, row0, n):          # ~12.5 % density per label, a pure function of the global row
+        w = engine.synth_codes(seed, row0, n, 64, dev).sign
+        for j in (1, 2):
+            w = w & engine.synth_codes(seed + j, row0, n, 64, dev).sign
+        return w & ((1 << nlab) - 1)
+
+    q = engine.synth_codes(SEED + 21, 0, nq, bits, dev).with_labels(labels(SEED + 30, 0, nq), nlab)
+    lo, hi = sharded.shard_bounds(nd, world, rank)
+    shard = engine.synth_codes(SEED + 20, lo, hi - lo, bits, dev).with_labels(labels(SEED + 40, lo, hi - lo), nlab)
+    comm = sharded.GroupComm(None)
+    res = None
+    for _ in range(2):
+        res = sharded.map_k_sharded_native(q, shard, None, nd, topn, comm=comm, want_pr=True, ternary=False)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        res = sharded.map_k_sharded_native(q, shard, None, nd, topn, comm=comm, want_pr=True, ternary=False)
+    b.record()
+    barrier()
+    ms = max_over_ranks(a.elapsed_time(b) / 3)
+    out = {"shape": f"{nq} x {nd}, {bits}-bit, {nlab} labels, mAP@ALL + precision@{list(topn)} + PR curve",
+           "n_gpus": world, "ms_per_call": ms, "map_queries_per_s": nq / (ms * 1e-3), "compares_per_s": nq * nd / (ms * 1e-3),
+           "map": float(res["map"].cpu()[0])}
+    ap_all = res["ap"].clone()
+    del shard
+    if rank == 0:
+        whole = engine.synth_codes(SEED + 20, 0, nd, bits, dev).with_labels(labels(SEED + 40, 0, nd), nlab)
+        one = None
+        for _ in range(2):
+            one = sharded.map_k_sharded_native(q, whole, None, nd, topn, comm=None, want_pr=True, ternary=False)
+        a.record()
+        one = sharded.map_k_sharded_native(q, whole, None, nd, topn, comm=None, want_pr=True, ternary=False)
+        b.record(); torch.cuda.synchronize(dev)
+        ms1 = a.elapsed_time(b)
+        err = float((ap_all - one["ap"]).abs().max())
+        out.update({"one_gpu_ms_per_call": ms1, "speedup_vs_one_gpu": ms1 / ms, "max_abs_ap_diff_vs_one_gpu": err,
+                    "n_rel_equal": bool(torch.equal(res["n_rel"], one["n_rel"])),
+                    "prec_max_abs_diff": float((res["prec"] - one["prec"]).abs().max()),
+                    "pr_max_abs_diff": float(max((res["pr"][0] - one["pr"][0]).abs().max(), (res["pr"][1] - one["pr"][1]).abs().max()))})
+        assert err < 1e-7 and out["n_rel_equal"], f"sharded mAP differs from the one-GPU result: {out}"
+    barrier()
+    return out
+
+
 def main_native(args):
     import ctypes
     import torch.distributed as dist
@@ -262,44 +442,35 @@ def main_native(args):
         ranges, stripes = [(0, D)], None
         db = engine.synth_codes(SEED, 0, D, BITS, dev)
     lo, hi = ranges[0][0], ranges[0][0] + db.n          # hi - lo = rows of this shard
-    q_packed = engine.synth_codes(SEED + 1, 0, Q, BITS, dev)
-    index = HammingIndex(db, lo, nd_total=D, stripes=stripes)
+    # a DIFFERENT chunk of the config's 1M queries every step (warm-up included): chunk i = query rows i*Q .. (i+1)*Q
+    n_chunks = args.warmup + args.steps
+    chunks = [engine.synth_codes(SEED + 1, i * Q, Q, BITS, dev) for i in range(n_chunks)]
+    index = HammingIndex(db, lo, nd_total=D, stripes=stripes, assume_binary=True)
 
     # ---- device-resident timing ("value") ------------------------------------------------------------------
-    # nvidia-smi is started before the warm-up: its NVML start-up takes driver locks and must not land in the timed
+    # NVML sampling is started before the warm-up: its start-up takes driver locks and must not land in the timed
     # region; only the samples that arrive inside the region are reported
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # One query chunk at a time.  `search_packed_async` (two chunks in flight on alternating streams) is available, but
-    # with one long-lived 768-thread CTA per SM the small kernels and the NCCL kernels between the launches of one chunk
-    # only get SM slots at CTA boundaries of the other chunk's scan: measured -25 % at 2 GPUs, and a loss on a single GPU
-    # too once the search became a chain of six to seven launches with refinement kernels in between.
-    pipelined = False
 
-    def run_steps(n, stats):
-        pending, keys = None, None
-        for _ in range(n):
-            if not pipelined:
-                keys = index.search_packed(q_packed, K, stats=stats)
-                continue
-            h = index.search_packed_async(q_packed, K, stats=stats)
-            if pending is not None:
-                keys = pending.result()
-            pending = h
-        return pending.result() if pending is not None else keys
+    # One query chunk at a time, each resolved (verdict read, failed queries redone) before the next is enqueued.  With N
+    # GPUs the result stays SHARDED BY QUERY SLICE: rank r merges, verifies and keeps the keys of its slice of the chunk
+    # (`gather=False`; an all-gather of the merged keys is one flag away and is what `search_packed` does by default).
+    def run_steps(first, n, stats):
+        keys = None
+        for i in range(first, first + n):
+            keys = index.search_packed(chunks[i], K, stats=stats, gather=False)
+        return keys
 
-    # warm-up on the timed code path (kernels loaded).  Its result is not kept: a third live [Q, K] key buffer next to
-    # the two the loop alternates between sends the caching allocator to cudaMalloc in the middle of the timed region
-    # (measured: 1-70 ms in the second timed step, wherever the warm-up ended).
-    run_steps(args.warmup, {"time_collect": True, "time_phases": True})
+    run_steps(0, args.warmup, {"time_collect": True, "time_phases": True})
     barrier()
     t_region0 = time.perf_counter()
     launches0 = lib.cmh_launch_count()
     stats = {"time_collect": True, "time_phases": True}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    keys = run_steps(args.steps, stats)
+    keys = run_steps(args.warmup, args.steps, stats)
     e1.record()
     barrier()
     launches = lib.cmh_launch_count() - launches0
@@ -308,17 +479,36 @@ def main_native(args):
     clocks = sampler.stop() if rank == 0 else None
     step_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     value = Q * D / (step_ms * 1e-3)
+    n_fail_total = stats.get("n_fail", 0)
 
-    # ---- dominant kernel (tc_collect_kernel: pilot + main launch of every step), timed live by the events the
-    # search recorded around its launches on the launching stream ---------------------------------------------
-    phases = {}
-    pe = stats.get("phase_events", [])
-    for (n0, a), (n1, b) in zip(pe, pe[1:]):
-        if n1 != "start":
-            phases[n1] = phases.get(n1, 0.0) + a.elapsed_time(b) / max(1, args.steps)
-    ev = stats.get("collect_events", [])
-    collect_ms = sum(ev[i].elapsed_time(ev[i + 1]) for i in range(0, len(ev), 2)) / max(1, args.steps)
-    n_collect = len(ev) // 2 / max(1, args.steps)
+    # ---- parity of what was just timed: a subsample of the LAST timed chunk re-ranked by the exact (popc, two-pass)
+    # sharded path - every rank's slice contributes queries - must give the same keys bit for bit ------------------
+    last = chunks[n_chunks - 1]
+    per_rank = -(-Q // world)
+    n_check = 64
+    take = max(1, n_check // world)
+    rows_check = torch.cat([torch.arange(r * per_rank, min(Q, r * per_rank + take)) for r in range(world)]).to(dev)
+    sub = engine.PackedSet(last.sign.index_select(0, rows_check).contiguous(), None, None, int(rows_check.numel()), BITS)
+    exact = sharded.topk_sharded(sub, db, K, lo, None, stripes=stripes)            # identical on every rank
+    q_lo, q_n = index.query_slice(Q)
+    mine = ((rows_check >= q_lo) & (rows_check < q_lo + q_n)).nonzero().squeeze(1)
+    equal = bool(torch.equal(keys.index_select(0, rows_check[mine] - q_lo), exact.index_select(0, mine)))
+    eq_t = torch.tensor([1 if equal else 0, int(mine.numel())], dtype=torch.int64, device=dev)
+    if world > 1:
+        flag = eq_t[:1].clone(); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        cnt = eq_t[1:].clone(); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        eq_t = torch.cat([flag, cnt])
+    parity = {"queries": int(eq_t[1]), "equal": bool(int(eq_t[0])), "n_fail": int(n_fail_total),
+              "against": "exact two-pass popc path (cmh_topk per shard + all-gather + merge) on the same chunk"}
+    if not parity["equal"]:
+        raise AssertionError(f"tensor-core keys differ from the exact path on the timed chunk: {parity}")
+
+    # ---- dominant kernel (tc_collect_kernel: pilot + main launches of every step), timed live by the events the
+    # library records around its launches on the launching stream (cmh_tc_timing) ----------------------------------
+    n_timed = max(1, stats.get("timed_searches", 1))
+    phases = {k_: v / n_timed for k_, v in stats.get("phase_ms_sum", {}).items()}
+    collect_ms = stats.get("collect_ms_sum", 0.0) / n_timed
+    n_collect = stats.get("n_collect", 0)
     pairs_shard = Q * (hi - lo)
     ops_per_pair = 2 * BITS                                   # 2 * B_pad int8 ops per pair
     achieved_tops = pairs_shard * ops_per_pair / (collect_ms * 1e-3) / 1e12 if collect_ms else None
@@ -332,7 +522,7 @@ def main_native(args):
         for _ in range(3):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
-            _cabi.check(lib.cmh_tc_probe(engine._ptr(q_packed.sign), Q, engine._ptr(db.sign), hi - lo, BITS,
+            _cabi.check(lib.cmh_tc_probe(engine._ptr(last.sign), Q, engine._ptr(db.sign), hi - lo, BITS,
                                          engine._ptr(thr_never), tb.seg_total, tb.seg_cap, engine._ptr(tb.cand),
                                          engine._ptr(tb.cnt), engine._ptr(tb.aux), mode, engine._stream(dev)), "cmh_tc_probe")
             b.record(stream)
@@ -342,77 +532,57 @@ def main_native(args):
     del tb
 
     # ---- end to end through the public API with host buffers ------------------------------------------------
-    from cmh_b200.synth import splitmix_rows
-    q_host = _host_float_codes(SEED + 1, 0, Q).pin_memory()
+    # per step: this step's float32 query codes (pinned host) H2D + pack; the packed shard (pinned host) uploaded in row
+    # ranges on a copy stream and scanned range by range as it lands; search; this rank's slice of the keys D2H
+    q_hosts = [_host_float_codes(SEED + 1, i * Q, Q).pin_memory() for i in range(n_chunks)]
     db_host = torch.empty((hi - lo, 1), dtype=torch.int64).pin_memory()
     db_host.copy_(db.sign)
     db_dev = torch.empty_like(db.sign)
-    keys_host = torch.empty((Q, K), dtype=torch.int64).pin_memory()
+    keys_host = torch.empty((per_rank if world > 1 else Q, K), dtype=torch.int64).pin_memory()
 
-    def e2e_step():
-        # the queries go first (H2D copies share one engine: behind the shard they would wait for all of it); the
-        # packed shard is uploaded in row ranges on a copy stream and the search scans each range as it lands
-        qp = cu.pack_codes(q_host.to(dev, non_blocking=True), dev)
+    def e2e_step(i):
+        # the queries go first (H2D copies share one engine: behind the shard they would wait for all of it)
+        qp = cu.pack_codes(q_hosts[i].to(dev, non_blocking=True), dev)
         idx = HammingIndex.from_packed_host(db_host, BITS, lo, nd_total=D, out=db_dev, pieces=3, stripes=stripes)
-        k = idx.search_packed(qp, K)
+        k = idx.search_packed(qp, K, gather=False)
         keys_host.copy_(k, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
 
-    for _ in range(max(1, args.warmup - 1)):
-        e2e_step()
+    for i in range(max(1, args.warmup - 1)):
+        e2e_step(i)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    for i in range(args.warmup, args.warmup + args.steps):
+        e2e_step(i)
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) / args.steps * 1e3)
     assert torch.equal(keys_host, keys.cpu()), "e2e keys differ from the device-resident run"
-    h2d = q_host.numel() * 4 + db_host.numel() * 8
+    h2d = q_hosts[0].numel() * 4 + db_host.numel() * 8
     d2h = keys_host.numel() * 8
+
+    # ---- N > 1: the reference's own call, sharded: calc_map_k_matrix + precision@N + PR curve at a
+    # scaled NUS-WIDE shape through cmh_map_k_sharded over the library's NCCL transport, against the one-GPU result ----
+    sharded_map = None
+    if world > 1 and not args.no_also:
+        sharded_map = bench_sharded_map(dev, rank, world, max_over_ranks, barrier)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- secondary: the reference's own evaluation calls at the shapes of configs 1-3, single GPU -----------------
-    # calc_map_k_matrix in both directions (I->T, T->I), p_topK where the config names precision@N, pr_curve where it
-    # names the PR curve: device float codes + labels in, pack + counting passes + host scalar out, cache cleared
-    # before every call (nothing is reused between calls)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+
+    # ---- secondary legs, single GPU: the reference's own evaluation calls at the shapes of configs 1-3 (+ the eval
+    # stage of config 5), K1 at HBM scale, the 128-bit tensor path -----------------------------------------------
     also = None
     if not args.no_also:
-        from cmh_b200.synth import CONFIGS, make_case
-
-        def per_call_ms(fn, reps=5):
-            for _ in range(2):
-                cu.clear_cache(); out = fn()
-            torch.cuda.synchronize(dev)
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                cu.clear_cache(); out = fn()
-            torch.cuda.synchronize(dev)
-            return (time.perf_counter() - t0) / reps * 1e3, out
-
-        also = {}
-        for name in ("c1", "c2-16", "c2-32", "c2-64", "c3", "c5"):     # c5: the eval stage of config 5
-            shape = CONFIGS[name]
-            t = make_case(shape, clustered=True, zero_query_frac=0.01)
-            qi, qt, ri, rt = (torch.from_numpy(t[k]).to(dev) for k in ("q_img", "q_txt", "r_img", "r_txt"))
-            qL, rL = torch.from_numpy(t["q_lab"]).to(dev), torch.from_numpy(t["r_lab"]).to(dev)
-            ms_i2t, m_i2t = per_call_ms(lambda: cu.calc_map_k_matrix(qi, rt, qL, rL, shape.k, local))
-            ms_t2i, m_t2i = per_call_ms(lambda: cu.calc_map_k_matrix(qt, ri, qL, rL, shape.k, local))
-            entry = {"shape": f"{shape.n_query} x {shape.n_db}, {shape.bits}-bit, {shape.n_labels} labels, "
-                              f"mAP@{'ALL' if shape.k is None else shape.k}",
-                     "map_i2t": float(m_i2t), "map_t2i": float(m_t2i), "ms_per_call_i2t": ms_i2t, "ms_per_call_t2i": ms_t2i,
-                     "map_queries_per_s": shape.n_query / (ms_i2t * 1e-3),
-                     "compares_per_s": shape.n_query * shape.n_db / (ms_i2t * 1e-3)}
-            if shape.topn:
-                ms_p, _ = per_call_ms(lambda: cu.p_topK(qi, rt, qL, rL, list(shape.topn), local))
-                entry["p_topK_ms_per_call"] = ms_p
-            if name == "c3":
-                ms_pr, _ = per_call_ms(lambda: cu.pr_curve(qi, rt, qL, rL, local))
-                entry["pr_curve_ms_per_call"] = ms_pr
-            also[name] = entry
+        also = bench_also(dev, local, hbm_peak, cpu=not args.no_cpu_baseline and world == 1)
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -422,12 +592,6 @@ def main_native(args):
                "sample": f"{nq} queries x {nd} rows of the same synthetic codes, 2 timed repetitions: float distance row + "
                          "full stable sort per query (utils/calc_utils.py:30-31), torch CPU, all host threads"}
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
     # int8 tensor peak: tcgen05 kind::i8 retires twice the MACs per clock of kind::f16, so 2 x the measured dense bf16
     # rate (burst figure: the kernel is timed alone, launch by launch)
     bf16 = peaks.get("bf16_tflops")
@@ -446,14 +610,17 @@ def main_native(args):
         "config": config_dict(args, world),
         "e2e": {"value": Q * D / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h,
-                "note": "per step: pinned-host packed database shard (uploaded in row ranges on a copy stream, scanned as "
-                        "they land) + float32 query codes H2D, index build (sample), pack, tensor-core search, "
-                        "(all-to-all + merge + all-gather), top-K keys D2H"},
+                "note": "per step and rank: pinned-host packed database shard (uploaded in row ranges on a copy stream, "
+                        "scanned as they land) + this step's float32 query codes H2D, index build (device-side sample of the "
+                        "first range), pack, one cmh_topk_tc call (scan, all-to-all by query slice, merge + verify), "
+                        "this rank's slice of the top-K keys D2H"},
         "gpu_launches": int(launches),
+        "parity_check": parity,
+        "phase_ms_per_step": phases,
         "clocks": clocks,
         "roofline": {
             "bound": "tensor", "kernel": "tc_collect_kernel (int8 tcgen05 GEMM + fused top-K candidate filter; "
-                                         f"{n_collect:g} launches per step: pilot rows + the rest)",
+                                         f"{n_collect:g} launches per step: pilot rows + the spans between the prefix-rule cuts)",
             "achieved": achieved_tops, "peak": i8_peak, "unit": "TOP/s (int8)",
             "frac": achieved_tops / i8_peak if achieved_tops else None,
             "peak_source": ("2 x MEASURED_PEAKS.json bf16_tflops (burst)" if bf16 else "fallback 2 x 1500 TFLOP/s") +
@@ -475,6 +642,7 @@ def main_native(args):
                     "algorithmic_bytes_per_launch_set": algo_bytes}},
         "cpu_baseline": cpu,
         "also": also,
+        "sharded_map": sharded_map,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -16,9 +16,10 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "libcmh_b200.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(_PKG_DIR), "include")
-SOURCES = ("api.cu", "pack.cu", "dense.cu", "eval_tile.cu", "eval_warp.cu", "eval_host.cu", "peaks.cu", "tc_collect.cu")
+SOURCES = ("api.cu", "pack.cu", "dense.cu", "eval_tile.cu", "eval_warp.cu", "eval_lane.cu", "eval_host.cu", "peaks.cu", "tc_collect.cu",
+           "tc_search.cu", "comm.cu", "sharded.cu")
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared")
+              "-Xcompiler", "-fPIC", "-shared", "-t", "0", "-ldl")
 
 CMH_MAX_TOPN = 64
 CMH_MAX_BITS = 4096
@@ -33,9 +34,14 @@ EXPORTS = (
     "cmh_finalize_map", "cmh_finalize_topn", "cmh_finalize_pr_workspace_bytes", "cmh_finalize_pr",
     "cmh_map_k_workspace_bytes", "cmh_map_k",
     "cmh_topk", "cmh_topk_merge",
-    "cmh_tc_supported", "cmh_tc_plan", "cmh_tc_collect", "cmh_tc_probe", "cmh_tc_cand_hist", "cmh_tc_choose", "cmh_tc_choose_prefix", "cmh_tc_choose_seen",
-    "cmh_topk_threshold", "cmh_topk_finalize", "cmh_topk_verify",
+    "cmh_tc_supported", "cmh_tc_plan", "cmh_tc_collect", "cmh_tc_probe", "cmh_tc_set_workers", "cmh_tc_cand_hist", "cmh_tc_choose", "cmh_tc_choose_prefix", "cmh_tc_choose_seen",
+    "cmh_topk_threshold", "cmh_topk_finalize", "cmh_topk_verify", "cmh_topk_merge_verify",
+    "cmh_comm_create", "cmh_comm_unique_id", "cmh_comm_create_rank", "cmh_comm_create_loopback", "cmh_comm_destroy",
+    "cmh_topk_sharded", "cmh_map_k_sharded_workspace_bytes", "cmh_map_k_sharded",
+    "cmh_tc_default_opts", "cmh_tc_pilot_stages", "cmh_struct_sizes", "cmh_tc_search_plan",
+    "cmh_tc_timing_create", "cmh_tc_timing_destroy", "cmh_tc_timing_read", "cmh_tc_timing_launches", "cmh_topk_tc",
 )
+ABI_VERSION = 2
 
 
 class CodeSet(ctypes.Structure):
@@ -52,6 +58,49 @@ class Plan(ctypes.Structure):
                 ("n_qtiles", ctypes.c_int32), ("chunk_rows", ctypes.c_int32), ("n_chunks", ctypes.c_int32),
                 ("nq", ctypes.c_int64), ("nd", ctypes.c_int64), ("nq_pad", ctypes.c_int64),
                 ("workspace_bytes", ctypes.c_uint64)]
+
+
+TC_MAX_STRIPES, TC_MAX_STAGES, TC_MAX_CUTS, TC_MAX_SPANS, TC_MAX_READY, TC_PHASES = 8, 4, 8, 32, 16, 8
+TC_PHASE_NAMES = ("thresholds", "pilot", "main", "finalize", "exchange")
+
+COMM_ALL_REDUCE = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p)
+COMM_ALL_GATHER = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p)
+COMM_ALL_TO_ALL = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p)
+
+
+class Comm(ctypes.Structure):
+    """``cmh_comm``: the transport of the exchange steps (built-in NCCL, or caller-supplied functions)"""
+    _fields_ = [("ctx", ctypes.c_void_p), ("rank", ctypes.c_int32), ("world", ctypes.c_int32),
+                ("all_reduce_u32", COMM_ALL_REDUCE), ("all_gather", COMM_ALL_GATHER), ("all_to_all", COMM_ALL_TO_ALL)]
+
+
+class TcOpts(ctypes.Structure):
+    """``cmh_tc_opts``"""
+    _fields_ = [("n_pilot", ctypes.c_int32), ("pilot_rows", ctypes.c_int64 * TC_MAX_STAGES), ("prefix", ctypes.c_int32),
+                ("n_prefix", ctypes.c_int32), ("prefix_frac", ctypes.c_double * TC_MAX_CUTS),
+                ("prefix_min_rows", ctypes.c_int64), ("tighten", ctypes.c_int32), ("cap", ctypes.c_int32),
+                ("seg_cap", ctypes.c_int32), ("exact_thresholds", ctypes.c_int32), ("gather", ctypes.c_int32),
+                ("n_ready", ctypes.c_int32), ("ready_rows", ctypes.c_int64 * TC_MAX_READY), ("sigma", ctypes.c_double)]
+
+
+class TcSearch(ctypes.Structure):
+    """``cmh_tc_search``"""
+    _fields_ = [("bits", ctypes.c_int32), ("K", ctypes.c_int32), ("world", ctypes.c_int32), ("rank", ctypes.c_int32),
+                ("nq", ctypes.c_int64), ("nd", ctypes.c_int64), ("nd_total", ctypes.c_int64), ("n_sample", ctypes.c_int64),
+                ("n_sample_all", ctypes.c_int64), ("n_stripes", ctypes.c_int32),
+                ("stripe_row", ctypes.c_int64 * TC_MAX_STRIPES), ("stripe_index", ctypes.c_int64 * TC_MAX_STRIPES),
+                ("n_stages", ctypes.c_int32), ("stage_rows", ctypes.c_int64 * TC_MAX_STAGES),
+                ("stage_rows_all", ctypes.c_int64 * TC_MAX_STAGES), ("n_prefix_cuts", ctypes.c_int32),
+                ("prefix_cut", ctypes.c_int64 * TC_MAX_CUTS), ("lockstep", ctypes.c_int32), ("n_spans", ctypes.c_int32),
+                ("span_lo", ctypes.c_int64 * TC_MAX_SPANS), ("span_hi", ctypes.c_int64 * TC_MAX_SPANS),
+                ("span_index", ctypes.c_int64 * TC_MAX_SPANS), ("span_seg_base", ctypes.c_int32 * TC_MAX_SPANS),
+                ("span_n_segs", ctypes.c_int32 * TC_MAX_SPANS), ("seg_total", ctypes.c_int32), ("seg_cap", ctypes.c_int32),
+                ("n_thr", ctypes.c_int32), ("thr_limit_slot", ctypes.c_int32), ("thr_final_slot", ctypes.c_int32),
+                ("per_rank", ctypes.c_int64), ("exch_width", ctypes.c_int32), ("opts", TcOpts), ("sample_plan", Plan),
+                ("off_cand", ctypes.c_uint64), ("off_cnt", ctypes.c_uint64), ("off_aux", ctypes.c_uint64),
+                ("off_thr", ctypes.c_uint64), ("off_hist", ctypes.c_uint64), ("off_sample_hist", ctypes.c_uint64),
+                ("off_part", ctypes.c_uint64), ("off_recv", ctypes.c_uint64), ("off_flags", ctypes.c_uint64),
+                ("off_eval", ctypes.c_uint64), ("off_gather", ctypes.c_uint64), ("workspace_bytes", ctypes.c_uint64)]
 
 
 def sources() -> List[str]:
@@ -99,8 +148,13 @@ def lib() -> ctypes.CDLL:
                     "(cmh_b200 has no CPU fallback)")
             L = ctypes.CDLL(LIB_PATH)
             _declare(L)
-            if L.cmh_abi_version() != 1:
-                raise RuntimeError("libcmh_b200.so ABI version mismatch")
+            if L.cmh_abi_version() != ABI_VERSION:
+                raise RuntimeError("libcmh_b200.so ABI version mismatch (rebuild: __graft_entry__.build())")
+            sizes = (ctypes.c_int32 * 6)()
+            L.cmh_struct_sizes(sizes, 6)
+            mine = [ctypes.sizeof(c) for c in (CodeSet, Plan, Comm, TcOpts, TcSearch)]
+            if list(sizes)[:5] != mine:
+                raise RuntimeError(f"ctypes struct mirrors {mine} do not match the library {list(sizes)[:5]}")
             _lib = L
     return _lib
 
@@ -135,6 +189,7 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cmh_topk.argtypes = [ppl, pcs, pcs, i32, i64, vp, vp, vp]
     L.cmh_topk_merge.argtypes = [vp, i32, i64, i32, vp, vp]
     L.cmh_tc_supported.argtypes = [i32, i32]
+    L.cmh_tc_set_workers.argtypes = [i32]
     L.cmh_tc_plan.argtypes = [i64, i64, i32, ctypes.POINTER(i32)]
     L.cmh_tc_collect.argtypes = [vp, i64, vp, i64, i32, i64, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     L.cmh_tc_cand_hist.argtypes = [vp, vp, i64, i32, i32, i32, i32, i32, vp, vp, vp]
@@ -144,11 +199,34 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cmh_topk_verify.argtypes = [vp, vp, i64, i32, i64, vp, vp, vp]
     L.cmh_tc_probe.argtypes = [vp, i64, vp, i64, i32, vp, i32, i32, vp, vp, vp, i32, vp]
     L.cmh_topk_threshold.argtypes = [vp, i64, i32, i64, i64, i32, vp, vp]
-    L.cmh_topk_finalize.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i64, i32, vp, vp, vp, vp]
+    L.cmh_topk_finalize.argtypes = [vp, vp, vp, i64, i32, i32, i32, i64, i32, i32, vp, vp, vp, vp]
+    L.cmh_topk_merge_verify.argtypes = [vp, i32, i64, i32, i32, i64, vp, vp, vp, vp]
+    pcm = ctypes.POINTER(Comm)
+    L.cmh_comm_create.argtypes = [i32, ctypes.POINTER(i32), ctypes.POINTER(pcm)]
+    L.cmh_comm_unique_id.argtypes = [vp]
+    L.cmh_comm_create_rank.argtypes = [vp, i32, i32, ctypes.POINTER(pcm)]
+    L.cmh_comm_create_loopback.argtypes = [i32, i32, ctypes.POINTER(pcm)]
+    L.cmh_comm_destroy.argtypes = [pcm]
+    L.cmh_topk_sharded.argtypes = [pcm, ppl, pcs, pcs, i32, i64, vp, vp, vp, vp]
+    L.cmh_map_k_sharded_workspace_bytes.argtypes = [i32, i64, i64, i32, i32, i32, i32]
+    L.cmh_map_k_sharded_workspace_bytes.restype = u64
+    L.cmh_map_k_sharded.argtypes = [pcm, pcs, pcs, i32, i32, i32, i64, i64, ctypes.POINTER(i64), i32, vp, vp, vp, vp, vp, vp,
+                                    vp, u64, vp]
+    L.cmh_tc_default_opts.argtypes = [ctypes.POINTER(TcOpts)]
+    L.cmh_tc_default_opts.restype = None
+    L.cmh_tc_pilot_stages.argtypes = [i64, i64, i32, ctypes.POINTER(i64)]
+    L.cmh_struct_sizes.argtypes = [ctypes.POINTER(ctypes.c_int32), i32]
+    L.cmh_tc_search_plan.argtypes = [pcm, i64, i64, i64, i32, i32, i32, ctypes.POINTER(i64), ctypes.POINTER(i64), i64,
+                                     ctypes.POINTER(TcOpts), ctypes.POINTER(TcSearch)]
+    L.cmh_tc_timing_create.argtypes = [ctypes.POINTER(vp)]
+    L.cmh_tc_timing_destroy.argtypes = [vp]
+    L.cmh_tc_timing_read.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
+    L.cmh_tc_timing_launches.argtypes = [vp, ctypes.POINTER(ctypes.c_float), i32]
+    L.cmh_topk_tc.argtypes = [ctypes.POINTER(TcSearch), pcm, vp, vp, vp, ctypes.POINTER(vp), vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("cmh_last_error", "cmh_finalize_pr_workspace_bytes", "cmh_map_k_workspace_bytes",
-                        "cmh_launch_count"):
+                        "cmh_launch_count", "cmh_map_k_sharded_workspace_bytes", "cmh_tc_default_opts"):
             fn.restype = i32
 
 

@@ -25,7 +25,7 @@ from . import engine as _e
 from .engine import PackedSet
 
 __all__ = ["calc_hammingDist", "calc_map_k_matrix", "calc_map_k", "calc_neighbor", "p_topK", "pr_curve",
-           "topk_hamming", "map_k_detail", "pack_codes", "pack_labels", "clear_cache"]
+           "topk_hamming", "map_k_detail", "pack_codes", "pack_labels", "clear_cache", "set_cache"]
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -58,7 +58,10 @@ def _on(x: torch.Tensor, device: torch.device) -> torch.Tensor:
 
 # Packed forms are cached per *tensor object* (weak reference + in-place version counter), never per data
 # pointer: `valid()` makes four calls on the same four buffers (train/base.py:259-262) and every buffer is packed
-# once.  A dead or modified tensor can never hit.
+# once.  A dead tensor or one modified through torch can never hit.  Writes that bypass torch's version counter
+# (`t.data[...] = ...`, a `torch.from_numpy` buffer changed through numpy, custom kernels) are invisible to it: call
+# `clear_cache()` after such a write, or switch the cache off with `set_cache(False)` (the reference recomputes from
+# the live buffer on every call).
 class _PackCache:
     def __init__(self, limit: int = 16):
         self._entries: Dict[Tuple[int, str, str], Tuple[weakref.ref, int, object]] = {}
@@ -90,10 +93,19 @@ class _PackCache:
 
 
 _cache = _PackCache()
+_cache_enabled = True
 
 
 def clear_cache() -> None:
     _cache.clear()
+
+
+def set_cache(enabled: bool) -> None:
+    """Enable / disable the pack cache (disabled: every call packs its inputs afresh, like the reference)."""
+    global _cache_enabled
+    _cache_enabled = bool(enabled)
+    if not _cache_enabled:
+        _cache.clear()
 
 
 def pack_codes(x, device=None, *, binarize: bool = False) -> PackedSet:
@@ -106,7 +118,7 @@ def pack_codes(x, device=None, *, binarize: bool = False) -> PackedSet:
         return x.packed()
     t = _to_tensor(x)
     device = _device_for(device, t)
-    owner = x if isinstance(x, torch.Tensor) else None
+    owner = x if isinstance(x, torch.Tensor) and _cache_enabled else None
     kind = "codes-b" if binarize else "codes"
     if owner is not None:
         hit = _cache.get(owner, kind, device)
@@ -134,7 +146,7 @@ def pack_labels(L, device=None) -> Tuple[torch.Tensor, int]:
     """Multi-hot labels ``[n, nlab]`` -> (int64 masks [n, ceil(nlab/64)] on the device, nlab)."""
     t = _to_tensor(L)
     device = _device_for(device, t)
-    owner = L if isinstance(L, torch.Tensor) else None
+    owner = L if isinstance(L, torch.Tensor) and _cache_enabled else None
     if owner is not None:
         hit = _cache.get(owner, "labels", device)
         if hit is not None:

@@ -56,7 +56,7 @@ class CodeBuffer:
         return idx
 
     def _put(self, index, x: torch.Tensor, mode: int) -> None:
-        if not x.is_cuda:
+        if x.device != self.device:                  # host tensors and tensors of ANOTHER GPU alike: the kernel runs here
             x = x.to(self.device)
         if x.dtype not in (torch.float32, torch.float16, torch.bfloat16, torch.float64):
             x = x.float()
@@ -80,6 +80,29 @@ class CodeBuffer:
     def put_argmax(self, index, logits: torch.Tensor) -> None:
         """DCHMT head: ``argmax(logits [n, bits, 2], -1)`` with class 0 -> -1 (`train/base.py:150-158`)."""
         self._put(index, logits, 1)
+
+    def reset(self) -> None:
+        """Forget everything written so far (all rows read as -1 again, zero / bad-index counters cleared): a buffer
+        reused across epochs returns to the +-1 fast path even if an earlier epoch stored exact zeros."""
+        self.sign.zero_()
+        self.valid.fill_(-1)
+        tail = self.bits - 64 * (self.sign.shape[1] - 1)
+        if tail < 64:
+            self.valid[:, self.sign.shape[1] - 1] = (1 << tail) - 1
+        self._counters.zero_()
+
+    def recount(self) -> int:
+        """Recount the exact zeros actually stored (rows overwritten since may have removed them) and return their
+        number; `packed()` then drops the valid plane again when there is none left."""
+        words = self.sign.shape[1]
+        full = torch.full((words,), -1, dtype=torch.int64, device=self.device)
+        tail = self.bits - 64 * (words - 1)
+        if tail < 64:
+            full[words - 1] = (1 << tail) - 1
+        missing = (~self.valid) & full                # real bit positions whose entry is an exact zero
+        n_zero = int(sum(int(((missing >> s) & 1).sum()) for s in range(64))) if bool(missing.any()) else 0
+        self._counters[0] = n_zero
+        return n_zero
 
     def packed(self) -> PackedSet:
         """The planes as the evaluation kernels take them (one tiny D2H: the zero / bad-index counters)."""

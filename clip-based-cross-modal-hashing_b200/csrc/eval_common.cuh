@@ -49,6 +49,7 @@ struct EvalArgs {
     int64_t index_base;
     int ntopn, K;
     uint32_t nmax;                  // largest precision@N cutoff (0 = none)
+    int big_ranks;                  // ranks may reach 2^23 and beyond (a long shard, or bases from other shards)
 };
 
 // precision@N cutoffs, passed to kernels by value

@@ -1,6 +1,7 @@
 // Host side of the ranking-by-counting path: launch plan, workspace carve-up, the small scan / reduce / finalise
 // kernels between the two heavy passes, and the extern "C" entry points declared in include/cmh_b200.h.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "eval_common.cuh"
@@ -21,8 +22,18 @@ int launch_rank_warp(const EvalArgs& a, bool tern, int wpc, const uint2* base, c
                      const TopnList& topn, double* ap_part, uint32_t* hits_part, cudaStream_t st);
 int launch_select_warp(const EvalArgs& a, bool tern, int wpc, const uint2* base, const int32_t* thr, uint64_t* keys,
                        cudaStream_t st);
+// eval_lane.cu: warp-per-query, lane-per-row kernels for binary codes up to 128 bits (layout W, 8 queries per CTA)
+bool lane_supported(const EvalArgs& a, bool tern);
+size_t lane_smem_bytes(const EvalArgs& a, int kind);
+int launch_hist_lane(const EvalArgs& a, uint32_t* chunk_hist, cudaStream_t st);
+int launch_rank_lane(const EvalArgs& a, const uint2* base, const uint32_t* total, const TopnList& topn, double* ap_part,
+                     uint32_t* hits_part, cudaStream_t st);
+constexpr int LANE_Q_TILE = 8;
 
 constexpr size_t MAX_DYN_SMEM = 227 * 1024;
+#ifndef CMH_AUTO_LANE
+#define CMH_AUTO_LANE 0       // the lane design is opt-in (CMH_EVAL_DESIGN=2 / cmh_eval_plan_design) until measured
+#endif
 constexpr int MAX_CHUNK_ROWS = 65520;  // pass-1 counters are 16 bit; multiple of 16 keeps bulk copies aligned
 constexpr int MIN_CHUNK_ROWS = 1024;   // amortises the per-CTA counter prologue / epilogue
 
@@ -335,23 +346,28 @@ __global__ void __launch_bounds__(256) pr_final_kernel(const double* __restrict_
 }
 
 // ---- top-K merge: rank of every candidate among all lists by binary search; unique keys -> unique ranks ----------
+// The lists of a query are staged in shared memory when they fit (in_smem); beyond that (n_lists * K * 8 bytes above the
+// budget, e.g. 8 shards x K = 4096) they are searched where they are - L2-resident, slower, but without a size limit.
 __global__ void __launch_bounds__(256) topk_merge_kernel(const uint64_t* __restrict__ keys_in, int n_lists, int64_t nq,
-                                                         int K, uint64_t* __restrict__ keys_out) {
+                                                         int K, int in_smem, uint64_t* __restrict__ keys_out) {
     extern __shared__ uint64_t sk[];  // [n_lists][K] for this query
     const int64_t q = blockIdx.x;
-    for (int i = threadIdx.x; i < n_lists * K; i += blockDim.x) {
-        const int g = i / K, j = i - g * K;
-        sk[i] = keys_in[((int64_t)g * nq + q) * K + j];
+    if (in_smem) {
+        for (int i = threadIdx.x; i < n_lists * K; i += blockDim.x) {
+            const int g = i / K, j = i - g * K;
+            sk[i] = keys_in[((int64_t)g * nq + q) * K + j];
+        }
+        __syncthreads();
     }
-    __syncthreads();
+    auto list_of = [&](int g) { return in_smem ? sk + g * K : keys_in + ((int64_t)g * nq + q) * K; };
     for (int i = threadIdx.x; i < n_lists * K; i += blockDim.x) {
         const int g = i / K, j = i - g * K;
-        const uint64_t key = sk[i];
+        const uint64_t key = list_of(g)[j];
         if (key == ~0ull) continue;  // padding
         int rank = j;
         for (int o = 0; o < n_lists && rank < K; ++o) {
             if (o == g) continue;
-            const uint64_t* lst = sk + o * K;
+            const uint64_t* lst = list_of(o);
             int lo = 0, hi = K;  // first position with lst[pos] >= key  (keys are unique across lists)
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
@@ -370,6 +386,14 @@ using namespace cmh;
 // =====================================================================================================================
 // extern "C"
 // =====================================================================================================================
+// Which design ranks an (nq, nd, nb) problem when the caller does not say: thread-per-query tile kernels (0), generic
+// warp-per-query kernels (1: any bucket count, ternary codes), lane kernels (2: binary codes <= 128 bits).
+static int auto_design(int64_t nq, int64_t nd, int nb, bool tile_ok, bool lane_ok) {
+    (void)nq; (void)nd; (void)nb;
+    if (lane_ok && CMH_AUTO_LANE) return 2;
+    return tile_ok ? 0 : 1;
+}
+
 static int make_plan(int64_t nq, int64_t nd, int bits, int nlab, int ternary, int max_topn, int design, cmh_plan* plan) {
     CMH_REQUIRE(plan, CMH_ERR_ARG, "cmh_eval_plan: NULL plan");
     CMH_REQUIRE(nq >= 0 && nd >= 0 && nlab >= 0 && max_topn >= 0 && max_topn <= CMH_MAX_TOPN, CMH_ERR_ARG,
@@ -385,12 +409,23 @@ static int make_plan(int64_t nq, int64_t nd, int bits, int nlab, int ternary, in
     a.ntopn = max_topn;
     const bool tile_ok = a.cw <= MAX_CW && a.lw <= MAX_LW && plan->nb <= TILE_MAX_NB &&
                          tile_smem_bytes(a, ternary != 0, 1) <= MAX_DYN_SMEM;
-    if (design < 0) design = tile_ok ? 0 : 1;
-    CMH_REQUIRE(design == 1 || tile_ok, CMH_ERR_UNSUPPORTED, "cmh_eval_plan: tile design cannot hold %d buckets", plan->nb);
+    const bool lane_ok = lane_supported(a, ternary != 0);
+    if (design < 0) {
+        // CMH_EVAL_DESIGN=0/1/2 forces a design where it applies (measurement aid)
+        static const int forced = [] { const char* e = getenv("CMH_EVAL_DESIGN"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : -1; }();
+        if (forced == 2 && lane_ok) design = 2;
+        else if (forced == 1) design = 1;
+        else if (forced == 0 && tile_ok) design = 0;
+        else design = auto_design(nq, nd, plan->nb, tile_ok, lane_ok);
+    }
+    CMH_REQUIRE(design != 0 || tile_ok, CMH_ERR_UNSUPPORTED, "cmh_eval_plan: tile design cannot hold %d buckets", plan->nb);
+    CMH_REQUIRE(design != 2 || lane_ok, CMH_ERR_UNSUPPORTED, "cmh_eval_plan: lane design needs binary codes of <= 128 bits");
     plan->design = design;
-    size_t smem; int max_cta_by_threads;
+    size_t smem; int max_cta_by_threads; int waves = 2;
     if (design == 0) {
         plan->q_tile = QT; smem = tile_smem_bytes(a, ternary != 0, 1); max_cta_by_threads = 2048 / QT;
+    } else if (design == 2) {
+        plan->q_tile = LANE_Q_TILE; smem = lane_smem_bytes(a, 1); max_cta_by_threads = 2048 / (LANE_Q_TILE * 32); waves = 4;
     } else {
         plan->q_tile = warp_queries_per_cta(a, ternary != 0);
         smem = warp_smem_bytes(a, ternary != 0, plan->q_tile); max_cta_by_threads = 2048 / (plan->q_tile * 32);
@@ -399,7 +434,7 @@ static int make_plan(int64_t nq, int64_t nd, int bits, int nlab, int ternary, in
     plan->nq_pad = round_up(std::max<int64_t>(nq, 1), plan->q_tile);
     plan->n_qtiles = (int32_t)(plan->nq_pad / plan->q_tile);
     const int ctas_per_sm = std::max(1, std::min<int>((int)(MAX_DYN_SMEM / smem), max_cta_by_threads));
-    const int64_t target_ctas = (int64_t)sm_count() * ctas_per_sm * 2;  // two full waves
+    const int64_t target_ctas = (int64_t)sm_count() * ctas_per_sm * waves;  // full waves of resident CTAs
     const int64_t want = std::max<int64_t>(1, ceil_div(target_ctas, plan->n_qtiles));
     int64_t rows = round_up(std::max<int64_t>(1, ceil_div(std::max<int64_t>(nd, 1), want)), 16);
     rows = std::max<int64_t>(rows, MIN_CHUNK_ROWS);
@@ -416,7 +451,7 @@ extern "C" int cmh_eval_plan(int64_t nq, int64_t nd, int bits, int nlab, int ter
 }
 extern "C" int cmh_eval_plan_design(int64_t nq, int64_t nd, int bits, int nlab, int ternary, int max_topn, int design,
                                     cmh_plan* plan) {
-    CMH_REQUIRE(design >= -1 && design <= 1, CMH_ERR_ARG, "cmh_eval_plan_design: design=%d", design);
+    CMH_REQUIRE(design >= -1 && design <= 2, CMH_ERR_ARG, "cmh_eval_plan_design: design=%d", design);
     return make_plan(nq, nd, bits, nlab, ternary, max_topn, design, plan);
 }
 
@@ -442,7 +477,9 @@ extern "C" int cmh_eval_hist(const cmh_plan* plan, const cmh_codeset* q, const c
         const dim3 grid((unsigned)ceil_div(a.nq, 256), (unsigned)a.nb);
         reduce_hist_kernel<false><<<grid, 256, 0, st>>>(a, w.chunk_hist, w.shard_all, w.shard_rel, hist_all, hist_rel);
     } else {
-        if ((rc = launch_hist_warp(a, plan->ternary != 0, plan->q_tile, w.chunk_hist, st))) return rc;
+        if (plan->design == 2) rc = launch_hist_lane(a, w.chunk_hist, st);
+        else rc = launch_hist_warp(a, plan->ternary != 0, plan->q_tile, w.chunk_hist, st);
+        if (rc) return rc;
         // grid.y (= query) is capped at 65535: walk the queries in slabs.  Shifting every [q][b]-major pointer by
         // q0 * nb moves the query origin (the chunk stride nq_pad * nb is unaffected).
         for (int64_t q0 = 0; q0 < a.nq; q0 += 65535) {
@@ -510,6 +547,7 @@ extern "C" int cmh_eval_rank(const cmh_plan* plan, const cmh_codeset* q, const c
     }
     a.ntopn = ntopn;
     a.nmax = ntopn ? tl.n[ntopn - 1] : 0u;
+    a.big_ranks = (global_all != nullptr || plan->nd >= (1ll << 23)) ? 1 : 0;   // ranks may exceed 2^23: no float bit tricks
 
     ScanArgs sa;
     sa.g_all = global_all ? global_all : w.shard_all;
@@ -521,6 +559,8 @@ extern "C" int cmh_eval_rank(const cmh_plan* plan, const cmh_codeset* q, const c
     if (plan->nd > 0) {
         if (plan->design == 0)
             rc = launch_rank_tile(a, plan->ternary != 0, w.base, w.total, tl, w.ap_part, w.hits_part, st);
+        else if (plan->design == 2)
+            rc = launch_rank_lane(a, w.base, w.total, tl, w.ap_part, w.hits_part, st);
         else
             rc = launch_rank_warp(a, plan->ternary != 0, plan->q_tile, w.base, w.total, tl, w.ap_part, w.hits_part, st);
         if (rc) return rc;
@@ -633,16 +673,16 @@ extern "C" int cmh_topk_merge(const uint64_t* keys_in, int n_lists, int64_t nq, 
     CMH_REQUIRE(n_lists >= 1 && nq >= 0 && K >= 1, CMH_ERR_ARG, "cmh_topk_merge: bad sizes");
     if (nq == 0) return CMH_OK;
     CMH_REQUIRE(keys_in && keys_out, CMH_ERR_ARG, "cmh_topk_merge: NULL pointer");
-    const size_t smem = (size_t)n_lists * K * 8;
-    CMH_REQUIRE(smem <= MAX_DYN_SMEM, CMH_ERR_UNSUPPORTED, "cmh_topk_merge: n_lists * K = %d exceeds shared memory",
-                n_lists * K);
+    const size_t want = (size_t)n_lists * K * 8;
+    const int in_smem = want <= 200 * 1024 ? 1 : 0;
+    const size_t smem = in_smem ? want : 0;
     CMH_REQUIRE(nq <= 0x7fffffffll, CMH_ERR_UNSUPPORTED, "cmh_topk_merge: too many queries per call");
     cudaStream_t st = (cudaStream_t)stream;
     fill_u64_kernel<<<(unsigned)std::min<int64_t>(ceil_div(nq * (int64_t)K, 256), (int64_t)sm_count() * 16), 256, 0, st>>>(
         keys_out, nq * (int64_t)K, ~0ull);
     CMH_LAUNCH_CHECK("fill_u64_kernel");
-    CMH_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_merge_kernel<<<(unsigned)nq, 256, smem, st>>>(keys_in, n_lists, nq, K, keys_out);
+    if (in_smem) CMH_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_merge_kernel<<<(unsigned)nq, 256, smem, st>>>(keys_in, n_lists, nq, K, in_smem, keys_out);
     CMH_LAUNCH_CHECK("topk_merge_kernel");
     return CMH_OK;
 }

@@ -1,0 +1,326 @@
+// Warp-per-query, lane-per-row ("lane") kernels of the ranking-by-counting path for binary codes of up to 128 bits -
+// the design for the reference's own calls (calc_map_k_matrix, utils/calc_utils.py:16-39) at the BASELINE.json shapes.
+//
+// Why a third design.  The thread-per-query kernels (eval_tile.cu) keep one counter column per THREAD: nb buckets x 8 B
+// x 128 threads - 132 KB of shared memory per CTA for 128-bit codes, i.e. one 4-warp CTA per SM (ncu, profiles/r02a:
+// rank_tile_kernel at the MS-COCO shape issues on 16 % of the cycles, 6 % of the warp slots are occupied).  Here a WARP
+// owns a query and its 32 lanes own 32 consecutive database rows, so the counters are per warp (nb x 8 B = 1 KB) and
+// the SM is full of warps.  The price is that "how many earlier rows of my bucket" is no longer a private running
+// counter: within the 32 rows of a step it comes from __match_any_sync (lanes holding the same bucket) + a popcount of
+// the peers below the lane, across steps from the warp's shared-memory counter, advanced by the last lane of each
+// group.  Index order - the stable tie order of the reference's forced-stable torch.sort (:31) - is lane order.
+//
+//   hist_lane_kernel   pass 1: per (query, chunk) bucket counts, all + relevant packed 16|16 (shared-memory atomics,
+//                      order does not matter)                                                        (:26-27,:30)
+//   rank_lane_kernel   pass 2: ranks from the exclusive-scan bases; every relevant row adds relrank / rank (:31-37)
+//
+// Database rows stream through shared memory in LANE_ROWS-row stages filled by the bulk-copy engine (cp.async.bulk +
+// mbarrier) while the previous stage is consumed; the 8 warps (= 8 queries) of a CTA share the stage.  Layout of the
+// per-chunk histograms / bases: "W" ([chunk][query][bucket], eval_common.cuh), shared with the generic warp kernels.
+#include "eval_common.cuh"
+
+namespace cmh {
+
+constexpr int LANE_WARPS = 8;     // queries per CTA
+constexpr int LANE_ROWS = 512;    // database rows per stage
+
+__host__ __device__ inline size_t lane_stage_bytes(int cws, int lws) { return (size_t)LANE_ROWS * (cws + lws) * 4; }
+__host__ __device__ inline int lane_nbp(int nb) { return (nb + 1 + 3) & ~3; }   // + the parking bucket of idle lanes
+
+size_t lane_smem_bytes(const EvalArgs& a, int kind /*0 hist, 1 rank*/) {
+    return 128 + 2 * lane_stage_bytes(a.cw_stride, a.lw_stride) + (size_t)LANE_WARPS * lane_nbp(a.nb) * (kind ? 8 : 4) +
+           (kind ? (size_t)LANE_WARPS * CMH_MAX_TOPN * 4 : 0);
+}
+
+bool lane_supported(const EvalArgs& a, bool tern) {
+    return !tern && (a.cw_stride == 2 || a.cw_stride == 4) && (a.lw_stride == 0 || a.lw_stride == 2 || a.lw_stride == 4) &&
+           a.nb <= 257;
+}
+
+// smem: [bars: 128 B][stage 0: codes, labels][stage 1: codes, labels][counters ...]; stage pointers are computed, not
+// stored in an array (an array indexed by the stage parity would live in local memory)
+struct LaneSmem {
+    unsigned char* raw;
+    uint32_t code_b, stage_b;
+    __device__ __forceinline__ uint64_t* bar(int st) const { return reinterpret_cast<uint64_t*>(raw) + st; }
+    __device__ __forceinline__ uint32_t* codes(int st) const { return reinterpret_cast<uint32_t*>(raw + 128 + (size_t)st * stage_b); }
+    __device__ __forceinline__ uint32_t* labels(int st) const {
+        return reinterpret_cast<uint32_t*>(raw + 128 + (size_t)st * stage_b + code_b);
+    }
+    __device__ __forceinline__ unsigned char* rest() const { return raw + 128 + 2 * (size_t)stage_b; }
+};
+
+__device__ __forceinline__ LaneSmem carve_lane_smem(unsigned char* raw, int cws, int lws) {
+    LaneSmem s;
+    s.raw = raw;
+    s.code_b = (uint32_t)LANE_ROWS * cws * 4;
+    s.stage_b = (uint32_t)lane_stage_bytes(cws, lws);
+    return s;
+}
+
+// Fill one stage with database rows [row0, row0 + rows): whole stages through the bulk-copy engine, the ragged last
+// stage of a chunk (and every stage of a shard view that is not 16-byte aligned) by the CTA.  Called by all threads.
+template <int CWS, int LWS>
+__device__ __forceinline__ void lane_load_stage(const EvalArgs& a, const LaneSmem& s, int st, int64_t row0, int rows) {
+    const uint32_t code_b = (uint32_t)rows * CWS * 4, lab_b = (uint32_t)rows * LWS * 4;
+    if (rows == LANE_ROWS && a.bulk_ok) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(s.bar(st), code_b + lab_b);
+            bulk_g2s(s.codes(st), a.ds + row0 * CWS, code_b, s.bar(st));
+            if (LWS) bulk_g2s(s.labels(st), a.dl + row0 * LWS, lab_b, s.bar(st));
+        }
+    } else {
+        for (int i = threadIdx.x; i < rows * CWS; i += blockDim.x) s.codes(st)[i] = a.ds[row0 * CWS + i];
+        if (LWS)
+            for (int i = threadIdx.x; i < rows * LWS; i += blockDim.x) s.labels(st)[i] = a.dl[row0 * LWS + i];
+        __syncthreads();
+        if (threadIdx.x == 0) mbar_arrive(s.bar(st));
+    }
+}
+
+// the query of a warp: the same words in every lane
+template <int CWS, int LWS>
+struct LaneQuery {
+    uint32_t s[CWS];
+    uint32_t l[LWS ? LWS : 1];
+
+    __device__ __forceinline__ void load(const EvalArgs& a, int64_t q) {
+        const bool live = q < a.nq;
+#pragma unroll
+        for (int w = 0; w < CWS; ++w) s[w] = live ? a.qs[q * CWS + w] : 0u;
+        if (LWS) {
+#pragma unroll
+            for (int w = 0; w < LWS; ++w) l[w] = live ? a.ql[q * LWS + w] : 0u;
+        }
+    }
+    // Hamming distance to the row at `rc` (padding words are zero on both sides)
+    __device__ __forceinline__ int bucket(const uint32_t* __restrict__ rc) const {
+        if (CWS == 2) {
+            const uint2 r = *reinterpret_cast<const uint2*>(rc);
+            return __popc(s[0] ^ r.x) + __popc(s[1] ^ r.y);
+        }
+        const uint4 r = *reinterpret_cast<const uint4*>(rc);
+        return __popc(s[0] ^ r.x) + __popc(s[1] ^ r.y) + __popc(s[2 % CWS] ^ r.z) + __popc(s[3 % CWS] ^ r.w);
+    }
+    __device__ __forceinline__ bool relevant(const uint32_t* __restrict__ rl) const {
+        if (LWS == 0) return false;
+        if (LWS == 2) {
+            const uint2 r = *reinterpret_cast<const uint2*>(rl);
+            return ((l[0] & r.x) | (l[1 % (LWS ? LWS : 1)] & r.y)) != 0u;
+        }
+        const uint4 r = *reinterpret_cast<const uint4*>(rl);
+        return ((l[0] & r.x) | (l[1 % (LWS ? LWS : 1)] & r.y) | (l[2 % (LWS ? LWS : 1)] & r.z) | (l[3 % (LWS ? LWS : 1)] & r.w)) != 0u;
+    }
+};
+
+// =================================================================================================================
+// pass 1
+// =================================================================================================================
+template <int CWS, int LWS>
+__global__ void __launch_bounds__(LANE_WARPS * 32) hist_lane_kernel(const EvalArgs a, uint32_t* __restrict__ chunk_hist) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const LaneSmem s = carve_lane_smem(smem_raw, CWS, LWS);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nbp = lane_nbp(a.nb);
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(s.rest()) + warp * nbp;
+    const int chunk = blockIdx.y;
+    const int64_t q = (int64_t)blockIdx.x * LANE_WARPS + warp;
+    const int64_t c_begin = (int64_t)chunk * a.chunk_rows;
+    const int c_rows = (int)min((int64_t)a.chunk_rows, a.nd - c_begin);
+    const int n_tiles = (c_rows + LANE_ROWS - 1) / LANE_ROWS;
+
+    if (threadIdx.x == 0) {
+        mbar_init(s.bar(0), 1);
+        mbar_init(s.bar(1), 1);
+        mbar_fence_init();
+    }
+    LaneQuery<CWS, LWS> qu;
+    qu.load(a, q);
+    for (int b = lane; b < nbp; b += 32) cnt[b] = 0u;
+    __syncthreads();
+    lane_load_stage<CWS, LWS>(a, s, 0, c_begin, min(LANE_ROWS, c_rows));
+    if (n_tiles > 1) lane_load_stage<CWS, LWS>(a, s, 1, c_begin + LANE_ROWS, min(LANE_ROWS, c_rows - LANE_ROWS));
+
+    for (int t = 0; t < n_tiles; ++t) {
+        const int st = t & 1;
+        mbar_wait(s.bar(st), (t >> 1) & 1);
+        const int rows = min(LANE_ROWS, c_rows - t * LANE_ROWS);
+        const uint32_t* __restrict__ tc = s.codes(st);
+        const uint32_t* __restrict__ tl = s.labels(st);
+        const int full = rows & ~31;
+#pragma unroll 4
+        for (int g = 0; g < full; g += 32) {
+            const int r = g + lane;
+            const int d = qu.bucket(tc + r * CWS);
+            atomicAdd(&cnt[d], qu.relevant(tl + r * LWS) ? 0x10001u : 1u);   // shared-memory atomic; order is irrelevant here
+        }
+        if (full + lane < rows) {
+            const int r = full + lane;
+            const int d = qu.bucket(tc + r * CWS);
+            atomicAdd(&cnt[d], qu.relevant(tl + r * LWS) ? 0x10001u : 1u);
+        }
+        __syncthreads();  // everyone is done with stage st
+        if (t + 2 < n_tiles)
+            lane_load_stage<CWS, LWS>(a, s, st, c_begin + (int64_t)(t + 2) * LANE_ROWS, min(LANE_ROWS, c_rows - (t + 2) * LANE_ROWS));
+    }
+    __syncwarp();
+    if (q < a.nq_pad)
+        for (int b = lane; b < a.nb; b += 32) chunk_hist[hist_index_W(a, chunk, b, q)] = cnt[b];
+}
+
+// =================================================================================================================
+// pass 2 - average precision + precision@N
+// =================================================================================================================
+// integer -> float without the XU pipe (POPC, I2F and MUFU.RCP share it): exact for x < 2^23
+template <bool BIG>
+__device__ __forceinline__ float lane_u2f(uint32_t x) {
+    if (BIG) return (float)x;
+    return __uint_as_float(0x4B000000u | x) - 8388608.0f;
+}
+
+// 1 / y for y >= 1: one MUFU.RCP, without the denormal rescaling __fdividef / __frcp_rn carry around
+__device__ __forceinline__ float lane_rcp(float y) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
+    return r;
+}
+
+template <int CWS, int LWS, bool BIG>
+__global__ void __launch_bounds__(LANE_WARPS * 32) rank_lane_kernel(const EvalArgs a, const uint2* __restrict__ base,
+                                                                    const uint32_t* __restrict__ total_arr, const TopnList topn,
+                                                                    double* __restrict__ ap_part,
+                                                                    uint32_t* __restrict__ hits_part) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const LaneSmem s = carve_lane_smem(smem_raw, CWS, LWS);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nbp = lane_nbp(a.nb);
+    uint2* cnt = reinterpret_cast<uint2*>(s.rest()) + warp * nbp;
+    uint32_t* hits = reinterpret_cast<uint32_t*>(s.rest() + (size_t)LANE_WARPS * nbp * 8) + warp * CMH_MAX_TOPN;
+    const int chunk = blockIdx.y;
+    const int64_t q = (int64_t)blockIdx.x * LANE_WARPS + warp;
+    const bool qlive = q < a.nq_pad;
+    const int64_t c_begin = (int64_t)chunk * a.chunk_rows;
+    const int c_rows = (int)min((int64_t)a.chunk_rows, a.nd - c_begin);
+    const int n_tiles = (c_rows + LANE_ROWS - 1) / LANE_ROWS;
+    const uint32_t lt = lanemask_lt();
+
+    if (threadIdx.x == 0) {
+        mbar_init(s.bar(0), 1);
+        mbar_init(s.bar(1), 1);
+        mbar_fence_init();
+    }
+    LaneQuery<CWS, LWS> qu;
+    qu.load(a, q);
+    const uint32_t total = qlive ? total_arr[q] : 0u;
+    for (int b = lane; b < nbp; b += 32)
+        cnt[b] = (qlive && b < a.nb) ? base[hist_index_W(a, chunk, b, q)] : make_uint2(0u, 0u);
+    for (int i = lane; i < a.ntopn; i += 32) hits[i] = 0u;
+    __syncthreads();
+    lane_load_stage<CWS, LWS>(a, s, 0, c_begin, min(LANE_ROWS, c_rows));
+    if (n_tiles > 1) lane_load_stage<CWS, LWS>(a, s, 1, c_begin + LANE_ROWS, min(LANE_ROWS, c_rows - LANE_ROWS));
+
+    const uint32_t nmax = a.nmax;
+    double acc = 0.0;
+    for (int t = 0; t < n_tiles; ++t) {
+        const int st = t & 1;
+        mbar_wait(s.bar(st), (t >> 1) & 1);
+        const int rows = min(LANE_ROWS, c_rows - t * LANE_ROWS);
+        const uint32_t* __restrict__ tc = s.codes(st);
+        const uint32_t* __restrict__ tl = s.labels(st);
+        float acc_t = 0.f;      // <= 16 terms <= 1 per lane and stage: float32 rounding stays below 16 * 2^-24 relative
+        // one step = 32 rows, lane = row.  `in`: false only for the idle lanes of a chunk's ragged last step.
+        auto step = [&](int g, bool in) {
+            const int r = g + lane;
+            const int d = in ? qu.bucket(tc + r * CWS) : a.nb;       // idle lanes park in bucket nb
+            const bool rel = in && qu.relevant(tl + r * LWS);
+            const uint32_t grp = __match_any_sync(0xffffffffu, d);   // the lanes (rows) of this step in my bucket
+            const uint32_t relmask = __ballot_sync(0xffffffffu, rel);
+            const uint2 c = cnt[d];
+            const uint32_t below = grp & lt;                         // ... of lower index
+            const uint32_t rank = c.x + (uint32_t)__popc(below) + 1u;
+            const uint32_t rr = c.y + (uint32_t)__popc(below & relmask) + (rel ? 1u : 0u);
+            // count / tindex (:35): x * rcp(y), <= 1.5 ulp per term, i.e. <= 2e-7 on an AP in [0, 1] (the bar is 1e-6)
+            const float term = lane_u2f<BIG>(rr) * lane_rcp(lane_u2f<BIG>(rank));
+            acc_t += (rel && rr <= total) ? term : 0.f;
+            if (rel && rank <= nmax) {                               // precision@N, rare
+                int i = 0;
+                while (rank > topn.n[i]) ++i;
+                atomicAdd(&hits[i], 1u);
+            }
+            __syncwarp();                                            // every lane has read its counter
+            if ((grp >> lane) == 1u) cnt[d] = make_uint2(rank, rr);  // the last row of the group leaves its own ranks behind
+            __syncwarp();
+        };
+        const int full = rows & ~31;
+#pragma unroll 2
+        for (int g = 0; g < full; g += 32) step(g, true);
+        if (full < rows) step(full, full + lane < rows);
+        acc += (double)acc_t;
+        __syncthreads();
+        if (t + 2 < n_tiles)
+            lane_load_stage<CWS, LWS>(a, s, st, c_begin + (int64_t)(t + 2) * LANE_ROWS, min(LANE_ROWS, c_rows - (t + 2) * LANE_ROWS));
+    }
+    // fixed-order reduction over the lanes: deterministic
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (qlive) {
+        if (lane == 0) ap_part[(int64_t)chunk * a.nq_pad + q] = acc;
+        __syncwarp();
+        for (int i = lane; i < a.ntopn; i += 32) hits_part[((int64_t)chunk * a.ntopn + i) * a.nq_pad + q] = hits[i];
+    }
+}
+
+// =================================================================================================================
+// launchers
+// =================================================================================================================
+template <typename Kern>
+static int prep_lane(Kern kern, size_t smem) {
+    CMH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return CMH_OK;
+}
+
+int launch_hist_lane(const EvalArgs& a, uint32_t* chunk_hist, cudaStream_t st) {
+    const dim3 grid((unsigned)(a.nq_pad / LANE_WARPS), (unsigned)a.n_chunks);
+    const size_t smem = lane_smem_bytes(a, 0);
+#define CMH_GO(CWS_, LWS_)                                                  \
+    do {                                                                    \
+        auto k = hist_lane_kernel<CWS_, LWS_>;                              \
+        int rc = prep_lane(k, smem);                                        \
+        if (rc) return rc;                                                  \
+        k<<<grid, LANE_WARPS * 32, smem, st>>>(a, chunk_hist);              \
+    } while (0)
+    if (a.cw_stride == 2) {
+        if (a.lw_stride == 0) CMH_GO(2, 0); else if (a.lw_stride == 2) CMH_GO(2, 2); else CMH_GO(2, 4);
+    } else {
+        if (a.lw_stride == 0) CMH_GO(4, 0); else if (a.lw_stride == 2) CMH_GO(4, 2); else CMH_GO(4, 4);
+    }
+#undef CMH_GO
+    CMH_LAUNCH_CHECK("hist_lane_kernel");
+    return CMH_OK;
+}
+
+int launch_rank_lane(const EvalArgs& a, const uint2* base, const uint32_t* total, const TopnList& tl, double* ap_part,
+                     uint32_t* hits_part, cudaStream_t st) {
+    const dim3 grid((unsigned)(a.nq_pad / LANE_WARPS), (unsigned)a.n_chunks);
+    const size_t smem = lane_smem_bytes(a, 1);
+    const bool big = a.big_ranks != 0;
+#define CMH_GO(CWS_, LWS_, BIG_)                                                        \
+    do {                                                                                \
+        auto k = rank_lane_kernel<CWS_, LWS_, BIG_>;                                    \
+        int rc = prep_lane(k, smem);                                                    \
+        if (rc) return rc;                                                              \
+        k<<<grid, LANE_WARPS * 32, smem, st>>>(a, base, total, tl, ap_part, hits_part); \
+    } while (0)
+#define CMH_ROW(CWS_)                                                                   \
+    do {                                                                                \
+        if (a.lw_stride == 2) { if (big) CMH_GO(CWS_, 2, true); else CMH_GO(CWS_, 2, false); } \
+        else                  { if (big) CMH_GO(CWS_, 4, true); else CMH_GO(CWS_, 4, false); } \
+    } while (0)
+    if (a.cw_stride == 2) CMH_ROW(2); else CMH_ROW(4);
+#undef CMH_ROW
+#undef CMH_GO
+    CMH_LAUNCH_CHECK("rank_lane_kernel");
+    return CMH_OK;
+}
+
+}  // namespace cmh

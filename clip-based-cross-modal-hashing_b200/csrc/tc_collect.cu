@@ -40,8 +40,9 @@
 // orders the candidates by key - (distance, index), all keys distinct - which IS the stable ranking, and flags any
 // query whose candidate list is short or overflowed for the exact two-pass path.
 #include <algorithm>
+#include <cmath>
 
-#include "common.cuh"
+#include "tc_internal.cuh"
 
 // Pipeline trace (debug builds only, -DCMH_TC_TRACE): CTA (0,0) records clock64() at the hand-offs of its first
 // TC_TRACE_ITERS iterations into the buffer registered with cmh_tc_set_trace: [role][iteration][event].
@@ -201,9 +202,8 @@ __device__ __forceinline__ uint4 expand16(uint32_t bits16) {
 
 // per-query bookkeeping shared by every CTA working on the query (global memory, zeroed by cmh_tc_collect)
 struct TcAux {
-    uint32_t h[4];        // candidates seen so far at dist == thr0 - j (j = 0, 1, 2) and at dist <= thr0 - 3 (j = 3)
-    uint32_t force_fail;  // a candidate segment overflowed: entries were dropped
-    uint32_t pad[3];
+    uint32_t h[4];        // candidates of THIS launch so far at dist == thr0 - j (j = 0, 1, 2) and at dist <= thr0 - 3 (j = 3)
+    uint32_t pad[4];      // (an overflowed segment shows in its count: cnt > seg_cap)
 };
 
 struct TcArgs {
@@ -559,7 +559,6 @@ __global__ void __launch_bounds__(WK ? TC_THREADS_WK : TC_THREADS, 1) tc_collect
             const int64_t q = q0 + t * TC_M + i;
             if (q < a.nq) {
                 a.cnt[(int64_t)seg_id * a.nq + q] = pos_s[i];
-                if (pos_s[i] > (uint32_t)a.seg_cap) a.aux[q].force_fail = 1u;
             }
         }
     } else {
@@ -800,7 +799,6 @@ __global__ void __launch_bounds__(WK ? TC_THREADS_WK : TC_THREADS, 1) tc_collect
             while (n_parked > 0) work_off();
             if (live) {
                 a.cnt[(int64_t)seg_id * a.nq + q] = pos;
-                if (pos > (uint32_t)a.seg_cap) a.aux[q].force_fail = 1u;
             }
         }
     }
@@ -829,6 +827,7 @@ __global__ void __launch_bounds__(256) topk_threshold_kernel(const uint32_t* __r
 }
 
 constexpr int FIN_MAX = 4096;
+constexpr uint64_t TC_KEY_FAIL = ~0ull - 1;   // first key of a failed per-shard list (no real key: dist field 2^31 - 1)
 constexpr int FIN_BINS = 129;   // bits <= 128 on the tensor path
 constexpr int FIN_THREADS = 512;
 
@@ -896,10 +895,18 @@ __device__ __forceinline__ uint64_t seg_flat_load(const uint64_t* __restrict__ b
 }
 
 constexpr int CH_THREADS = 256;
+// the threshold rule shared by tc_choose_kernel and the fused form below: the smallest bucket b <= thr_in whose
+// cumulative count reaches `need` gives min(thr_in, b + offset); thr_in when there is none
+struct ChooseRule {
+    double need;          // < 0: no fused choose
+    int offset;
+    const int32_t* thr_in;
+    int32_t* thr_out;
+};
 __global__ void __launch_bounds__(CH_THREADS) tc_cand_hist_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt,
                                                                   int64_t nq, int seg_lo, int seg_hi, int seg_total, int seg_cap,
                                                                   int nb, uint32_t* __restrict__ hist_out,
-                                                                  uint32_t* __restrict__ overflow) {
+                                                                  uint32_t* __restrict__ overflow, const ChooseRule rule) {
     constexpr int BLOCK = CH_THREADS * SEG_IT;
     __shared__ uint32_t hist[FIN_BINS];
     __shared__ uint32_t s_off[BLOCK + 1], s_warp[CH_THREADS / 32];
@@ -923,8 +930,38 @@ __global__ void __launch_bounds__(CH_THREADS) tc_cand_hist_kernel(const uint64_t
     }
     if (over) s_over = 1u;
     __syncthreads();
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) hist_out[q * nb + i] = i < FIN_BINS ? hist[i] : 0u;
-    if (threadIdx.x == 0) overflow[q] = s_over;
+    if (hist_out != nullptr) {
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) hist_out[q * nb + i] = i < FIN_BINS ? hist[i] : 0u;
+        if (threadIdx.x == 0) overflow[q] = s_over;
+    }
+    if (rule.need >= 0.0 && threadIdx.x == 0) {      // one GPU: nothing to exchange between the histogram and the rule
+        const int t_in = rule.thr_in[q];
+        int t = t_in;
+        if (s_over == 0u) {
+            double cum = 0.0;
+            for (int b = 0; b <= min(t_in, min(nb, FIN_BINS) - 1); ++b) {
+                cum += (double)hist[b];
+                if (cum >= rule.need) { t = min(t_in, b + rule.offset); break; }
+            }
+        }
+        rule.thr_out[q] = t;
+    }
+}
+
+// sharded, contiguous ranges: every[r][q][b] all-gathered candidate histograms -> lower = sum over ranks <= rank
+// (rows of lower index than what this shard still has to scan), seen = sum over all ranks
+__global__ void __launch_bounds__(256) tc_sum_ranks_kernel(const uint32_t* __restrict__ every, int world, int rank, int64_t n,
+                                                           uint32_t* __restrict__ lower, uint32_t* __restrict__ seen) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t lo = 0, all = 0;
+    for (int r = 0; r < world; ++r) {
+        const uint32_t v = every[(int64_t)r * n + i];
+        all += v;
+        if (r <= rank) lo += v;
+    }
+    lower[i] = lo;
+    seen[i] = all;
 }
 
 __global__ void __launch_bounds__(256) tc_choose_kernel(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ overflow,
@@ -967,10 +1004,9 @@ __global__ void __launch_bounds__(256) topk_verify_kernel(const uint64_t* __rest
 
 __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64_t* __restrict__ cand,
                                                                     const uint32_t* __restrict__ cnt,
-                                                                    const TcAux* __restrict__ aux,
                                                                     const int32_t* __restrict__ thr_limit, int64_t nq,
                                                                     int n_chunks, int seg_cap, int K, int64_t nd, int partial,
-                                                                    uint64_t* __restrict__ keys,
+                                                                    int width, uint64_t* __restrict__ keys,
                                                                     uint32_t* __restrict__ fail_flags,
                                                                     uint32_t* __restrict__ fail_count) {
     constexpr int BLOCK = FIN_THREADS * SEG_IT;
@@ -1005,7 +1041,7 @@ __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64
     __syncthreads();
     // partial (one shard of several): emit what there is, up to K; the K-th key is judged after the merge
     const int64_t want = partial ? min(need, (int64_t)s_total) : need;
-    bool fail = s_over != 0u || (int64_t)s_total < want || aux[q].force_fail != 0u;
+    bool fail = s_over != 0u || (int64_t)s_total < want;
     if (!fail) {
         if (threadIdx.x == 0) {
             int64_t cum = 0;
@@ -1024,7 +1060,8 @@ __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64
         if (fail) atomicAdd(fail_count, 1u);
     }
     if (fail) {
-        for (int i = threadIdx.x; i < K; i += blockDim.x) keys[q * K + i] = ~0ull;
+        // a failed shard list starts with the marker: the merge flags the query whatever the other shards hold
+        for (int i = threadIdx.x; i < width; i += blockDim.x) keys[q * width + i] = (partial && i == 0) ? TC_KEY_FAIL : ~0ull;
         return;
     }
     // pass 2: place the candidates at or below the K-th bucket, bucket by bucket and - inside a bucket - in the order
@@ -1094,7 +1131,72 @@ __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64
             }
         }
     }
-    for (int i = threadIdx.x; i < K; i += blockDim.x) keys[q * K + i] = i < keep ? sk[i] : ~0ull;
+    for (int i = threadIdx.x; i < width; i += blockDim.x) keys[q * width + i] = i < keep ? sk[i] : ~0ull;
+}
+
+// ---- sharded: merge of the per-shard lists of one query slice + verification, one CTA per query -----------------------
+// lists: [n_lists][nq][W] ascending keys (pads UINT64_MAX; a list that starts with TC_KEY_FAIL comes from a shard whose
+// candidate segments overflowed).  Every key's rank among all lists by binary search (keys are unique across shards).
+// A list that arrives FULL (W < K keys, none a pad) may have been cut: what it lost lies above its last key, so the
+// result is exact unless that key ranks before the K-th of the merge.  The K-th key must also come from a complete
+// bucket (<= thr_limit).  Lists live in shared memory when they fit, else they are searched where they are.
+__global__ void __launch_bounds__(256) topk_merge_verify_kernel(const uint64_t* __restrict__ lists, int n_lists, int64_t nq /* rows per list block */,
+                                                                int W, int K, int64_t need, const int32_t* __restrict__ thr_limit,
+                                                                int in_smem, uint64_t* __restrict__ keys_out,
+                                                                uint32_t* __restrict__ fail_flags) {
+    extern __shared__ uint64_t sk[];  // [n_lists][W] for this query (in_smem)
+    __shared__ uint32_t s_fail;
+    __shared__ uint64_t s_kth;
+    const int64_t q = blockIdx.x;
+    if (threadIdx.x == 0) { s_fail = 0u; s_kth = ~0ull; }
+    for (int i = threadIdx.x; i < K; i += blockDim.x) keys_out[q * K + i] = ~0ull;
+    if (in_smem)
+        for (int i = threadIdx.x; i < n_lists * W; i += blockDim.x) {
+            const int g = i / W, j = i - g * W;
+            sk[i] = lists[((int64_t)g * nq + q) * W + j];
+        }
+    __syncthreads();
+    auto list_of = [&](int g) { return in_smem ? sk + g * W : lists + ((int64_t)g * nq + q) * W; };
+    for (int i = threadIdx.x; i < n_lists * W; i += blockDim.x) {
+        const int g = i / W, j = i - g * W;
+        const uint64_t key = list_of(g)[j];
+        if (key == TC_KEY_FAIL) { s_fail = 1u; continue; }
+        if (key == ~0ull) continue;  // padding
+        int rank = j;
+        for (int o = 0; o < n_lists && rank < K; ++o) {
+            if (o == g) continue;
+            const uint64_t* lst = list_of(o);
+            int lo = 0, hi = W;      // first position with lst[pos] >= key
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (lst[mid] < key) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < K) keys_out[q * K + rank] = key;
+        if (need > 0 && rank == (int)need - 1) s_kth = key;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bool fail = s_fail != 0u;
+        const uint64_t kth = s_kth;
+        if (need > 0 && (kth == ~0ull || (thr_limit != nullptr && (int)(uint32_t)(kth >> 33) > thr_limit[q]))) fail = true;
+        if (W < K)
+            for (int g = 0; g < n_lists && !fail; ++g) {
+                const uint64_t last = list_of(g)[W - 1];
+                if (last != ~0ull && last != TC_KEY_FAIL && last < kth) fail = true;   // the cut may have cost a key
+            }
+        fail_flags[q] = fail ? 1u : 0u;
+    }
+}
+
+// fail_count = number of flagged queries (flags identical on every rank after the all-gather); failed queries' keys -> pads
+__global__ void __launch_bounds__(256) tc_count_flags_kernel(const uint32_t* __restrict__ flags, int64_t n, uint32_t* __restrict__ count) {
+    uint32_t c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        c += flags[i] != 0u ? 1u : 0u;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
 }
 
 }  // namespace cmh
@@ -1106,9 +1208,14 @@ using namespace cmh;
 // so exactly one CTA - which owns the whole TMEM - is resident per SM.
 static int tc_T(int words) { return words == 1 ? 4 : 2; }
 static int tc_stages(int words) { return words == 1 ? 6 : 3; }
-static bool tc_workers() {       // experimental hit-worker variant of the kernel (CMH_TC_WORKERS=1); off by default
-    static const bool on = [] { const char* e = getenv("CMH_TC_WORKERS"); return e && e[0] == '1'; }();
-    return on;
+// CMH_TC_WORKERS=0 / 1 (or cmh_tc_set_workers) forces the draining-warp / hit-worker variant for every launch
+// (measurement aid; 64-bit codes); unset / -1: chosen per launch (tc_collect_launch)
+static int g_tc_workers_mode = [] { const char* e = getenv("CMH_TC_WORKERS"); return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1; }();
+static int tc_workers_mode() { return g_tc_workers_mode; }
+extern "C" int cmh_tc_set_workers(int mode) {
+    CMH_REQUIRE(mode >= -1 && mode <= 1, CMH_ERR_ARG, "cmh_tc_set_workers: mode=%d", mode);
+    g_tc_workers_mode = mode;
+    return CMH_OK;
 }
 static size_t tc_smem_bytes(int words) {
     const int st = tc_stages(words), T = tc_T(words);
@@ -1148,13 +1255,13 @@ extern "C" int cmh_tc_plan(int64_t nq, int64_t nd, int bits, int* n_chunks) {
     return CMH_OK;
 }
 
-static int tc_collect_impl(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits,
-                           int64_t index_base, const int32_t* thr, int K, int seg_base, int seg_total, int seg_cap,
-                           uint64_t* cand, uint32_t* cnt, uint32_t* aux, int probe, void* stream) {
+namespace cmh {
+int tc_collect_launch(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits, int64_t index_base,
+                      const int32_t* thr, int K, int seg_base, int seg_total, int seg_cap, uint64_t* cand, uint32_t* cnt,
+                      uint32_t* aux, int probe, bool skip_cnt_zero, cudaStream_t st) {
     CMH_REQUIRE(cmh_tc_supported(bits, 0), CMH_ERR_UNSUPPORTED, "cmh_tc_collect: bits=%d (64 or 128, +-1 codes only)", bits);
     CMH_REQUIRE(nq >= 0 && nd >= 0 && seg_cap >= 1 && K >= 0 && index_base >= 0 && index_base + nd <= (1ll << 32),
                 CMH_ERR_ARG, "cmh_tc_collect: bad sizes");
-    cudaStream_t st = (cudaStream_t)stream;
     if (nq == 0) return CMH_OK;
     int64_t n_qgroups, n_chunks, chunk_rows;
     tc_geometry(nq, nd, bits / 64, &n_qgroups, &n_chunks, &chunk_rows);
@@ -1167,9 +1274,10 @@ static int tc_collect_impl(const uint64_t* q_sign, int64_t nq, const uint64_t* d
                 "cmh_tc_collect: seg_total * seg_cap = %lld keys per query (must stay below 2^31)", (long long)seg_total * seg_cap);
     CMH_REQUIRE(q_sign && thr && cand && cnt && aux, CMH_ERR_ARG, "cmh_tc_collect: NULL pointer");
     static_assert(sizeof(TcAux) == 32, "cmh_tc_collect: aux is uint32 [nq][8]");
-    CMH_CUDA(cudaMemsetAsync(cnt + (size_t)seg_base * nq, 0, (size_t)n_segs * nq * 4, st));
-    CMH_CUDA(cudaMemsetAsync(aux, 0, (size_t)nq * sizeof(TcAux), st));
+    // every (segment, query) count of the launch is written by the kernel; only a launch without rows needs the memset
+    if (!skip_cnt_zero || nd == 0) CMH_CUDA(cudaMemsetAsync(cnt + (size_t)seg_base * nq, 0, (size_t)n_segs * nq * 4, st));
     if (nd == 0) return CMH_OK;
+    if (K > 0) CMH_CUDA(cudaMemsetAsync(aux, 0, (size_t)nq * sizeof(TcAux), st));   // the tightening counters of THIS launch
     CMH_REQUIRE(d_sign, CMH_ERR_ARG, "cmh_tc_collect: NULL database");
     CMH_REQUIRE(n_qgroups <= 0x7fffffffll && chunk_rows <= 0x7fffffff, CMH_ERR_UNSUPPORTED,
                 "cmh_tc_collect: launch geometry out of range");
@@ -1177,14 +1285,16 @@ static int tc_collect_impl(const uint64_t* q_sign, int64_t nq, const uint64_t* d
     a.q = q_sign; a.d = d_sign; a.thr = thr; a.cand = cand; a.cnt = cnt; a.aux = reinterpret_cast<TcAux*>(aux);
     a.nq = nq; a.nd = nd; a.index_base = index_base; a.chunk_rows = (int)chunk_rows; a.n_segs = seg_total;
     a.seg_base = seg_base; a.seg_cap = seg_cap; a.bits = bits; a.K = K; a.probe = probe; a.trace = g_tc_trace;
-    const size_t smem = tc_smem_bytes(words) + (tc_workers() ? (size_t)TC_WK_WORDS * 4 : 0);
+    // Which variant drains the hits (profiles/r02a: 8192 x 100M, 64-bit): the main launches (K > 0: thresholds close to the
+    // K-th distance, few hits) run 6 % faster with the hit workers - the draining warps only park - while the pilot launches
+    // (K = 0: loose thresholds, 20-30x the candidates) saturate the one worker per group and are faster with the warps
+    // working their own queues off.  128-bit codes: the worker state does not fit next to 2 x 64 KB of operands.
+    const bool workers = tc_workers_mode() == 1 || (tc_workers_mode() < 0 && words == 1 && K > 0 && !(probe & 128));
+    const size_t smem = tc_smem_bytes(words) + (workers ? (size_t)TC_WK_WORDS * 4 : 0);
     const dim3 grid((unsigned)n_qgroups, (unsigned)n_chunks);
-    if (tc_workers() && words == 1) {
+    if (workers && words == 1) {
         CMH_CUDA(cudaFuncSetAttribute(tc_collect_kernel<1, 4, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_collect_kernel<1, 4, 6, true><<<grid, TC_THREADS_WK, smem, st>>>(a);
-    } else if (tc_workers()) {
-        CMH_CUDA(cudaFuncSetAttribute(tc_collect_kernel<2, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_collect_kernel<2, 2, 3, true><<<grid, TC_THREADS_WK, smem, st>>>(a);
     } else if (words == 1) {
         CMH_CUDA(cudaFuncSetAttribute(tc_collect_kernel<1, 4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_collect_kernel<1, 4, 6><<<grid, TC_THREADS, smem, st>>>(a);
@@ -1195,20 +1305,87 @@ static int tc_collect_impl(const uint64_t* q_sign, int64_t nq, const uint64_t* d
     CMH_LAUNCH_CHECK("tc_collect_kernel");
     return CMH_OK;
 }
+}  // namespace cmh
 
 extern "C" int cmh_tc_collect(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits,
                               int64_t index_base, const int32_t* thr, int K, int seg_base, int seg_total, int seg_cap,
                               uint64_t* cand, uint32_t* cnt, uint32_t* aux, void* stream) {
-    return tc_collect_impl(q_sign, nq, d_sign, nd, bits, index_base, thr, K, seg_base, seg_total, seg_cap, cand, cnt, aux,
-                           0, stream);
+    return tc_collect_launch(q_sign, nq, d_sign, nd, bits, index_base, thr, K, seg_base, seg_total, seg_cap, cand, cnt, aux,
+                             0, false, (cudaStream_t)stream);
 }
 
 extern "C" int cmh_tc_probe(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits,
                             const int32_t* thr, int seg_total, int seg_cap, uint64_t* cand, uint32_t* cnt, uint32_t* aux,
                             int probe, void* stream) {
-    CMH_REQUIRE(probe >= 0 && probe < 128, CMH_ERR_ARG, "cmh_tc_probe: probe=%d", probe);
-    return tc_collect_impl(q_sign, nq, d_sign, nd, bits, 0, thr, 0, 0, seg_total, seg_cap, cand, cnt, aux, probe, stream);
+    CMH_REQUIRE(probe >= 0 && probe < 256, CMH_ERR_ARG, "cmh_tc_probe: probe=%d", probe);
+    // bit 8 (256 would collide): probes time the kernel of the MAIN launches (hit workers) unless bit 7 asks for the pilot's
+    return tc_collect_launch(q_sign, nq, d_sign, nd, bits, 0, thr, (probe & 128) ? 0 : 1000000000, 0, seg_total, seg_cap, cand, cnt,
+                             aux, probe, false, (cudaStream_t)stream);
 }
+
+namespace cmh {
+// histogram of the candidates in segments [seg_lo, seg_hi) and / or - `need` >= 0 - the threshold rule applied to it in
+// the same launch (hist / overflow may then be NULL)
+int tc_cand_hist_rule(const uint64_t* cand, const uint32_t* cnt, int64_t nq, int seg_lo, int seg_hi, int seg_total, int seg_cap,
+                      int nb, uint32_t* hist, uint32_t* overflow, double need, int offset, const int32_t* thr_in,
+                      int32_t* thr_out, cudaStream_t st) {
+    if (nq == 0) return CMH_OK;
+    const ChooseRule rule{need, offset, thr_in, thr_out};
+    tc_cand_hist_kernel<<<(unsigned)nq, CH_THREADS, 0, st>>>(cand, cnt, nq, seg_lo, seg_hi, seg_total, seg_cap, nb, hist, overflow, rule);
+    CMH_LAUNCH_CHECK("tc_cand_hist_kernel");
+    return CMH_OK;
+}
+int tc_choose_rule(const uint32_t* hist, const uint32_t* overflow, int64_t nq, int nb, double need, int offset,
+                   const int32_t* thr_in, int32_t* thr_out, cudaStream_t st) {
+    if (nq == 0) return CMH_OK;
+    tc_choose_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(hist, overflow, nq, nb, need, offset, thr_in, thr_out);
+    CMH_LAUNCH_CHECK("tc_choose_kernel");
+    return CMH_OK;
+}
+double tc_refine_need(int64_t n_seen, int64_t nd, int K, double sigma) {
+    const double kf = (double)K * (double)n_seen / (double)std::max<int64_t>(nd, 1);
+    return n_seen >= nd ? (double)std::min<int64_t>(K, nd) : kf + sigma * std::sqrt(kf) + 4.0;
+}
+int tc_sum_ranks(const uint32_t* every, int world, int rank, int64_t n, uint32_t* lower, uint32_t* seen, cudaStream_t st) {
+    if (n == 0) return CMH_OK;
+    tc_sum_ranks_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(every, world, rank, n, lower, seen);
+    CMH_LAUNCH_CHECK("tc_sum_ranks_kernel");
+    return CMH_OK;
+}
+int tc_count_flags(const uint32_t* flags, int64_t n, uint32_t* count, cudaStream_t st) {
+    CMH_CUDA(cudaMemsetAsync(count, 0, 4, st));
+    if (n == 0) return CMH_OK;
+    tc_count_flags_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), 64), 256, 0, st>>>(flags, n, count);
+    CMH_LAUNCH_CHECK("tc_count_flags_kernel");
+    return CMH_OK;
+}
+constexpr size_t TC_MERGE_SMEM_MAX = 200 * 1024;
+int tc_merge_verify(const uint64_t* lists, int n_lists, int64_t nq_lists, int64_t nq, int W, int K, int64_t nd_total,
+                    const int32_t* thr_limit, uint64_t* keys_out, uint32_t* fail_flags, cudaStream_t st) {
+    if (nq == 0) return CMH_OK;
+    const size_t smem = (size_t)n_lists * W * 8;
+    const int in_smem = smem <= TC_MERGE_SMEM_MAX ? 1 : 0;
+    if (in_smem) CMH_CUDA(cudaFuncSetAttribute(topk_merge_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_merge_verify_kernel<<<(unsigned)nq, 256, in_smem ? smem : 0, st>>>(lists, n_lists, nq_lists, W, K, std::min<int64_t>(K, nd_total),
+                                                                          thr_limit, in_smem, keys_out, fail_flags);
+    CMH_LAUNCH_CHECK("topk_merge_verify_kernel");
+    return CMH_OK;
+}
+int tc_finalize(const uint64_t* cand, const uint32_t* cnt, const int32_t* thr_limit, int64_t nq, int n_chunks, int seg_cap, int K,
+                int64_t nd, int partial, int width, uint64_t* keys, uint32_t* fail_flags, uint32_t* fail_count, cudaStream_t st) {
+    if (nq == 0) return CMH_OK;
+    CMH_CUDA(cudaMemsetAsync(fail_count, 0, 4, st));
+    topk_finalize_kernel<<<(unsigned)nq, FIN_THREADS, 0, st>>>(cand, cnt, partial ? nullptr : thr_limit, nq, n_chunks, seg_cap, K, nd,
+                                                              partial, width, keys, fail_flags, fail_count);
+    CMH_LAUNCH_CHECK("topk_finalize_kernel");
+    return CMH_OK;
+}
+int tc_geometry_segs(int64_t nq, int64_t nd, int bits) {
+    int64_t g, c, r;
+    tc_geometry(nq, nd, bits / 64, &g, &c, &r);
+    return (int)c * (TC_BUFS / tc_T(bits / 64));
+}
+}  // namespace cmh
 
 extern "C" int cmh_tc_cand_hist(const uint64_t* cand, const uint32_t* cnt, int64_t nq, int seg_lo, int seg_hi, int seg_total,
                                 int seg_cap, int nb, uint32_t* hist, uint32_t* overflow, void* stream) {
@@ -1217,10 +1394,8 @@ extern "C" int cmh_tc_cand_hist(const uint64_t* cand, const uint32_t* cnt, int64
     if (nq == 0) return CMH_OK;
     CMH_REQUIRE(cand && cnt && hist && overflow, CMH_ERR_ARG, "cmh_tc_cand_hist: NULL pointer");
     CMH_REQUIRE(nq <= 0x7fffffffll, CMH_ERR_UNSUPPORTED, "cmh_tc_cand_hist: too many queries per call");
-    tc_cand_hist_kernel<<<(unsigned)nq, CH_THREADS, 0, (cudaStream_t)stream>>>(cand, cnt, nq, seg_lo, seg_hi, seg_total, seg_cap, nb,
-                                                                       hist, overflow);
-    CMH_LAUNCH_CHECK("tc_cand_hist_kernel");
-    return CMH_OK;
+    return tc_cand_hist_rule(cand, cnt, nq, seg_lo, seg_hi, seg_total, seg_cap, nb, hist, overflow, -1.0, 0, nullptr, nullptr,
+                             (cudaStream_t)stream);
 }
 
 extern "C" int cmh_tc_choose(const uint32_t* hist, const uint32_t* overflow, int64_t nq, int nb, int64_t n_seen, int64_t nd,
@@ -1229,8 +1404,7 @@ extern "C" int cmh_tc_choose(const uint32_t* hist, const uint32_t* overflow, int
                 "cmh_tc_choose: bad sizes");
     if (nq == 0) return CMH_OK;
     CMH_REQUIRE(hist && thr_in && thr_out, CMH_ERR_ARG, "cmh_tc_choose: NULL pointer");
-    const double kf = (double)K * (double)n_seen / (double)std::max<int64_t>(nd, 1);
-    const double need = n_seen >= nd ? (double)std::min<int64_t>(K, nd) : kf + sigma * std::sqrt(kf) + 4.0;
+    const double need = tc_refine_need(n_seen, nd, K, sigma);
     tc_choose_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, (cudaStream_t)stream>>>(hist, overflow, nq, nb, need, 0, thr_in, thr_out);
     CMH_LAUNCH_CHECK("tc_choose_kernel");
     return CMH_OK;
@@ -1288,19 +1462,26 @@ extern "C" int cmh_topk_threshold(const uint32_t* hist, int64_t nq, int nb, int6
     return CMH_OK;
 }
 
-extern "C" int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, const uint32_t* aux, const int32_t* thr_limit,
-                                 int64_t nq, int n_chunks, int seg_cap, int K, int64_t nd, int partial, uint64_t* keys,
-                                 uint32_t* fail_flags, uint32_t* fail_count, void* stream) {
+extern "C" int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, const int32_t* thr_limit, int64_t nq, int n_chunks,
+                                 int seg_cap, int K, int64_t nd, int partial, int width, uint64_t* keys, uint32_t* fail_flags,
+                                 uint32_t* fail_count, void* stream) {
     CMH_REQUIRE(nq >= 0 && n_chunks >= 1 && seg_cap >= 1 && K >= 1 && nd >= 0, CMH_ERR_ARG, "cmh_topk_finalize: bad sizes");
     CMH_REQUIRE(K <= FIN_MAX, CMH_ERR_UNSUPPORTED, "cmh_topk_finalize: K=%d > %d", K, FIN_MAX);
+    CMH_REQUIRE(partial ? (width >= 1 && width <= K) : (width == K || width == 0), CMH_ERR_ARG,
+                "cmh_topk_finalize: width=%d (K for a whole database, 1..K for a shard)", width);
     if (nq == 0) return CMH_OK;
-    CMH_REQUIRE(cand && cnt && aux && keys && fail_flags && fail_count, CMH_ERR_ARG, "cmh_topk_finalize: NULL pointer");
+    CMH_REQUIRE(cand && cnt && keys && fail_flags && fail_count, CMH_ERR_ARG, "cmh_topk_finalize: NULL pointer");
     CMH_REQUIRE(nq <= 0x7fffffffll, CMH_ERR_UNSUPPORTED, "cmh_topk_finalize: too many queries per call");
-    cudaStream_t st = (cudaStream_t)stream;
-    CMH_CUDA(cudaMemsetAsync(fail_count, 0, 4, st));
-    topk_finalize_kernel<<<(unsigned)nq, FIN_THREADS, 0, st>>>(cand, cnt, reinterpret_cast<const TcAux*>(aux),
-                                                              partial ? nullptr : thr_limit, nq, n_chunks, seg_cap, K, nd,
-                                                              partial, keys, fail_flags, fail_count);
-    CMH_LAUNCH_CHECK("topk_finalize_kernel");
-    return CMH_OK;
+    return tc_finalize(cand, cnt, thr_limit, nq, n_chunks, seg_cap, K, nd, partial, partial ? width : K, keys, fail_flags,
+                       fail_count, (cudaStream_t)stream);
+}
+
+extern "C" int cmh_topk_merge_verify(const uint64_t* lists, int n_lists, int64_t nq, int width, int K, int64_t nd_total,
+                                     const int32_t* thr_limit, uint64_t* keys, uint32_t* fail_flags, void* stream) {
+    CMH_REQUIRE(n_lists >= 1 && nq >= 0 && width >= 1 && K >= 1 && width <= K && nd_total >= 0, CMH_ERR_ARG,
+                "cmh_topk_merge_verify: bad sizes");
+    if (nq == 0) return CMH_OK;
+    CMH_REQUIRE(lists && keys && fail_flags, CMH_ERR_ARG, "cmh_topk_merge_verify: NULL pointer");
+    CMH_REQUIRE(nq <= 0x7fffffffll, CMH_ERR_UNSUPPORTED, "cmh_topk_merge_verify: too many queries per call");
+    return tc_merge_verify(lists, n_lists, nq, nq, width, K, nd_total, thr_limit, keys, fail_flags, (cudaStream_t)stream);
 }

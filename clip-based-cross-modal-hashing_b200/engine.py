@@ -372,16 +372,6 @@ def topk_exact(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, stripes=
 TC_DEFAULT_CAP = 16384      # candidate slots per query and launch, split evenly over the launch's segments
 TC_MIN_SEG = 64
 TC_MAX_K = 4096
-TC_PILOT_MIN_ROWS = 8_000_000     # databases at least this long get a pilot launch over their first rows
-TC_PILOT_FRACTIONS = (64,)        # ... the first 1/64 of the rows, followed by a refinement of the thresholds (measured
-                                  # optimum; a further stage at 1/8 gains nothing: the main launches tighten by themselves)
-TC_PILOT_EARLY = 512              # shards of at least TC_PILOT_EARLY_MIN_ROWS refine once more, after 1/512 of their rows:
-TC_PILOT_EARLY_MIN_ROWS = 64_000_000   # the sample's thresholds are loose (K f < 1 sample rows at the K-th distance) and
-                                  # the 1/64 pilot at those costs 1.8 ms per 8192 queries on 100M rows; two stages 1.2 ms
-TC_PILOT_SIGMA = 5.0
-TC_PREFIX_MIN_ROWS = 4_000_000    # shards at least this long apply the prefix rule ...
-TC_PREFIX_FRACTIONS = (0.3, 0.5, 0.7, 0.85)   # ... after these fractions of their rows (swept: 43.1 ms against 50.5 without)
-TC_PREFIX_FRACTIONS_SHARDED = (0.3, 0.6)      # ... of every shard's rows when the database is sharded (each cut is an all-gather)
 
 
 def tc_supported(q: PackedSet, d: PackedSet, K: int = 1) -> bool:
@@ -390,9 +380,9 @@ def tc_supported(q: PackedSet, d: PackedSet, K: int = 1) -> bool:
 
 
 class TcBuffers:
-    """Device scratch of the `cmh_tc_collect` launches over the row ranges ``regions`` of one database: candidate
-    segments uint64 [nq][seg_total][seg_cap], per-segment counts uint32 [seg_total][nq], per-query bookkeeping
-    uint32 [nq][8].  ``seg_base[i]`` / ``n_segs[i]``: the segments launch i fills."""
+    """Device scratch of bare `cmh_tc_collect` launches (measurement aids and kernel-level tests; a search owns its
+    scratch through `cmh_tc_search_plan`): candidate segments uint64 [nq][seg_total][seg_cap], per-segment counts
+    uint32 [seg_total][nq], per-query bookkeeping uint32 [nq][8]."""
 
     def __init__(self, nq: int, regions: Sequence[int], bits: int, cap: int, device: torch.device,
                  seg_cap: Optional[int] = None):
@@ -409,310 +399,303 @@ class TcBuffers:
         self.cand = torch.empty((nq, self.seg_total, self.seg_cap), dtype=torch.int64, device=device)
         self.cnt = torch.empty((self.seg_total, nq), dtype=torch.int32, device=device)
         self.aux = torch.empty((nq, 8), dtype=torch.int32, device=device)
-        self.thr = torch.empty(nq, dtype=torch.int32, device=device)
-        self.thr2 = torch.empty(nq, dtype=torch.int32, device=device)
-        self.thr3 = torch.empty(nq, dtype=torch.int32, device=device)
-        self.thr4 = torch.empty(nq, dtype=torch.int32, device=device)
-        self.fail_flags = torch.empty(nq, dtype=torch.int32, device=device)
-        self.fail_count = torch.zeros(1, dtype=torch.int32, device=device)
-
-
-def tc_pilot_rows(nd: int) -> int:
-    """Rows scanned by the pilot launches (0 = none): a multiple of the 256-row tile."""
-    if nd < TC_PILOT_MIN_ROWS:
-        return 0
-    return (nd // TC_PILOT_FRACTIONS[-1]) // 256 * 256
 
 
 def tc_pilot_stages(nd: int, nd_total: int, world: int = 1) -> list:
-    """Cumulative row counts (multiples of the 256-row tile, ascending, < nd) after which the thresholds are refined.
-    The NUMBER of stages depends on the whole database and the number of shards only - every shard takes part in
-    every refinement."""
-    if nd_total < TC_PILOT_MIN_ROWS:
-        return []
-    fractions = TC_PILOT_FRACTIONS
-    if nd_total // max(1, int(world)) >= TC_PILOT_EARLY_MIN_ROWS:
-        fractions = (TC_PILOT_EARLY,) + tuple(fractions)
-    return [(nd // f) // 256 * 256 for f in fractions]
+    """Cumulative row counts (multiples of the 256-row tile) after which a search refines its thresholds
+    (`cmh_tc_pilot_stages`).  The NUMBER of stages depends on the whole database and the number of shards only."""
+    rows = (ctypes.c_int64 * _cabi.TC_MAX_STAGES)()
+    n = _cabi.lib().cmh_tc_pilot_stages(int(nd), int(nd_total), int(world), rows)
+    return [int(rows[i]) for i in range(n)]
+
+
+def tc_pilot_rows(nd: int) -> int:
+    """Rows scanned by the pilot launches of an unsharded database (0 = none)."""
+    st = tc_pilot_stages(nd, nd, 1)
+    return st[-1] if st else 0
 
 
 class LocalComm:
-    """The exchange steps of the tensor-core top-K for a database that lives on ONE GPU (no-ops).  `sharded.GroupComm`
-    is the `torch.distributed` version for a database sharded over the ranks of a process group."""
+    """A database that lives on ONE GPU: no exchange steps.  `sharded.GroupComm` spans the ranks of a
+    `torch.distributed` process group (NCCL transport inside the library)."""
     world = 1
     rank = 0
 
-    def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
-        return t
+    def handle(self):
+        return None
 
-    def all_reduce_max(self, t: torch.Tensor) -> torch.Tensor:
-        return t
 
-    def all_gather_stack(self, t: torch.Tensor) -> torch.Tensor:
-        return t.unsqueeze(0)
+class _DevBytes:
+    """A device pointer as something `torch.as_tensor` accepts (callback transports only)."""
 
-    def all_to_all(self, t: torch.Tensor) -> torch.Tensor:
-        return t
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class CallbackComm:
+    """`cmh_comm` filled with Python functions: wraps any object with ``rank``, ``world``, ``all_reduce_sum(t)``,
+    ``all_reduce_max(t)``, ``all_gather_stack(t)`` and ``all_to_all(t)`` (tensors in, tensors out) as the library's
+    transport.  This is the bring-your-own-transport form of the C ABI; the tests drive several shards of one GPU
+    through it with a barrier-based double.  The functions run on the caller's thread, on torch's current stream."""
+
+    def __init__(self, comm, device: torch.device):
+        self.comm, self.device, self.error = comm, device, None
+        self.rank, self.world = int(comm.rank), int(comm.world)
+
+        def view(ptr, nbytes, dtype=torch.uint8):
+            return torch.as_tensor(_DevBytes(ptr, nbytes), device=self.device).view(dtype)
+
+        def guard(fn):
+            def run(*a):
+                try:
+                    fn(*a)
+                    return 0
+                except BaseException as e:  # noqa: BLE001 - reported through the C ABI's return code
+                    self.error = e
+                    return 1
+            return run
+
+        def all_reduce(_ctx, buf, count, op, _stream):
+            t = view(buf, count * 4, torch.int32)
+            t.copy_(self.comm.all_reduce_max(t.clone()) if op == 1 else self.comm.all_reduce_sum(t.clone()))
+
+        def all_gather(_ctx, send, recv, nbytes, _stream):
+            got = self.comm.all_gather_stack(view(send, nbytes).clone())
+            view(recv, nbytes * self.world).copy_(got.reshape(-1))
+
+        def all_to_all(_ctx, send, recv, nbytes, _stream):
+            got = self.comm.all_to_all(view(send, nbytes * self.world).clone().view(self.world, nbytes))
+            view(recv, nbytes * self.world).copy_(got.reshape(-1))
+
+        self._fns = (_cabi.COMM_ALL_REDUCE(guard(all_reduce)), _cabi.COMM_ALL_GATHER(guard(all_gather)),
+                     _cabi.COMM_ALL_TO_ALL(guard(all_to_all)))
+        self.struct = _cabi.Comm(None, self.rank, self.world, *self._fns)
+
+    def handle(self):
+        return ctypes.pointer(self.struct)
+
+
+def _comm_handle(comm, device):
+    """(ctypes pointer to a `cmh_comm` or None, the object that must stay alive while it is used)"""
+    if comm is None:
+        return None, None
+    if hasattr(comm, "handle"):
+        return comm.handle(), comm
+    cb = CallbackComm(comm, device)
+    return cb.handle(), cb
+
+
+class TcSearchPlan:
+    """`cmh_tc_search` + its device scratch (+ optional timing handle) for one (queries per call, shard) geometry."""
+
+    def __init__(self, plan: "_cabi.TcSearch", device: torch.device):
+        self.plan = plan
+        self.device = device
+        self.workspace = torch.empty(max(1, int(plan.workspace_bytes)), dtype=torch.uint8, device=device)
+        self._timing = None
+
+    def timing(self):
+        if self._timing is None:
+            h = ctypes.c_void_p()
+            with torch.cuda.device(self.device):
+                check(_cabi.lib().cmh_tc_timing_create(ctypes.byref(h)), "cmh_tc_timing_create")
+            self._timing = h
+        return self._timing
+
+    def read_timing(self):
+        ph = (ctypes.c_float * _cabi.TC_PHASES)()
+        col, n = ctypes.c_float(0), ctypes.c_int(0)
+        check(_cabi.lib().cmh_tc_timing_read(self._timing, ph, ctypes.byref(col), ctypes.byref(n)), "cmh_tc_timing_read")
+        return {name: float(ph[i]) for i, name in enumerate(_cabi.TC_PHASE_NAMES)}, float(col.value), int(n.value)
+
+    def launch_ms(self) -> list:
+        """Device time of each tc_collect launch of the last timed search."""
+        ms = (ctypes.c_float * _cabi.TC_MAX_SPANS)()
+        check(_cabi.lib().cmh_tc_timing_launches(self._timing, ms, _cabi.TC_MAX_SPANS), "cmh_tc_timing_launches")
+        n = sum(1 for i in range(self.plan.n_spans) if self.plan.span_hi[i] > self.plan.span_lo[i])
+        return [float(ms[i]) for i in range(n)]
+
+    def _view(self, off: int, shape, dtype):
+        n = 1
+        for v in shape:
+            n *= int(v)
+        return self.workspace[off:off + n * dtype.itemsize].view(dtype).view(*shape)
+
+    @property
+    def cnt(self) -> torch.Tensor:
+        return self._view(int(self.plan.off_cnt), (self.plan.seg_total, self.plan.nq), torch.int32)
+
+    def thr(self, slot: int) -> torch.Tensor:
+        return self._view(int(self.plan.off_thr) + int(slot) * int(self.plan.nq) * 4, (self.plan.nq,), torch.int32)
+
+    def __del__(self):
+        if getattr(self, "_timing", None) is not None:
+            try:
+                _cabi.lib().cmh_tc_timing_destroy(self._timing)
+            except Exception:  # noqa: BLE001 - interpreter shutdown
+                pass
+
+
+def tc_search_plan(comm_handle, nq: int, nd: int, nd_total: int, bits: int, K: int, stripes, n_sample: int, *,
+                   pilot=None, prefix: bool = True, prefix_fractions=None, prefix_min_rows: Optional[int] = None,
+                   tighten: bool = True, cap: int = TC_DEFAULT_CAP, seg_cap: Optional[int] = None,
+                   exact_thresholds: bool = False, gather: bool = True, ready_rows=(), device=None) -> "_cabi.TcSearch":
+    """`cmh_tc_search_plan` (collective over the comm's ranks when it spans several)."""
+    L = _cabi.lib()
+    o = _cabi.TcOpts()
+    L.cmh_tc_default_opts(ctypes.byref(o))
+    if pilot is not None:
+        rows = [int(x) for x in (pilot if isinstance(pilot, (list, tuple)) else [pilot]) if int(x) > 0]
+        if len(rows) > _cabi.TC_MAX_STAGES:
+            raise ValueError(f"at most {_cabi.TC_MAX_STAGES} pilot stages")
+        o.n_pilot = len(rows)
+        for i, r in enumerate(rows):
+            o.pilot_rows[i] = r
+    o.prefix = 1 if prefix else 0
+    if prefix_fractions is not None:
+        fr = [float(f) for f in prefix_fractions]
+        if len(fr) > _cabi.TC_MAX_CUTS:
+            raise ValueError(f"at most {_cabi.TC_MAX_CUTS} prefix cuts")
+        o.n_prefix = len(fr)
+        for i, f in enumerate(fr):
+            o.prefix_frac[i] = f
+    if prefix_min_rows is not None:
+        o.prefix_min_rows = int(prefix_min_rows)
+    o.tighten = 1 if tighten else 0
+    o.cap = int(cap)
+    o.seg_cap = 0 if seg_cap is None else int(seg_cap)
+    o.exact_thresholds = 1 if exact_thresholds else 0
+    o.gather = 1 if gather else 0
+    ready_rows = [int(r) for r in ready_rows]
+    if len(ready_rows) > _cabi.TC_MAX_READY:
+        raise ValueError(f"at most {_cabi.TC_MAX_READY} upload ranges")
+    o.n_ready = len(ready_rows)
+    for i, r in enumerate(ready_rows):
+        o.ready_rows[i] = r
+    srow = (ctypes.c_int64 * len(stripes))(*[int(a) for a, _ in stripes])
+    sidx = (ctypes.c_int64 * len(stripes))(*[int(b) for _, b in stripes])
+    plan = _cabi.TcSearch()
+    import contextlib
+    with (torch.cuda.device(device) if device is not None else contextlib.nullcontext()):   # host arithmetic on one GPU
+        check(L.cmh_tc_search_plan(comm_handle, int(nq), int(nd), int(nd_total), int(bits), int(K), len(stripes), srow, sidx,
+                                   int(n_sample), ctypes.byref(o), ctypes.byref(plan)), "cmh_tc_search_plan")
+    return plan
 
 
 def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Optional[PackedSet] = None,
             cap: int = TC_DEFAULT_CAP, stats: Optional[dict] = None, tighten: bool = True,
-            seg_cap: Optional[int] = None, pilot: Optional[int] = None, comm=None, nd_total: Optional[int] = None,
+            seg_cap: Optional[int] = None, pilot=None, comm=None, nd_total: Optional[int] = None,
             exact_fallback=None, buffers: Optional[dict] = None, ready=None, defer: bool = False, prefix: bool = True,
-            stripes=None):
-    """int64 [nq, K] ascending keys, identical to ``RankPass(q, d).topk(K, index_base)`` (to the global stable
+            stripes=None, gather: bool = True, prefix_fractions=None, prefix_min_rows: Optional[int] = None):
+    """Top-``K`` keys on the tensor cores - `cmh_topk_tc`, one library call that owns the whole launch chain (sample
+    histogram -> thresholds -> pilot launches + refinement -> main launches with the exact prefix rule -> finalize ->
+    exchange).  int64 [nq, K] ascending keys, identical to ``RankPass(q, d).topk(K, index_base)`` (to the global stable
     ranking when ``d`` is one shard of a database of ``nd_total`` rows and ``comm`` spans the shards).
 
     sample  a subset of the rows of ``d`` (any rows, contiguous in memory) used only to guess the per-query
-            thresholds; None = use ``d`` itself (exact thresholds when unsharded, an extra popc pass)
-    pilot   cumulative row counts of the pilot launches (None = `tc_pilot_stages`; an int = one stage): the rows up
-            to each count are scanned with the thresholds known so far, and what they hold refines the thresholds
-            for the rest
-    comm    exchange steps (`LocalComm`, `sharded.GroupComm`): the sample / pilot histograms are all-reduced so that
-            every shard filters with the same global thresholds - a shard then contributes only its share of the ~K
-            rows below them; the per-shard results are exchanged all-to-all (rank r merges the r-th slice of the
-            queries: 1/N of the traffic and of the merge work of an all-gather) and the merged slices all-gathered
+            thresholds; None = a full popc histogram of ``d`` (exact thresholds; one GPU only)
+    pilot   cumulative row counts of the pilot launches (None = `tc_pilot_stages`; an int = one stage)
+    comm    `LocalComm` / `sharded.GroupComm` (NCCL inside the library) / any object with the exchange methods of
+            `CallbackComm`: every shard filters with the same global thresholds and contributes only its share of
+            the ~K rows below them; rank r merges and verifies the r-th slice of the queries
+    gather  sharded: True = every rank returns all [nq, K] keys; False = rank r returns ITS slice, int64 [per_rank, K] -
+            the keys of queries ``r * per_rank ...`` (per_rank = ceil(nq / world); rows past nq are pads)
     ready   [(row_end, torch.cuda.Event), ...] in row order: rows below row_end of ``d`` are valid once the event has
-            completed (a database that is still being uploaded on another stream); the scan is cut at those
-            boundaries and every launch waits only for the rows it reads
-    prefix  apply the prefix rule (`cmh_tc_choose_prefix` / `cmh_tc_choose_seen`) at `TC_PREFIX_FRACTIONS` of the rows:
-            exact; sharded databases all-gather the candidate histograms of the rows scanned so far at each cut
-    stripes ``[(local_row, global_index), ...]`` (`check_stripes`): the shard is several row ranges of the database
-            instead of one (``index_base`` is then ignored).  With ``comm`` spanning several shards the stripes must be
-            LOCKSTEP stripes - the same number on every shard, stripe j of every shard below stripe j+1 of every shard
-            in global index: the prefix rule is then applied at the stripe boundaries on the all-reduced histograms,
-            with everything scanned so far (on any shard) of lower index than everything still to come, as on one GPU
+            completed (a database that is still being uploaded on another stream)
+    prefix  apply the exact prefix rule (at ``prefix_fractions`` of the shard's rows, default 0.3 / 0.5 / 0.7 / 0.85 on
+            one GPU, 0.3 / 0.6 for contiguous shards; at the stripe boundaries for lockstep stripes)
+    stripes ``[(local_row, global_index), ...]`` (`check_stripes`); with a comm of several ranks they must be LOCKSTEP
+            stripes (`sharded.lockstep_stripes`)
     defer   return a callable instead of the keys: everything is enqueued, and calling it reads the verdict (a host
-            sync), redoes failed queries and returns the keys - lets a caller keep two query chunks in flight
-    buffers a dict the caller keeps between calls: the multi-GB candidate scratch is allocated once per query-chunk
-            size instead of per call
-    exact_fallback(sub_q) -> keys for the queries whose candidate lists came out short or overflowed (the exact
-            two-pass path; default: `RankPass.topk` on ``d``, which is only right when unsharded)"""
+            sync), redoes failed queries and returns the keys
+    buffers a dict the caller keeps between calls: plan + multi-GB candidate scratch are made once per geometry
+    exact_fallback(sub_q) -> [n, K] global keys of the queries whose candidate lists came out short or overflowed"""
     if not tc_supported(q, d, K):
         raise ValueError("tensor-core top-K needs +-1 codes of 64 or 128 bits and K <= 4096")
-    comm = LocalComm() if comm is None else comm
     K = int(K)
     dev = q.device
     nq = q.n
+    world = 1 if comm is None else int(comm.world)
+    rank = 0 if comm is None else int(comm.rank)
     nd_total = d.n if nd_total is None else int(nd_total)
-    per_rank = -(-nq // comm.world)                  # queries merged by each rank (the last slice may be padded)
-    keys_all = torch.empty((per_rank * comm.world, K), dtype=torch.int64, device=dev)
-    keys = keys_all[:nq]
+    per_rank = -(-nq // world)
+    sliced = world > 1 and not gather
     if nq == 0 or nd_total == 0:
-        if nq and nd_total == 0:
-            keys.fill_(-1)
-        done = keys
+        done = torch.full((per_rank if sliced else nq, K), -1, dtype=torch.int64, device=dev)
         return (lambda: done) if defer else done
-    if keys_all.shape[0] > nq:
-        keys_all[nq:].fill_(-1)
-    L = _cabi.lib()
-    nb = q.bits + 1
-    smp = d if sample is None else sample
-    # refinement stages: cumulative local row counts; the same number of stages on every shard
-    if pilot is None:
-        stages = tc_pilot_stages(d.n, nd_total, comm.world)
-    else:
-        stages = [int(x) for x in (pilot if isinstance(pilot, (list, tuple)) else [pilot]) if int(x) > 0]
-    if sample is None and comm.world == 1:
-        stages = []                                  # exact thresholds need no refinement
-    stages = [min(e, d.n) for e in stages]
-    ends = sorted({e for e in stages if 0 < e < d.n})
-    # the prefix rule (exact): after these rows the candidates so far bound what later rows can still contribute
-    # (every shard takes part in every exchange, so whether and how often is decided from the global sizes alone)
     stripes = check_stripes(stripes, d.n, index_base)
-    lockstep = comm.world > 1 and len(stripes) > 1
-    ascending = all(b[1] >= a[1] + (b[0] - a[0]) for a, b in zip(stripes, stripes[1:]))
-    prefix_cuts = []
-    if lockstep:
-        if prefix:
-            prefix_cuts = [lo for lo, _ in stripes[1:]]
-    elif prefix and ascending and -(-nd_total // comm.world) >= TC_PREFIX_MIN_ROWS:
-        fractions = TC_PREFIX_FRACTIONS if comm.world == 1 else TC_PREFIX_FRACTIONS_SHARDED
-        prefix_cuts = [min(d.n, int(d.n * f) // 256 * 256) for f in fractions]
-    prefix_ends = {e for e in prefix_cuts if (stages[-1] if stages else 0) < e < d.n}
-    cuts = sorted({0, d.n} | set(ends) | prefix_ends | {int(e) for e, _ in (ready or ()) if 0 < int(e) < d.n} |
-                  {lo for lo, _ in stripes if 0 < lo < d.n})
-
-    def global_index(row: int) -> int:               # of a local row (spans never straddle a stripe boundary)
-        lo, g = [st_ for st_ in stripes if st_[0] <= row][-1]
-        return g + (row - lo)
-    spans = [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]] or [(0, 0)]
-    regions = [hi - lo for lo, hi in spans]
-
-    def wait_rows(hi: int) -> None:
-        for end, ev in (ready or ()):
-            if int(end) >= hi:
-                torch.cuda.current_stream(dev).wait_event(ev)
-                return
-
-    bkey = (nq, tuple(regions), q.bits, int(cap), seg_cap, str(dev))
-    b = buffers.get(bkey) if buffers is not None else None
-    if b is None:
-        b = TcBuffers(nq, regions, q.bits, cap, dev, seg_cap)
+    exact_thr = sample is None
+    if exact_thr and world > 1:
+        raise ValueError("a sharded tensor-core top-K needs a sample of every shard")
+    n_sample = 0 if exact_thr else sample.n
+    ready = list(ready or ())
+    handle, keep = _comm_handle(comm, dev)
+    key = (nq, d.n, nd_total, q.bits, K, tuple(stripes), n_sample, exact_thr,
+           None if pilot is None else tuple(pilot) if isinstance(pilot, (list, tuple)) else int(pilot), bool(prefix),
+           None if prefix_fractions is None else tuple(prefix_fractions), prefix_min_rows, bool(tighten), int(cap), seg_cap,
+           bool(gather), tuple(int(e) for e, _ in ready), world, rank, str(dev))
+    sp = buffers.get(key) if buffers is not None else None
+    if sp is None:
+        plan = tc_search_plan(handle, nq, d.n, nd_total, q.bits, K, stripes, n_sample, pilot=pilot, prefix=prefix,
+                              prefix_fractions=prefix_fractions, prefix_min_rows=prefix_min_rows, tighten=tighten, cap=cap,
+                              seg_cap=seg_cap, exact_thresholds=exact_thr, gather=gather,
+                              ready_rows=[e for e, _ in ready], device=dev)
         if buffers is not None:
             buffers.clear()                          # one geometry at a time: the scratch is large
-            buffers[bkey] = b
-    if comm.world > 1:
-        ckey = ("counts", smp.n, tuple(stages))
-        got = buffers.get(ckey) if buffers is not None else None
-        if got is None:
-            counts = comm.all_reduce_sum(torch.tensor([smp.n] + stages, dtype=torch.int64, device=dev))
-            got = tuple(int(v) for v in counts.tolist())
-            if buffers is not None:
-                buffers[ckey] = got
-        n_sample_all, stages_all = got[0], list(got[1:])
-    else:
-        n_sample_all, stages_all = smp.n, list(stages)
-    if stats is not None and stats.get("time_phases"):
-        e = torch.cuda.Event(enable_timing=True)
-        e.record(torch.cuda.current_stream(dev))
-        stats.setdefault("phase_events", []).append(("start", e))
-    if smp.n:
-        h_all, _ = RankPass(q.with_labels(None, 0), smp.with_labels(None, 0), need_labels=False).hist()
-    else:
-        h_all = torch.zeros((nq, nb), dtype=torch.int32, device=dev)
-    h_all = comm.all_reduce_sum(h_all)
+        sp = TcSearchPlan(plan, dev)
+        if buffers is not None:
+            buffers[key] = sp
+    p = sp.plan
+    keys = torch.empty((per_rank if sliced else (per_rank * world if world > 1 else nq), K), dtype=torch.int64, device=dev)
+    fail_flags = torch.empty(per_rank * world, dtype=torch.int32, device=dev)
+    fail_count = torch.empty(1, dtype=torch.int32, device=dev)
+    timed = stats is not None and (stats.get("time_phases") or stats.get("time_collect"))
+    events = None
+    if ready:
+        events = (ctypes.c_void_p * len(ready))(*[ctypes.c_void_p(ev.cuda_event) for _, ev in ready])
     with torch.cuda.device(dev):
-        st = _stream(dev)
-        check(L.cmh_topk_threshold(_ptr(h_all), nq, nb, n_sample_all, nd_total, K, _ptr(b.thr), st), "cmh_topk_threshold")
-        timed = stats is not None and stats.get("time_collect")
-
-        def mark():
-            if timed:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record(torch.cuda.current_stream(dev))
-                stats.setdefault("collect_events", []).append(e)
-
-        def phase(name):
-            if stats is not None and stats.get("time_phases"):
-                e = torch.cuda.Event(enable_timing=True)
-                e.record(torch.cuda.current_stream(dev))
-                stats.setdefault("phase_events", []).append((name, e))
-
-        phase("thresholds_done")
-        thr_cur, thr_next = b.thr, b.thr2
-        thr_limit = None
-        last_stage = stages[-1] if stages else 0
-        si = 0                                       # next stage to close
-        launched = False
-
-        def refine_upto(i_stage: int, seg_hi: int):
-            # the candidates of the rows scanned so far (kept at thresholds >= the current ones): exact counts of
-            # every bucket at or below the current threshold; all-reduced over the shards
-            nonlocal thr_cur, thr_next
-            ph = torch.zeros((nq, nb), dtype=torch.int32, device=dev)
-            over = torch.zeros(nq, dtype=torch.int32, device=dev)
-            if seg_hi > 0:
-                check(L.cmh_tc_cand_hist(_ptr(b.cand), _ptr(b.cnt), nq, 0, seg_hi, b.seg_total, b.seg_cap, nb, _ptr(ph),
-                                         _ptr(over), st), "cmh_tc_cand_hist")
-            ph, over = comm.all_reduce_sum(ph), comm.all_reduce_max(over)
-            check(L.cmh_tc_choose(_ptr(ph), _ptr(over), nq, nb, stages_all[i_stage], nd_total, K, TC_PILOT_SIGMA,
-                                  _ptr(thr_cur), _ptr(thr_next), st), "cmh_tc_choose")
-            thr_cur, thr_next = thr_next, thr_cur
-
-        def prefix_upto(seg_hi: int):
-            # The prefix rule (exact, no statistics).  K candidates at dist <= b among rows of LOWER index than what is
-            # still to be scanned (this shard's rows so far + the same prefix of every lower-ranked shard): later rows
-            # only matter below b.  K candidates at dist <= b ANYWHERE among the rows scanned so far (all shards):
-            # later rows only matter at or below b.  One all-gather of the per-shard histograms serves both.
-            nonlocal thr_cur, thr_limit
-            if thr_limit is None:
-                thr_limit = thr_cur                  # the statistical bound, the same on every shard
-            ph = torch.zeros((nq, nb), dtype=torch.int32, device=dev)
-            over = torch.zeros(nq, dtype=torch.int32, device=dev)
-            if seg_hi > 0:
-                check(L.cmh_tc_cand_hist(_ptr(b.cand), _ptr(b.cnt), nq, 0, seg_hi, b.seg_total, b.seg_cap, nb, _ptr(ph),
-                                         _ptr(over), st), "cmh_tc_cand_hist")
-            out = b.thr3 if thr_cur is not b.thr3 else b.thr4
-            if lockstep:
-                # lockstep stripes: whatever any shard has scanned lies below whatever any shard has still to scan
-                ph = comm.all_reduce_sum(ph)
-                check(L.cmh_tc_choose_prefix(_ptr(ph), None, nq, nb, K, _ptr(thr_cur), _ptr(out), st), "cmh_tc_choose_prefix")
-            elif comm.world > 1:
-                every = comm.all_gather_stack(ph)                                    # [world, nq, nb]
-                lower = every[:comm.rank + 1].sum(0, dtype=torch.int32).contiguous()
-                seen = every.sum(0, dtype=torch.int32).contiguous()
-                check(L.cmh_tc_choose_prefix(_ptr(lower), None, nq, nb, K, _ptr(thr_cur), _ptr(out), st), "cmh_tc_choose_prefix")
-                check(L.cmh_tc_choose_seen(_ptr(seen), None, nq, nb, K, _ptr(out), _ptr(out), st), "cmh_tc_choose_seen")
-            else:
-                check(L.cmh_tc_choose_prefix(_ptr(ph), _ptr(over), nq, nb, K, _ptr(thr_cur), _ptr(out), st), "cmh_tc_choose_prefix")
-            thr_cur = out
-
-        pj = 0                                       # next prefix exchange
-
-        def close(hi: int, seg_hi: int):
-            # exchanges due once the rows below `hi` have been scanned: the pilot stages, then - never before the last
-            # stage, so that the order is the same on every shard - the prefix rule.  A shard that has no rows at a
-            # cut (a short or empty shard) still takes part.
-            nonlocal si, pj
-            while si < len(stages) and stages[si] <= hi:
-                if stages_all[si] > 0:
-                    refine_upto(si, seg_hi)
-                si += 1
-                phase("pilot_done")
-            while si == len(stages) and pj < len(prefix_cuts) and prefix_cuts[pj] <= hi:
-                prefix_upto(seg_hi)
-                pj += 1
-
-        close(0, 0)
-        for i, (lo, hi) in enumerate(spans):
-            if hi <= lo:
-                continue
-            in_pilot = hi <= last_stage              # pilot spans keep EVERY row at or below the threshold (K = 0)
-            if not in_pilot and thr_limit is None:
-                thr_limit = thr_cur                  # the statistical bound; later (prefix) thresholds are exact exclusions
-            wait_rows(hi)
-            mark()
-            # tightening (main spans) uses this launch's own counts: K rows found locally are K rows found globally
-            check(L.cmh_tc_collect(_ptr(q.sign), nq, _ptr(d.sign[lo:]), hi - lo, q.bits, global_index(lo),
-                                   _ptr(thr_cur), 0 if in_pilot or not tighten else K, b.seg_base[i], b.seg_total,
-                                   b.seg_cap, _ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), st), "cmh_tc_collect")
-            mark()
-            launched = True
-            if hi < d.n:                             # after the last row there is nothing left to tighten for
-                close(hi, b.seg_base[i] + b.n_segs[i])
-        close(d.n, b.seg_total if launched else 0)
-        if not launched:
-            b.cnt.zero_()
-            b.aux.zero_()
-        thr_main = thr_limit if thr_limit is not None else thr_cur
-        phase("main_done")
-        partial = 1 if comm.world > 1 else 0
-        check(L.cmh_topk_finalize(_ptr(b.cand), _ptr(b.cnt), _ptr(b.aux), _ptr(thr_main), nq, b.seg_total, b.seg_cap, K,
-                                  nd_total, partial, _ptr(keys), _ptr(b.fail_flags), _ptr(b.fail_count), st),
-              "cmh_topk_finalize")
-        phase("finalize_done")
-        if comm.world > 1:
-            mine = topk_merge(comm.all_to_all(keys_all.view(comm.world, per_rank, K)), K)     # [per_rank, K]
-            keys = comm.all_gather_stack(mine).view(per_rank * comm.world, K)[:nq]
-            b.fail_flags = comm.all_reduce_max(b.fail_flags)
-            check(L.cmh_topk_verify(_ptr(keys), _ptr(thr_main), nq, K, nd_total, _ptr(b.fail_flags), _ptr(b.fail_count),
-                                    st), "cmh_topk_verify")
-    phase("exchange_done")
-    # the verdict is read by `finish`: at once, or - `defer` - when the caller asks for the result, so that the next
-    # query chunk can be enqueued (on another stream) before this one has drained
-    fail_count = b.fail_count.clone() if defer else b.fail_count
-    fail_flags = b.fail_flags.clone() if defer else b.fail_flags
+        rc = _cabi.lib().cmh_topk_tc(ctypes.byref(p), handle, _ptr(q.sign), _ptr(d.sign) if d.n else None,
+                                     None if exact_thr or n_sample == 0 else _ptr(sample.sign), events, _ptr(keys),
+                                     _ptr(fail_flags), _ptr(fail_count), _ptr(sp.workspace),
+                                     sp.timing() if timed else None, _stream(dev))
+    if rc and getattr(keep, "error", None) is not None:
+        raise keep.error
+    check(rc, "cmh_topk_tc")
     if stats is not None:
-        stats["candidates"] = b.cnt.sum(0)
-        stats["thr"] = thr_main
-        stats["thr_final"] = thr_cur                 # after the prefix rule (differs between shards)
-        stats["pilot_rows"] = stages
+        stats["candidates"] = sp.cnt.sum(0)
+        stats["thr"] = sp.thr(p.thr_limit_slot).clone()
+        stats["thr_final"] = sp.thr(p.thr_final_slot).clone()      # after the prefix rule (differs between contiguous shards)
+        stats["pilot_rows"] = [int(p.stage_rows[i]) for i in range(p.n_stages)]
+        stats["n_launches"] = sum(1 for i in range(p.n_spans) if p.span_hi[i] > p.span_lo[i])
+        stats["exch_width"] = int(p.exch_width)
 
     def finish() -> torch.Tensor:
-        n_fail = int(fail_count.item())
+        n_fail = int(fail_count.item())              # the one host sync of a search
         if stats is not None:
             stats["n_fail"] = n_fail
+            if timed:
+                ph, col, n_col = sp.read_timing()
+                acc = stats.setdefault("phase_ms_sum", {})
+                for name, v in ph.items():
+                    acc[name] = acc.get(name, 0.0) + v
+                stats["collect_ms_sum"] = stats.get("collect_ms_sum", 0.0) + col
+                stats["n_collect"] = n_col
+                stats["launch_ms"] = sp.launch_ms()
+                stats["timed_searches"] = stats.get("timed_searches", 0) + 1
         if n_fail:
-            rows = torch.nonzero(fail_flags, as_tuple=False).squeeze(1)
+            rows = torch.nonzero(fail_flags[:nq], as_tuple=False).squeeze(1)
             sub = PackedSet(q.sign.index_select(0, rows).contiguous(), None, None, int(rows.numel()), q.bits)
             if exact_fallback is None:
-                if comm.world > 1:
+                if world > 1:
                     raise RuntimeError("a sharded tensor-core top-K needs exact_fallback")
                 redo = topk_exact(sub, d, K, index_base, stripes)
             else:
                 redo = exact_fallback(sub)
-            keys.index_copy_(0, rows, redo)
-        return keys
+            if sliced:
+                mine = (rows >= rank * per_rank) & (rows < (rank + 1) * per_rank)
+                keys.index_copy_(0, rows[mine] - rank * per_rank, redo[mine])
+            else:
+                keys.index_copy_(0, rows, redo)
+        return keys if sliced else keys[:nq]
 
     return finish if defer else finish()

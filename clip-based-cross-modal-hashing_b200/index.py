@@ -53,7 +53,9 @@ class HammingIndex:
     SAMPLE_ROWS = 65_536
 
     def __init__(self, db: PackedSet, index_base: int = 0, group=None, nd_total: Optional[int] = None,
-                 sample: Optional[PackedSet] = None, ready=None, stripes=None):
+                 sample: Optional[PackedSet] = None, ready=None, stripes=None, assume_binary: bool = False):
+        # assume_binary: the caller guarantees +-1 codes of the same length on EVERY shard (`from_packed*`): the
+        # constructor then needs no collective and no host sync when nd_total is given
         self._ready = ready                      # [(row_end, event)]: an upload still in flight (`from_packed_host`)
         # a shard made of several row ranges of the database (`sharded.lockstep_stripes`): [(local_row, global_index)]
         self.stripes = _e.check_stripes(stripes, db.n, index_base) if stripes else None
@@ -76,7 +78,7 @@ class HammingIndex:
         self.nd_total = int(nd_total)
         # every rank must take the same path: the tensor cores need +-1 codes (no valid plane) on ALL shards
         tc_ok = db.valid is None and _e.tc_supported(db, db)
-        if distributed:
+        if distributed and not assume_binary:
             t = torch.tensor([1 if tc_ok else 0], dtype=torch.int64, device=db.device)
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=group)
             tc_ok = bool(int(t.item()))
@@ -107,7 +109,7 @@ class HammingIndex:
         if not words.is_cuda:
             raise RuntimeError("packed database must be on a CUDA device")
         return cls(PackedSet(words.contiguous().view(torch.int64), None, None, words.shape[0], bits), index_base, group,
-                   nd_total, stripes=stripes)
+                   nd_total, stripes=stripes, assume_binary=nd_total is not None)
 
     @classmethod
     def from_packed_host(cls, words: torch.Tensor, bits: int, index_base: int = 0, group=None,
@@ -128,16 +130,17 @@ class HammingIndex:
         if tuple(dst.shape) != (n, nwords) or dst.dtype != torch.int64 or dst.data_ptr() % 16:
             raise ValueError("out must be a 16-byte aligned int64 [D, words] device tensor")
         words = words.view(torch.int64)
-        # the threshold sample comes from the host copy (a strided gather of ~64K rows), not from rows in flight
         total = n if nd_total is None else int(nd_total)
-        share = max(4096, cls.SAMPLE_ROWS * max(n, 1) // max(total, 1))
-        smp_rows = words[::max(1, n // share)].contiguous()
-        sample = PackedSet(smp_rows.to(dev, non_blocking=True), None, None, smp_rows.shape[0], bits)
         copy_stream = torch.cuda.Stream(dev)
         copy_stream.wait_stream(torch.cuda.current_stream(dev))      # `out` may still be read by earlier work
-        n_pilot = _e.tc_pilot_rows(n)
-        ends = sorted({e for e in ([n_pilot] if n_pilot else []) +
-                       [n_pilot + (n - n_pilot) * (i + 1) // pieces // 256 * 256 for i in range(pieces - 1)] + [n]
+        world = 1
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            world = torch.distributed.get_world_size(group)
+        stages = _e.tc_pilot_stages(n, total, world)
+        n_pilot = stages[-1] if stages else 0
+        first = n_pilot if n_pilot else min(n, max(4096, n // 64) // 256 * 256 or n)
+        ends = sorted({e for e in [first] +
+                       [first + (n - first) * (i + 1) // pieces // 256 * 256 for i in range(pieces - 1)] + [n]
                        if 0 < e <= n})
         ready, lo = [], 0
         with torch.cuda.stream(copy_stream):
@@ -147,23 +150,52 @@ class HammingIndex:
                 ev.record(copy_stream)
                 ready.append((hi, ev))
                 lo = hi
+        # the threshold sample is a strided gather of the FIRST range once it has landed (no host-side pass over the
+        # database): ~SAMPLE_ROWS rows of the whole database, this shard's share of them.  Any subset of the shard's rows
+        # is a valid sample - thresholds are only statistical bounds, exactness never depends on them.
+        share = max(4096, cls.SAMPLE_ROWS * max(n, 1) // max(total, 1))
+        head = ends[0] if ends else 0
+        cur = torch.cuda.current_stream(dev)
+        if ready:
+            cur.wait_event(ready[0][1])
+        smp_rows = dst[:head:max(1, head // share)].contiguous() if head else dst[:0]
+        sample = PackedSet(smp_rows, None, None, smp_rows.shape[0], bits)
         return cls(PackedSet(dst, None, None, n, bits), index_base, group, nd_total, sample=sample, ready=ready,
-                   stripes=stripes)
+                   stripes=stripes, assume_binary=nd_total is not None)
 
     def _upload_done(self) -> None:
         if self._ready:
             torch.cuda.current_stream(self.db.device).wait_event(self._ready[-1][1])
             self._ready = None
 
-    def search_packed(self, q: PackedSet, K: int, stats: Optional[dict] = None) -> torch.Tensor:
-        """int64 [Q, K] ascending keys ``(2*dist << 32) | global_row`` (-1 pads rows beyond the database)."""
+    def query_slice(self, nq: int):
+        """(first query, number of queries) of the slice this rank merges - the rows `search_packed(..., gather=False)`
+        returns on this rank."""
+        rank, world = _sh._world(self.group)
+        per_rank = -(-int(nq) // world)
+        lo = min(int(nq), rank * per_rank)
+        return lo, max(0, min(per_rank, int(nq) - lo))
+
+    def search_packed(self, q: PackedSet, K: int, stats: Optional[dict] = None, gather: bool = True) -> torch.Tensor:
+        """int64 [Q, K] ascending keys ``(2*dist << 32) | global_row`` (-1 pads rows beyond the database).
+        Sharded database, ``gather=False``: the result stays sharded by query slice - rank r returns
+        int64 [ceil(Q / world), K], the keys of the queries `query_slice` names (no all-gather of the merged keys)."""
         if self.sample is not None and q.valid is None and q.bits == self.db.bits and 1 <= int(K) <= _e.TC_MAX_K:
             ready, self._ready = self._ready, None       # only the first search can overlap the upload
             return _sh.topk_tc_sharded(q, self.db, int(K), self.index_base, self.nd_total, sample=self.sample,
                                        group=self.group, stats=stats, buffers=self._tc_buffers, ready=ready,
-                                       stripes=self.stripes)
+                                       stripes=self.stripes, gather=gather)
         self._upload_done()
-        return _sh.topk_sharded(q, self.db, int(K), self.index_base, self.group, ternary=None, stripes=self.stripes)
+        keys = _sh.topk_sharded(q, self.db, int(K), self.index_base, self.group, ternary=None, stripes=self.stripes)
+        if not gather:
+            rank, world = _sh._world(self.group)
+            if world > 1:
+                per_rank = -(-q.n // world)
+                out = torch.full((per_rank, int(K)), -1, dtype=torch.int64, device=keys.device)
+                lo, n = self.query_slice(q.n)
+                out[:n] = keys[lo:lo + n]
+                return out
+        return keys
 
     def search_packed_async(self, q: PackedSet, K: int, stats: Optional[dict] = None) -> "PendingSearch":
         """`search_packed` without waiting: the search is enqueued on one of two alternating side streams (each with

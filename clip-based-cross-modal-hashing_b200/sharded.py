@@ -110,12 +110,51 @@ def map_k_sharded(q, d_shard, k: Optional[int], nd_total: int, topn: Sequence[in
     return {"map": m, "ap": ap, "n_rel": n_rel, "prec": prec, "pr": pr}
 
 
+_NATIVE = {}      # process group -> (ctypes pointer to the library's NCCL cmh_comm, rank, world)
+
+
+def native_comm(group=None):
+    """The library's own NCCL transport (`cmh_comm_create_rank`) over the ranks of ``group``: rank 0 draws the NCCL
+    unique id, `torch.distributed` ships its 128 bytes, every rank joins on its current CUDA device.  Made once per
+    group and kept for the life of the process.  Collective."""
+    import ctypes
+    from . import _cabi
+    key = id(group) if group is not None else None
+    if key in _NATIVE:
+        return _NATIVE[key][0]
+    rank, world = _world(group)
+    L = _cabi.lib()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ident = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        buf = ctypes.create_string_buffer(128)
+        _cabi.check(L.cmh_comm_unique_id(buf), "cmh_comm_unique_id")
+        ident.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast(ident, src=src, group=group)
+    raw = bytes(ident.cpu().numpy().tobytes())
+    out = ctypes.POINTER(_cabi.Comm)()
+    _cabi.check(L.cmh_comm_create_rank(raw, world, rank, ctypes.byref(out)), "cmh_comm_create_rank")
+    _NATIVE[key] = (out, rank, world)
+    return out
+
+
 class GroupComm:
-    """The exchange steps of `engine.topk_tc` over the ranks of a process group (NCCL on GPUs)."""
+    """The ranks of a `torch.distributed` process group as the transport of the exchange steps.  On GPUs (NCCL backend)
+    `handle()` is the library's own NCCL communicator - the collectives are then issued by the C orchestrator
+    (`cmh_topk_tc`, `cmh_map_k_sharded`) in line with its kernels; the tensor methods below serve the Python-level paths
+    (`map_k_sharded`, `topk_sharded`) and the gloo tests."""
 
     def __init__(self, group=None):
         self.group = group
         self.rank, self.world = _world(group)
+
+    def handle(self):
+        if self.world == 1:
+            return None
+        if dist.get_backend(self.group) != "nccl":
+            raise RuntimeError("the library's transport needs an NCCL process group (one rank per GPU)")
+        return native_comm(self.group)
 
     def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
         if self.world > 1:
@@ -145,6 +184,49 @@ class GroupComm:
         return out
 
 
+def map_k_sharded_native(q, d_shard, k: Optional[int], nd_total: int, topn: Sequence[int] = (), comm=None,
+                         want_pr: bool = False, ternary: Optional[bool] = None):
+    """`map_k_sharded` as ONE library call (`cmh_map_k_sharded`): the two counting passes and their exchange steps are
+    issued by the C ABI over ``comm`` (`GroupComm` -> the library's NCCL transport; None -> one shard).  Same result
+    dict."""
+    import ctypes
+    from . import _cabi
+    eng = _engine
+    L = _cabi.lib()
+    dev = q.device
+    tern = (q.valid is not None or d_shard.valid is not None) if ternary is None else bool(ternary)
+    if tern:
+        if q.valid is None:
+            q = eng.PackedSet(q.sign, eng._full_valid(q), q.labels, q.n, q.bits, q.nlab)
+        if d_shard.valid is None:
+            d_shard = eng.PackedSet(d_shard.sign, eng._full_valid(d_shard), d_shard.labels, d_shard.n, d_shard.bits, d_shard.nlab)
+    handle, keep = eng._comm_handle(comm, dev)
+    world = 1 if comm is None else int(comm.world)
+    topn = [int(t) for t in topn]
+    nq, bits = q.n, q.bits
+    nbytes = int(L.cmh_map_k_sharded_workspace_bytes(world, nq, d_shard.n, bits, q.nlab, 1 if tern else 0, len(topn)))
+    if nbytes == 0:
+        raise ValueError(f"cmh_map_k_sharded: cannot plan {nq} x {d_shard.n}, {bits} bits: {_cabi.last_error()}")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ap = torch.empty(nq, dtype=torch.float64, device=dev)
+    m = torch.zeros(1, dtype=torch.float32, device=dev)
+    n_rel = torch.zeros(nq, dtype=torch.int64, device=dev)
+    prec = torch.zeros(len(topn), dtype=torch.float32, device=dev) if topn else None
+    P = torch.zeros(bits + 1, dtype=torch.float32, device=dev) if want_pr else None
+    R = torch.zeros(bits + 1, dtype=torch.float32, device=dev) if want_pr else None
+    qs, ds = q.struct(), d_shard.struct()
+    with torch.cuda.device(dev):
+        rc = L.cmh_map_k_sharded(handle, ctypes.byref(qs), ctypes.byref(ds), bits, q.nlab, 1 if tern else 0,
+                                 -1 if k is None else int(k), int(nd_total), _cabi.i64_array(topn), len(topn), eng._ptr(ap),
+                                 eng._ptr(m), eng._ptr(n_rel), eng._ptr(prec), eng._ptr(P), eng._ptr(R), eng._ptr(ws), nbytes,
+                                 eng._stream(dev))
+    if rc and getattr(keep, "error", None) is not None:
+        raise keep.error
+    _cabi.check(rc, "cmh_map_k_sharded")
+    ap.record_stream(torch.cuda.current_stream(dev))
+    return {"map": m, "ap": ap, "n_rel": n_rel, "prec": prec, "pr": (P, R) if want_pr else None, "_ws": ws}
+
+
 def topk_sharded(q, d_shard, K: int, index_base: int, group=None, eng=_engine,
                  ternary: Optional[bool] = None, stripes=None) -> torch.Tensor:
     """Global top-``K`` keys int64 [Q, K] (ascending, ``-1`` pads) - identical on every rank.
@@ -164,12 +246,13 @@ def topk_sharded(q, d_shard, K: int, index_base: int, group=None, eng=_engine,
 
 def topk_tc_sharded(q, d_shard, K: int, index_base: int, nd_total: int, sample=None, group=None, eng=_engine,
                     stats: Optional[dict] = None, **kw) -> torch.Tensor:
-    """Global top-``K`` keys on the tensor cores (`engine.topk_tc`): the shards filter with the same global
-    thresholds (all-reduced sample and pilot histograms, a few KB per query chunk), so each contributes only its
-    share of the ~K rows below them; the per-shard results are all-gathered and merged, and the merged K-th key is
-    verified against the thresholds.  Queries that fail the check are redone by `topk_sharded` on every rank."""
+    """Global top-``K`` keys on the tensor cores (`engine.topk_tc` -> `cmh_topk_tc`): the shards filter with the same
+    global thresholds (all-reduced sample and pilot histograms), so each contributes only its share of the ~K rows below
+    them; the per-shard lists are exchanged all-to-all by query slice, merged and verified by the slice's rank.  Queries
+    that fail the check are redone by `topk_sharded` on every rank.  ``gather=False``: rank r returns only its slice."""
     comm = GroupComm(group)
     stripes = kw.get("stripes")
-    return eng.topk_tc(q, d_shard, K, index_base, sample=sample, comm=comm, nd_total=nd_total, stats=stats,
+    return eng.topk_tc(q, d_shard, K, index_base, sample=sample, comm=comm if comm.world > 1 else None, nd_total=nd_total,
+                       stats=stats,
                        exact_fallback=lambda sub: topk_sharded(sub, d_shard, K, index_base, group, eng, stripes=stripes),
                        **kw)

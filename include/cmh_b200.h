@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define CMH_ABI_VERSION 1
+#define CMH_ABI_VERSION 2
 
 #define CMH_OK 0
 #define CMH_ERR_ARG (-1)         /* NULL / negative size / inconsistent arguments            */
@@ -205,6 +205,9 @@ int cmh_tc_collect(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, i
  * not stored / parked slices dropped / flagged slices not parked).  Outputs are meaningless. */
 int cmh_tc_probe(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits, const int32_t* thr,
                  int seg_total, int seg_cap, uint64_t* cand, uint32_t* cnt, uint32_t* aux, int probe, void* stream);
+/* Measurement aid: which variant of the kernel drains the hits - 0 the draining warps work their own queues off, 1 hit
+ * workers (64-bit codes), -1 (default) chosen per launch: workers for the main launches of 64-bit codes. */
+int cmh_tc_set_workers(int mode);
 /* Thresholds from a pilot launch.  Step 1: hist (device uint32 [nq][nb], bucket = Hamming distance) of the candidates
  * in segments [seg_lo, seg_hi) - every row at or below thr_in[q] among the rows a K = 0 launch scanned - and
  * overflow[q] (device uint32 [nq]) = 1 when one of those segments lost entries.  A sharded database all-reduces the
@@ -234,20 +237,171 @@ int cmh_tc_choose_seen(const uint32_t* hist, const uint32_t* overflow, int64_t n
 int cmh_topk_threshold(const uint32_t* hist, int64_t nq, int nb, int64_t n_sample, int64_t nd, int K,
                        int32_t* thr, void* stream);
 /* Per query: K-th distance from the candidates' own histogram over all n_chunks (= seg_total) segments, sort of the
- * candidates at or below it, K smallest keys out (UINT64_MAX pads; K <= 4096).  thr_limit (device int32 [nq] or
+ * candidates at or below it, smallest keys out (UINT64_MAX pads; K <= 4096).  thr_limit (device int32 [nq] or
  * NULL): the smallest initial threshold any launch used for the query - buckets above it are incomplete.
- * partial = 0: the segments cover the whole nd-row database; fail_flags[q] (device uint32 [nq]) = 1 and *fail_count
- * (device uint32) incremented when a candidate segment overflowed, the query holds fewer than min(K, nd) candidates,
- * more than 4096 at or below the K-th distance, or its K-th distance lies above thr_limit: those queries must be
- * re-run through cmh_topk (exact path).  partial = 1: the segments cover one shard; whatever the query holds (up to K)
- * is emitted, only overflow fails, and the merged result is judged by cmh_topk_verify. */
-int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, const uint32_t* aux, const int32_t* thr_limit,
-                      int64_t nq, int n_chunks, int seg_cap, int K, int64_t nd, int partial, uint64_t* keys,
-                      uint32_t* fail_flags, uint32_t* fail_count, void* stream);
+ * partial = 0 (width = K): the segments cover the whole nd-row database; keys: device [nq][K]; fail_flags[q] (device
+ * uint32 [nq]) = 1 and *fail_count (device uint32) incremented when a candidate segment overflowed, the query holds fewer
+ * than min(K, nd) candidates, more than 4096 at or below the K-th distance, or its K-th distance lies above thr_limit:
+ * those queries must be re-run through cmh_topk (exact path).
+ * partial = 1: the segments cover one shard; the `width` (<= K) smallest keys the query holds are emitted (keys: device
+ * [nq][width]); only overflow fails - the list then starts with the marker UINT64_MAX - 1 - and the merged result is
+ * judged by cmh_topk_merge_verify. */
+int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, const int32_t* thr_limit, int64_t nq, int n_chunks,
+                      int seg_cap, int K, int64_t nd, int partial, int width, uint64_t* keys, uint32_t* fail_flags,
+                      uint32_t* fail_count, void* stream);
+/* Merge of per-shard lists (cmh_topk_finalize, partial = 1) + verdict, per query: lists: device uint64
+ * [n_lists][nq][width]; keys: device [nq][K] smallest; fail_flags[q] = 1 when a list carries the overflow marker, the
+ * min(K, nd_total)-th key is missing or lies above thr_limit[q] (an incomplete bucket; thr_limit may be NULL), or a list
+ * that arrived full (width < K) ends below the K-th key (the cut may have cost a row). */
+int cmh_topk_merge_verify(const uint64_t* lists, int n_lists, int64_t nq, int width, int K, int64_t nd_total,
+                          const int32_t* thr_limit, uint64_t* keys, uint32_t* fail_flags, void* stream);
 /* After the merge of per-shard results: fail_flags[q] |= the min(K, nd)-th key is a pad or its distance lies above
  * thr_limit[q] (an incomplete bucket); *fail_count = number of flagged queries. */
 int cmh_topk_verify(const uint64_t* keys, const int32_t* thr_limit, int64_t nq, int K, int64_t nd, uint32_t* fail_flags,
                     uint32_t* fail_count, void* stream);
+
+/* ---- multi-GPU transport --------------------------------------------------------------------------------------- */
+/* The exchange steps of the sharded paths (one exchange per metric) go through this table.  Either the
+ * built-in NCCL transport (cmh_comm_create / cmh_comm_create_rank; libnccl.so.2 is bound at run time with dlopen, the
+ * copy the process has already loaded - e.g. torch's - is preferred) or a caller-supplied one: fill the struct with
+ * your own functions (they enqueue on `stream` and return 0 / a positive error code).  All ranks make the same calls
+ * in the same order.  With the NCCL transport one host thread drives one device. */
+typedef struct cmh_comm {
+    void* ctx;
+    int32_t rank, world;
+    /* in-place element-wise reduction of `count` uint32 over the ranks; op 0 = sum, 1 = max */
+    int (*all_reduce_u32)(void* ctx, uint32_t* buf, int64_t count, int op, void* stream);
+    /* recv (world * bytes) = the ranks' send buffers (bytes each), in rank order */
+    int (*all_gather)(void* ctx, const void* send, void* recv, int64_t bytes, void* stream);
+    /* block s (bytes each) of send goes to rank s; block s of recv came from rank s */
+    int (*all_to_all)(void* ctx, const void* send, void* recv, int64_t bytes, void* stream);
+} cmh_comm;
+
+#define CMH_COMM_ID_BYTES 128
+/* One process driving `ndev` devices (ncclCommInitAll): out[i] is the transport of devs[i] (devs == NULL: 0..ndev-1). */
+int cmh_comm_create(int ndev, const int* devs, cmh_comm** out);
+/* One process per GPU: rank 0 calls cmh_comm_unique_id, ships the 128 bytes to the other ranks by any means (a file,
+ * MPI, torch.distributed.broadcast), and every rank calls cmh_comm_create_rank on its current device. */
+int cmh_comm_unique_id(void* id128);
+int cmh_comm_create_rank(const void* id128, int world, int rank, cmh_comm** out);
+/* Measurement aid: ONE GPU plays rank `rank` of `world` statistically identical shards (sums are world x the local
+ * value, gathered / exchanged blocks are copies of the local block), so that the per-shard GPU work of an N-GPU search
+ * can be timed on one GPU.  Results are not a ranking of any database. */
+int cmh_comm_create_loopback(int world, int rank, cmh_comm** out);
+int cmh_comm_destroy(cmh_comm* comm);
+
+/* Exact (popc) global top-K of a database sharded over the ranks of `comm`: local cmh_topk, all-gather, K-way merge.
+ * plan / workspace as for cmh_topk; gathered: device uint64 [world][nq][K] scratch; keys: device [nq][K], identical on
+ * every rank.  comm == NULL (or world 1): plain cmh_topk. */
+int cmh_topk_sharded(const cmh_comm* comm, const cmh_plan* plan, const cmh_codeset* q, const cmh_codeset* d_shard, int K,
+                     int64_t index_base, uint64_t* gathered, uint64_t* keys, void* workspace, void* stream);
+/* calc_map_k_matrix (utils/calc_utils.py:16-39) - plus precision@N and the PR curve - with the database sharded by
+ * contiguous row ranges over the ranks of `comm` (rank r holds the rows after those of ranks < r): pass 1 per shard,
+ * all-gather of the shard histograms, pass 2 with the global bucket bases + the rows of lower shards, all-gather of the
+ * partial AP sums (added in rank order: the result is bit-identical on every rank and for every world size up to the
+ * order of that one sum), all-reduce of the precision@N hit counts.
+ *   ternary     1 when ANY shard or the queries hold exact zeros (then every side needs its valid plane)
+ *   topn/ntopn  HOST list of precision@N cut-offs (may be NULL / 0); prec: device float [ntopn]
+ *   ap          device double [nq] or NULL;  map: device float [1];  n_rel: device int64 [nq] or NULL
+ *   P, R        device float [bits + 1] or NULL (both): Hamming-radius PR curve over the whole database
+ * workspace >= cmh_map_k_sharded_workspace_bytes(world, ...).  comm == NULL: one shard. */
+uint64_t cmh_map_k_sharded_workspace_bytes(int world, int64_t nq, int64_t nd_shard, int bits, int nlab, int ternary, int ntopn);
+int cmh_map_k_sharded(const cmh_comm* comm, const cmh_codeset* q, const cmh_codeset* d_shard, int bits, int nlab,
+                      int ternary, int64_t k, int64_t nd_total, const int64_t* topn, int ntopn, double* ap, float* map,
+                      int64_t* n_rel, float* prec, float* P, float* R, void* workspace, uint64_t workspace_bytes,
+                      void* stream);
+
+/* ---- the tensor-core top-K search as ONE call ------------------------------------------------------------------- */
+/* cmh_topk_tc owns the whole launch chain of the benchmarked path (north star config 4): sample histogram ->
+ * thresholds -> pilot launches + refinement -> main launches with the exact prefix rule at every cut -> finalize ->
+ * (sharded: all-to-all by query slice, merge + verify).  cmh_tc_search_plan fixes the geometry once per
+ * (queries per call, shard) - it is a collective call when comm spans several ranks - and says how much device
+ * scratch a search needs. */
+#define CMH_TC_MAX_STRIPES 8
+#define CMH_TC_MAX_STAGES 4
+#define CMH_TC_MAX_CUTS 8
+#define CMH_TC_MAX_SPANS 32
+#define CMH_TC_MAX_READY 16
+#define CMH_TC_PHASES 8
+
+typedef struct cmh_tc_opts {
+    int32_t n_pilot;                        /* -1: automatic stages; else cumulative local row counts in pilot_rows     */
+    int64_t pilot_rows[CMH_TC_MAX_STAGES];
+    int32_t prefix;                         /* apply the exact prefix rule (default 1)                                   */
+    int32_t n_prefix;                       /* -1: automatic fractions; else prefix_frac[0..n_prefix) of the shard's rows */
+    double prefix_frac[CMH_TC_MAX_CUTS];
+    int64_t prefix_min_rows;                /* rows per shard below which the rule is not worth its launches (-1: default) */
+    int32_t tighten;                        /* tighten thresholds inside the main launches (default 1)                   */
+    int32_t cap;                            /* candidate slots per query and launch (0: default 16384)                   */
+    int32_t seg_cap;                        /* slots per candidate segment (0: cap / segments of the widest launch)      */
+    int32_t exact_thresholds;               /* 1: thresholds from a full popc histogram of the shard (no sample; world 1)  */
+    int32_t gather;                         /* sharded: 1 = all-gather the merged query slices so every rank holds all keys */
+    int32_t n_ready;                        /* rows that arrive with run-time events (a database still being uploaded)   */
+    int64_t ready_rows[CMH_TC_MAX_READY];
+    double sigma;                           /* margin of the refined thresholds (0: default 5)                           */
+} cmh_tc_opts;
+
+typedef struct cmh_tc_search {
+    int32_t bits, K, world, rank;
+    int64_t nq, nd, nd_total, n_sample, n_sample_all;
+    int32_t n_stripes;
+    int64_t stripe_row[CMH_TC_MAX_STRIPES], stripe_index[CMH_TC_MAX_STRIPES];
+    int32_t n_stages;
+    int64_t stage_rows[CMH_TC_MAX_STAGES], stage_rows_all[CMH_TC_MAX_STAGES];
+    int32_t n_prefix_cuts;
+    int64_t prefix_cut[CMH_TC_MAX_CUTS];
+    int32_t lockstep;
+    int32_t n_spans;
+    int64_t span_lo[CMH_TC_MAX_SPANS], span_hi[CMH_TC_MAX_SPANS], span_index[CMH_TC_MAX_SPANS];
+    int32_t span_seg_base[CMH_TC_MAX_SPANS], span_n_segs[CMH_TC_MAX_SPANS];
+    int32_t seg_total, seg_cap;
+    int32_t n_thr;                          /* threshold vectors a search writes (int32 [nq] each, at off_thr)           */
+    int32_t thr_limit_slot, thr_final_slot; /* the statistical bound / the last (prefix-tightened) thresholds            */
+    int64_t per_rank;                       /* queries merged by each rank (ceil(nq / world))                            */
+    int32_t exch_width;                     /* keys per (query, shard) in the exchange                                   */
+    cmh_tc_opts opts;
+    cmh_plan sample_plan;                   /* popc histogram of the queries against the sample                          */
+    uint64_t off_cand, off_cnt, off_aux, off_thr, off_hist, off_sample_hist, off_part, off_recv, off_flags, off_eval,
+             off_gather;
+    uint64_t workspace_bytes;
+} cmh_tc_search;
+
+void cmh_tc_default_opts(cmh_tc_opts* opts);
+/* the automatic pilot stages of a shard of nd rows in a database of nd_total rows over `world` shards: cumulative local
+ * row counts into rows[CMH_TC_MAX_STAGES]; returns their number (0: database too small for a pilot) */
+int cmh_tc_pilot_stages(int64_t nd, int64_t nd_total, int world, int64_t* rows);
+/* sizeof of {cmh_codeset, cmh_plan, cmh_comm, cmh_tc_opts, cmh_tc_search} and CMH_ABI_VERSION into sizes[0..n): lets a
+ * binding check that its struct mirrors match the library.  Returns the number of values available. */
+int cmh_struct_sizes(int32_t* sizes, int n);
+/* stripes: (local_row, global_index) pairs - the local rows from stripe_row[j] up to the next stripe are the database
+ * rows stripe_index[j], stripe_index[j] + 1, ... (one contiguous shard: n_stripes = 1, {0, index_base}).  With a comm
+ * of several ranks and several stripes the stripes must be LOCKSTEP stripes (stripe j of every shard below stripe j+1
+ * of every shard in global index); the prefix rule is then applied at the stripe boundaries.  n_sample: rows of the
+ * sample this shard passes to cmh_topk_tc (ignored with opts.exact_thresholds). */
+int cmh_tc_search_plan(const cmh_comm* comm, int64_t nq, int64_t nd, int64_t nd_total, int bits, int K, int n_stripes,
+                       const int64_t* stripe_row, const int64_t* stripe_index, int64_t n_sample, const cmh_tc_opts* opts,
+                       cmh_tc_search* plan);
+/* optional per-phase device timing of a search (CUDA events owned by the handle) */
+typedef struct cmh_tc_timing cmh_tc_timing;
+int cmh_tc_timing_create(cmh_tc_timing** out);
+int cmh_tc_timing_destroy(cmh_tc_timing* t);
+/* after the search has completed: phase_ms[CMH_TC_PHASES] = thresholds, pilot, main, finalize, exchange (then zeros),
+ * *collect_ms = sum over the tc_collect launches, *n_collect = their number.  Synchronises the last event. */
+int cmh_tc_timing_read(cmh_tc_timing* t, float* phase_ms, float* collect_ms, int* n_collect);
+/* the duration of each of the search's tc_collect launches, in launch order, into ms[0..n) (zeros past the last) */
+int cmh_tc_timing_launches(cmh_tc_timing* t, float* ms, int n);
+
+/* q_sign: device [nq][words]; d_sign: this shard's rows; sample_sign: device [n_sample][words] (any subset of the
+ * shard's rows; NULL with opts.exact_thresholds); ready_events: opts.n_ready cudaEvent_t (rows below ready_rows[i] are
+ * valid once event i has completed), else NULL.
+ * keys: device uint64.  world 1: [nq][K].  Sharded, gather 0: [per_rank][K] - the rows of queries
+ * rank * per_rank ... (-1 pads past nq); gather 1: [per_rank * world][K].
+ * fail_flags: device uint32 [per_rank * world] (identical on every rank), *fail_count (device uint32) their number:
+ * those queries must be redone through the exact path (cmh_topk / cmh_topk_sharded); their keys are pads.
+ * Everything is enqueued on `stream`; nothing synchronises. */
+int cmh_topk_tc(const cmh_tc_search* plan, const cmh_comm* comm, const uint64_t* q_sign, const uint64_t* d_sign,
+                const uint64_t* sample_sign, void* const* ready_events, uint64_t* keys, uint32_t* fail_flags,
+                uint32_t* fail_count, void* workspace, cmh_tc_timing* timing, void* stream);
 
 #ifdef __cplusplus
 }

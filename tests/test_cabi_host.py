@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(cuda_lib):
     raw = ctypes.CDLL(_cabi.LIB_PATH)
     for name in declared:
         assert hasattr(raw, name), f"{name} is declared in the header but not exported by libcmh_b200.so"
-    assert cuda_lib.cmh_abi_version() == 1
+    assert cuda_lib.cmh_abi_version() == _cabi.ABI_VERSION == 2
 
 
 def test_structs_mirror_header():
@@ -37,6 +37,57 @@ def test_structs_mirror_header():
     fields = re.sub(r"/\*.*?\*/", "", fields, flags=re.S)
     names = [n.strip() for decl in fields.split(";") if decl.strip() for n in decl.strip().split(None, 1)[1].split(",")]
     assert names == [f[0] for f in _cabi.Plan._fields_]
+
+
+def test_search_structs_match_the_library(cuda_lib):
+    """The mirrors of `cmh_comm`, `cmh_tc_opts` and `cmh_tc_search` are as long as the library's structs and carry the
+    header's field names in the header's order."""
+    sizes = (ctypes.c_int32 * 6)()
+    assert cuda_lib.cmh_struct_sizes(sizes, 6) == 6
+    assert list(sizes) == [ctypes.sizeof(c) for c in (_cabi.CodeSet, _cabi.Plan, _cabi.Comm, _cabi.TcOpts, _cabi.TcSearch)] + [2]
+    src = open(HEADER).read()
+    for cname, mirror in (("cmh_comm", _cabi.Comm), ("cmh_tc_opts", _cabi.TcOpts), ("cmh_tc_search", _cabi.TcSearch)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), src, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            fp = re.match(r".*\(\*(\w+)\)\(", decl, re.S)        # function pointer member
+            if fp:
+                names.append(fp.group(1))
+                continue
+            for n in decl.split(None, 1)[1].split(","):
+                names.append(re.sub(r"\[.*?\]|\*", "", n).strip())
+        assert names == [f[0] for f in mirror._fields_], cname
+
+
+def test_search_plan_geometry(cuda_lib):
+    """`cmh_tc_search_plan` is host arithmetic on one GPU: launches cut at the pilot stages and the prefix-rule rows,
+    every shard of a sharded database would get the same number of exchanges, and a lockstep stripe boundary inside the
+    pilot rows is refused (the strict prefix rule would not be valid there)."""
+    from cmh_b200 import engine
+    p = engine.tc_search_plan(None, 8192, 100_000_000, 100_000_000, 64, 1000, [(0, 0)], 65536)
+    assert p.n_stages == 2 and p.n_prefix_cuts == 4 and p.n_spans == 7 and p.exch_width == 1000
+    assert [p.span_lo[i] for i in range(1, 7)] == [p.span_hi[i] for i in range(6)] and p.span_hi[6] == 100_000_000
+    assert p.n_thr == 7 and p.thr_limit_slot == 2 and p.thr_final_slot == 6
+    assert p.seg_total == sum(p.span_n_segs[i] for i in range(7)) and p.workspace_bytes > p.off_cand
+    small = engine.tc_search_plan(None, 100, 300_000, 300_000, 128, 50, [(0, 7)], 0, exact_thresholds=True)
+    assert small.n_stages == 0 and small.n_prefix_cuts == 0 and small.n_spans == 1 and small.span_index[0] == 7
+    assert small.n_sample == 300_000
+    with pytest.raises(ValueError):
+        engine.tc_search_plan(None, 100, 1000, 1000, 32, 50, [(0, 0)], 0)            # 32-bit codes: no tensor path
+    with pytest.raises(ValueError):
+        engine.tc_search_plan(None, 100, 1000, 1000, 64, 5000, [(0, 0)], 0)          # K > 4096
+
+
+def test_comm_entry_points_reject_bad_arguments(cuda_lib):
+    assert cuda_lib.cmh_comm_create_rank(None, 2, 0, None) == -1
+    assert cuda_lib.cmh_comm_create(0, None, None) == -1
+    assert cuda_lib.cmh_comm_destroy(None) == 0
+    assert cuda_lib.cmh_map_k_sharded_workspace_bytes(0, 10, 10, 64, 24, 0, 0) == 0
+    assert cuda_lib.cmh_map_k_sharded_workspace_bytes(8, 2100, 25_000, 64, 21, 0, 11) > 0
 
 
 def test_argument_errors_use_the_error_convention(cuda_lib):

@@ -107,13 +107,21 @@ def test_synth_codes_match_cpu_twin(dev):
 # ---------------------------------------------------------------------------------------------------------------
 # golden vectors from the reference
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("design", [-1, 1])
+@pytest.mark.parametrize("design", [-1, 0, 1, 2])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
 def test_map_k_matches_reference_goldens(dev, case, design):
+    """Every kernel design (0 thread-per-query tile, 1 generic warp, 2 lane; -1 = the library's own choice) against the
+    goldens the reference's own module produced."""
     if design == 1 and case.slow:
         pytest.skip("generic design is covered on the small cases")
     g, T = load_golden(case), _T(case)
     cu = _cu()
+    bits = T["qB"].shape[1]
+    ternary = bool((T["qB"] == 0).any() or (T["rB"] == 0).any())
+    if design == 2 and (ternary or bits > 128):
+        pytest.skip("the lane design covers binary codes up to 128 bits")
+    if design == 0 and (2 * bits + 1 if ternary else bits + 1) > 200:
+        pytest.skip("the tile design holds at most 200 buckets")
     for k in case.ks:
         res = cu.map_k_detail(T["qB"].to(dev), T["rB"].to(dev), T["qL"], T["rL"], k, 0, design=design)
         assert np.array_equal(res["n_rel"].cpu().numpy(), g["n_rel"])
@@ -367,7 +375,7 @@ class _ThreadComm:
     def __init__(self, world):
         import threading
         self.world = world
-        self.barrier = threading.Barrier(world)
+        self.barrier = threading.Barrier(world, timeout=120)      # a mismatched exchange fails the test instead of hanging it
         self.slots = [None] * world
         self.local = threading.local()
 
@@ -411,7 +419,7 @@ class _ThreadComm:
                                                          (64, 3, 2_400_123, 300, 100_000, "lockstep"),
                                                          (64, 4, 1_000_001, 1000, 0, "lockstep"),
                                                          (128, 2, 1_500_000, 500, 150_016, "lockstep")])
-def test_tc_topk_sharded_matches_single(dev, bits, world, D, K, pilot, prefix, monkeypatch):
+def test_tc_topk_sharded_matches_single(dev, bits, world, D, K, pilot, prefix):
     """Shards that filter with all-reduced (global) thresholds + merge + verify == the exact single-shard ranking;
     with ``prefix``, the shards also tighten by the cross-shard prefix rule (all-gathered candidate histograms);
     "lockstep": every shard holds one piece of each of three global stripes (`sharded.lockstep_stripes`) and the
@@ -421,9 +429,8 @@ def test_tc_topk_sharded_matches_single(dev, bits, world, D, K, pilot, prefix, m
     lockstep = prefix == "lockstep"
     if lockstep:
         prefix = None
-    if prefix is not None:
-        monkeypatch.setattr(engine, "TC_PREFIX_MIN_ROWS", 1000)
-        monkeypatch.setattr(engine, "TC_PREFIX_FRACTIONS_SHARDED", prefix)
+    prefix_kw = {} if prefix is None else {"prefix_fractions": prefix, "prefix_min_rows": 1000}
+    gather = D % 2 == 0                               # the same on every rank (it decides a collective): both forms are covered
     Q = 300
     db = engine.synth_codes(500 + bits, 0, D, bits, dev)
     q = engine.synth_codes(600 + bits, 0, Q, bits, dev)
@@ -449,7 +456,7 @@ def test_tc_topk_sharded_matches_single(dev, bits, world, D, K, pilot, prefix, m
             smp = engine.PackedSet(shard.sign[::97].contiguous(), None, None, (shard.n + 96) // 97, bits)
             st = {}
             out[rank] = (engine.topk_tc(q, shard, K, lo, sample=smp, comm=comm, nd_total=D, stats=st, pilot=pilot,
-                                        stripes=stripes,
+                                        stripes=stripes, gather=gather, **prefix_kw,
                                         exact_fallback=lambda sub: engine.RankPass(sub, db, need_labels=False).topk(K, 0)),
                          st)
         except Exception as e:  # noqa: BLE001
@@ -460,9 +467,16 @@ def test_tc_topk_sharded_matches_single(dev, bits, world, D, K, pilot, prefix, m
     [t.start() for t in threads]
     [t.join() for t in threads]
     assert not errs, errs
-    for keys, st in out:
-        assert torch.equal(keys, want)
+    per_rank = -(-Q // world)
+    for rank, (keys, st) in enumerate(out):
+        if gather:                                   # gathered: every query on this rank
+            assert torch.equal(keys, want)
+        else:                                        # left sharded by query slice: this rank's slice, pads past the end
+            lo_q, hi_q = rank * per_rank, min(Q, (rank + 1) * per_rank)
+            assert keys.shape == (per_rank, K)
+            assert torch.equal(keys[:hi_q - lo_q], want[lo_q:hi_q]) and bool((keys[hi_q - lo_q:] == -1).all())
         assert st["n_fail"] == 0
+        assert st["exch_width"] <= K
     # each shard collected only its share of the candidates
     assert sum(int(st["candidates"].sum()) for _, st in out) < 40 * K * Q
     if prefix is not None or lockstep:               # the rule did tighten, and never above the statistical bound
@@ -767,7 +781,6 @@ def test_finalize_and_cand_hist_over_many_segments(dev, n_segs, seg_cap, nq, K):
     row = torch.randperm(nq * n_segs * seg_cap, generator=g).reshape(nq, n_segs, seg_cap)
     cand = ((2 * dist) << 32) | row
     cand_d, cnt_d = cand.to(dev), cnt.to(dev)
-    aux = torch.zeros((nq, 8), dtype=torch.int32, device=dev)
     st, p = engine._stream(dev), engine._ptr
     # histogram of a sub-range of the segments
     lo, hi = n_segs // 5, n_segs
@@ -778,8 +791,16 @@ def test_finalize_and_cand_hist_over_many_segments(dev, n_segs, seg_cap, nq, K):
     flags = torch.zeros(nq, dtype=torch.int32, device=dev)
     nfail = torch.zeros(1, dtype=torch.int32, device=dev)
     thr = torch.full((nq,), 20, dtype=torch.int32, device=dev)
-    engine.check(L.cmh_topk_finalize(p(cand_d), p(cnt_d), p(aux), p(thr), nq, n_segs, seg_cap, K, 10**9, 0, p(keys), p(flags),
+    engine.check(L.cmh_topk_finalize(p(cand_d), p(cnt_d), p(thr), nq, n_segs, seg_cap, K, 10**9, 0, K, p(keys), p(flags),
                                      p(nfail), st), "cmh_topk_finalize")
+    # the per-shard form: the `width` smallest keys a query holds, an overflowed query announces itself with the marker
+    width = max(1, K // 3)
+    part = torch.empty((nq, width), dtype=torch.int64, device=dev)
+    pflags = torch.zeros(nq, dtype=torch.int32, device=dev)
+    pfail = torch.zeros(1, dtype=torch.int32, device=dev)
+    engine.check(L.cmh_topk_finalize(p(cand_d), p(cnt_d), None, nq, n_segs, seg_cap, K, 10**9, 1, width, p(part), p(pflags),
+                                     p(pfail), st), "cmh_topk_finalize")
+    part = part.cpu()
     ph, ov, keys, flags = ph.cpu(), ov.cpu(), keys.cpu(), flags.cpu()
     n_fail = 0
     for q in range(nq):
@@ -789,6 +810,14 @@ def test_finalize_and_cand_hist_over_many_segments(dev, n_segs, seg_cap, nq, K):
         assert torch.equal(ph[q].to(torch.int64), torch.bincount(sub >> 33, minlength=nb)[:nb])
         assert int(ov[q]) == (1 if q == over_q else 0)
         every = torch.sort(torch.cat(ent)).values
+        if q == over_q:
+            assert int(part[q, 0]) == -2 and bool((part[q, 1:] == -1).all())            # marker, then pads
+        elif every.numel():
+            kth = every[min(K, every.numel()) - 1] >> 33                                 # the shard's K-th bucket
+            keep = int(((every >> 33) <= kth).sum())
+            assert keep <= 4096
+            m = min(width, keep)
+            assert torch.equal(part[q, :m], every[:m]) and bool((part[q, m:] == -1).all())
         if q == over_q or every.numel() < K:
             assert int(flags[q]) == 1 and bool((keys[q] == -1).all())
             n_fail += 1
@@ -825,3 +854,151 @@ def test_stripes_single_gpu_and_exact_path(dev):
     want = engine.topk_merge(torch.stack(lists), K)
     smp = engine.PackedSet(shard.sign[::53].contiguous(), None, None, (shard.n + 52) // 53, 64)
     assert torch.equal(engine.topk_tc(q, shard, K, 0, sample=smp, stripes=stripes), want)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: the benchmarked configuration itself, the C-owned orchestration and the sharded entry points
+# ---------------------------------------------------------------------------------------------------------------
+def test_benchmarked_path_two_stage_pilot_against_oracle(dev):
+    """The path bench.py times, at a size that takes its branches: a 64M-row shard gets the TWO-stage pilot (1/512 and
+    1/64 of the rows) and the four prefix-rule cuts.  64 queries, top-1000: the keys of `cmh_topk_tc` must equal the
+    threaded C oracle (`oracle/cmh_oracle_c.c`, 4.1e9 popcounts) AND the exact two-pass popc path, with no query
+    taking the exact fallback."""
+    from cmh_b200 import engine
+    from cmh_b200.index import HammingIndex
+    from cmh_b200.synth import splitmix_rows
+    D, Q, K, seed = 64_000_000, 64, 1000, 4000
+    db = engine.synth_codes(seed, 0, D, 64, dev)
+    q = engine.synth_codes(seed + 7, 0, Q, 64, dev)
+    index = HammingIndex(db, 0, nd_total=D)
+    st = {}
+    got = index.search_packed(q, K, stats=st)
+    assert st["n_fail"] == 0
+    assert len(st["pilot_rows"]) == 2 and st["pilot_rows"] == engine.tc_pilot_stages(D, D, 1)
+    assert st["n_launches"] == 7                                       # 2 pilot stages + 5 spans between the 4 cuts
+    assert bool((st["thr_final"] <= st["thr"]).all()) and bool((st["thr_final"] < st["thr"]).any())
+    assert torch.equal(got, engine.topk_exact(q, db, K, 0))
+    ds = splitmix_rows(seed, 0, D, 1, 64); qs = splitmix_rows(seed + 7, 0, Q, 1, 64)
+    assert np.array_equal(db.sign[::1_000_003].cpu().numpy().view(np.uint64), ds[::1_000_003])     # same database
+    want = c_oracle.topk_packed(qs, np.full_like(qs, np.uint64(2**64 - 1)), ds, np.full_like(ds, np.uint64(2**64 - 1)), 64, K)
+    assert np.array_equal(got.cpu().numpy().view(np.uint64), want)
+
+
+def test_merge_verify_kernel(dev):
+    """`cmh_topk_merge_verify`: merged keys == sort of the union; the verdict flags an overflow marker, a missing K-th
+    key, a K-th key above the limit and a full (possibly cut) list that ends below the K-th key - and nothing else."""
+    from cmh_b200 import _cabi, engine
+    L = _cabi.lib()
+    g = torch.Generator().manual_seed(5)
+    n_lists, nq, W, K = 3, 6, 8, 12
+    pool = torch.randperm(4000, generator=g)[:nq * 40].view(nq, 40)
+    dist = torch.randint(3, 6, (nq, 40), generator=g)
+    keys = torch.sort((2 * dist << 32) | pool, dim=1).values                       # 40 unique ascending keys per query
+    lists = torch.full((n_lists, nq, W), -1, dtype=torch.int64)
+    owner = torch.randint(0, n_lists, (nq, 40), generator=g)
+    held = [[keys[q][owner[q] == s] for s in range(n_lists)] for q in range(nq)]   # what every shard holds, ascending
+    for q in range(nq):
+        for s in range(n_lists):
+            h = held[q][s][:W]
+            lists[s, q, :h.numel()] = h
+    lists[1, 4, 0] = -2                                                            # query 4: shard 1 overflowed
+    lim = torch.full((nq,), 5, dtype=torch.int32)
+    lim[5] = 3                                                                     # query 5: the K-th key lies above the limit
+    out = torch.empty((nq, K), dtype=torch.int64, device=dev)
+    flags = torch.zeros(nq, dtype=torch.int32, device=dev)
+    engine.check(L.cmh_topk_merge_verify(engine._ptr(lists.to(dev)), n_lists, nq, W, K, 10**9, engine._ptr(lim.to(dev)),
+                                         engine._ptr(out), engine._ptr(flags), engine._stream(dev)), "cmh_topk_merge_verify")
+    out, flags = out.cpu(), flags.cpu()
+    for q in range(nq):
+        sent = torch.sort(torch.cat([h[:W] for h in held[q]])).values
+        cut = any(h.numel() >= W and int(h[W - 1]) < int(sent[K - 1]) for h in held[q]) if sent.numel() >= K else True
+        expect_fail = q == 4 or sent.numel() < K or cut or (q == 5 and int(sent[K - 1] >> 33) > 3)
+        assert int(flags[q]) == (1 if expect_fail else 0), q
+        if not expect_fail:
+            assert torch.equal(out[q], keys[q][:K])                                # and it IS the global answer
+    assert 0 < int(flags.sum()) < nq
+
+
+def test_topk_merge_beyond_shared_memory(dev):
+    """8 lists x K = 4096 (256 KB of keys per query) do not fit a CTA's shared memory: the merge searches the lists in
+    place instead of refusing (world * K was capped at 29056)."""
+    from cmh_b200 import engine
+    g = torch.Generator().manual_seed(9)
+    n_lists, nq, K = 8, 5, 4096
+    allk = torch.randperm(n_lists * K * 2, generator=g)[:n_lists * K].view(n_lists, K) + (7 << 33)
+    lists = torch.sort(allk, dim=1).values.unsqueeze(1).repeat(1, nq, 1)
+    lists[3, 2, 100:] = -1                                                         # a short list
+    got = engine.topk_merge(lists.to(dev), K).cpu()
+    for q in range(nq):
+        flat = lists[:, q].reshape(-1)
+        assert torch.equal(got[q], torch.sort(flat[flat >= 0]).values[:K])
+
+
+@pytest.mark.parametrize("name,world", [("small_b64_l24", 1), ("small_b64_l24", 3), ("small_b64_ternary", 2),
+                                        ("small_b128_l80", 4)])
+def test_map_k_sharded_c_entry(dev, name, world):
+    """`cmh_map_k_sharded` (hist -> all-gather -> rank -> all-gather of the partial sums, one C call per shard) over a
+    callback transport: shards of one GPU driven by threads.  Every rank must return the single-GPU result: n_rel and
+    precision@N hit-derived values exactly, AP within 1e-12, the PR curve within 1e-7."""
+    import threading
+    from cmh_b200 import engine, sharded
+    case = BY_NAME[name]
+    T = _T(case)
+    cu = _cu()
+    q, d = cu._prepare(T["qB"].to(dev), T["rB"].to(dev), T["qL"], T["rL"], 0)
+    tern = q.valid is not None or d.valid is not None
+    topn, k = (1, 10, 100), case.ks[-1]
+    single = cu.map_k_detail(T["qB"].to(dev), T["rB"].to(dev), T["qL"], T["rL"], k, 0, topn=topn)
+    P1, R1 = engine.finalize_pr(single["hist_all"], single["hist_rel"], q.bits, tern)
+    comm = _ThreadComm(world)
+    out, errs = [None] * world, []
+
+    def run(rank):
+        try:
+            comm.bind(rank)
+            torch.cuda.set_device(dev)
+            lo, hi = sharded.shard_bounds(d.n, world, rank)
+            out[rank] = sharded.map_k_sharded_native(q, d.rows(lo, hi), k, d.n, topn, comm=comm if world > 1 else None,
+                                                     want_pr=True, ternary=tern)
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+            comm.barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errs, errs
+    for res in out:
+        assert torch.equal(res["n_rel"], single["n_rel"])
+        np.testing.assert_allclose(res["ap"].cpu().numpy(), single["ap"].cpu().numpy(), rtol=0, atol=1e-12)
+        assert abs(float(res["map"].cpu()[0]) - float(single["map"].cpu()[0])) < 1e-7
+        np.testing.assert_allclose(res["prec"].cpu().numpy(), single["prec"].cpu().numpy(), rtol=0, atol=1e-7)
+        np.testing.assert_allclose(res["pr"][0].cpu().numpy(), P1.cpu().numpy(), rtol=0, atol=1e-7)
+        np.testing.assert_allclose(res["pr"][1].cpu().numpy(), R1.cpu().numpy(), rtol=0, atol=1e-7)
+    if world > 1:                                    # identical on every rank, bit for bit
+        assert all(torch.equal(res["ap"], out[0]["ap"]) for res in out)
+
+
+def test_lockstep_boundary_inside_pilot_is_refused(dev):
+    """a lockstep stripe boundary before the last pilot stage would apply the strict prefix rule after other
+    shards have scanned into the next stripe; the plan refuses it instead of ranking wrongly."""
+    with pytest.raises(ValueError, match="pilot"):
+        _plan_lockstep_bad(dev)
+
+
+def _plan_lockstep_bad(dev):
+    import ctypes
+    from cmh_b200 import _cabi
+    L = _cabi.lib()
+    fake = _cabi.Comm(None, 0, 2, _cabi.COMM_ALL_REDUCE(lambda *a: 1), _cabi.COMM_ALL_GATHER(lambda *a: 1),
+                      _cabi.COMM_ALL_TO_ALL(lambda *a: 1))
+    o = _cabi.TcOpts()
+    L.cmh_tc_default_opts(ctypes.byref(o))
+    o.n_pilot = 1
+    o.pilot_rows[0] = 200_192
+    srow = (ctypes.c_int64 * 2)(0, 100_096)
+    sidx = (ctypes.c_int64 * 2)(0, 500_000)
+    plan = _cabi.TcSearch()
+    _cabi.check(L.cmh_tc_search_plan(ctypes.pointer(fake), 64, 1_000_000, 2_000_000, 64, 100, 2, srow, sidx, 4096,
+                                     ctypes.byref(o), ctypes.byref(plan)), "cmh_tc_search_plan")
