@@ -17,7 +17,7 @@ CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "libcmh_b200.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(_PKG_DIR), "include")
 SOURCES = ("api.cu", "pack.cu", "dense.cu", "eval_tile.cu", "eval_warp.cu", "eval_lane.cu", "eval_host.cu", "peaks.cu", "tc_collect.cu",
-           "tc_search.cu", "comm.cu", "sharded.cu")
+           "tc_search.cu", "comm.cu", "sharded.cu", "head.cu")
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-t", "0", "-ldl")
 
@@ -28,7 +28,7 @@ DTYPE_CODES = {"float32": 0, "float16": 1, "bfloat16": 2, "float64": 3, "int8": 
 # every symbol include/cmh_b200.h declares (tests check that the built library exports each of them)
 EXPORTS = (
     "cmh_abi_version", "cmh_last_error", "cmh_device_info", "cmh_launch_count", "cmh_measure_popc_peak",
-    "cmh_pack_codes", "cmh_pack_scatter", "cmh_unpack_codes", "cmh_pack_labels", "cmh_synth_codes",
+    "cmh_pack_codes", "cmh_pack_scatter", "cmh_hash_head_pack", "cmh_unpack_codes", "cmh_pack_labels", "cmh_synth_codes",
     "cmh_hamming_dense", "cmh_neighbor_dense",
     "cmh_eval_plan", "cmh_eval_plan_design", "cmh_eval_hist", "cmh_eval_rank",
     "cmh_finalize_map", "cmh_finalize_topn", "cmh_finalize_pr_workspace_bytes", "cmh_finalize_pr",
@@ -170,6 +170,7 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cmh_pack_codes.argtypes = [vp, i32, i64, i32, i64, vp, vp, vp, vp]
     L.cmh_unpack_codes.argtypes = [vp, vp, i64, i32, vp, i64, vp]
     L.cmh_pack_scatter.argtypes = [vp, i32, i64, i32, i64, i32, vp, i64, vp, vp, vp, vp]
+    L.cmh_hash_head_pack.argtypes = [vp, i32, i64, i32, i64, i32, vp, vp, i32, vp, i64, vp, vp, vp, vp]
     L.cmh_pack_labels.argtypes = [vp, i32, i64, i32, i64, vp, vp, vp]
     L.cmh_synth_codes.argtypes = [u64, i64, i64, i32, vp, vp]
     L.cmh_hamming_dense.argtypes = [pcs, pcs, i32, vp, i64, vp]

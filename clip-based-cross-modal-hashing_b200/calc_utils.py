@@ -108,16 +108,46 @@ def set_cache(enabled: bool) -> None:
         _cache.clear()
 
 
-def pack_codes(x, device=None, *, binarize: bool = False) -> PackedSet:
-    """Sign + bit-pack ``[n, bits]`` codes on the device (kernel K1).  Entries must be in {-1, 0, +1} (what
-    `torch.sign` / the argmax heads emit, train/base.py:141-158) unless ``binarize`` is set, in which case the
-    sign of any real value is taken (the duplicate API `utils/utils.py:77-78` does that)."""
+class _PendingCodes:
+    """Codes whose pack kernel is enqueued but whose counters (zeros / values outside {-1, 0, +1}) have not been read."""
+
+    def __init__(self, owner, kind, device, sign, valid, n, bits, counters, binarize):
+        self.owner, self.kind, self.device = owner, kind, device
+        self.sign, self.valid, self.n, self.bits, self.counters, self.binarize = sign, valid, n, bits, counters, binarize
+
+    def resolve(self, n_zero: int, n_odd: int) -> PackedSet:
+        if n_odd and not self.binarize:
+            raise ValueError(f"{n_odd} code entries are outside {{-1, 0, +1}}: pass sign()-binarised codes "
+                             "(train/base.py:141) - the reference's float dot product on raw activations is not "
+                             "a Hamming distance")
+        ps = PackedSet(self.sign, self.valid if n_zero else None, None, self.n, self.bits, 0, n_zero)
+        if self.owner is not None:
+            _cache.put(self.owner, self.kind, self.device, ps)
+        return ps
+
+
+class _PendingLabels:
+    def __init__(self, owner, device, masks, nlab, counters):
+        self.owner, self.device, self.masks, self.nlab, self.counters = owner, device, masks, nlab, counters
+
+    def resolve(self, n_neg: int, _unused: int = 0):
+        if n_neg:
+            raise ValueError("labels must be non-negative multi-hot (the reference's `dot > 0` relevance, "
+                             "utils/calc_utils.py:26, is a set intersection only then)")
+        out = (self.masks, self.nlab)
+        if self.owner is not None:
+            _cache.put(self.owner, "labels", self.device, out)
+        return out
+
+
+def _pack_codes_enqueue(x, device, binarize: bool, counters: torch.Tensor):
+    """Enqueue K1 on codes; returns a finished PackedSet (already packed input / cache hit) or a `_PendingCodes` whose
+    two counters live in ``counters`` (int64 [2], zeroed by the caller)."""
     if isinstance(x, PackedSet):                     # already packed (engine level)
         return x
     if hasattr(x, "packed") and hasattr(x, "put"):   # codes.CodeBuffer: binarised and packed at the source
         return x.packed()
     t = _to_tensor(x)
-    device = _device_for(device, t)
     owner = x if isinstance(x, torch.Tensor) and _cache_enabled else None
     kind = "codes-b" if binarize else "codes"
     if owner is not None:
@@ -129,23 +159,12 @@ def pack_codes(x, device=None, *, binarize: bool = False) -> PackedSet:
     if t.dim() != 2:
         raise ValueError(f"codes must be [n, bits], got {tuple(t.shape)}")
     td = _on(t, device)
-    counters = torch.zeros(2, dtype=torch.int64, device=device)
     sign, valid = _e.pack_codes_device(td, counters)
-    n_zero, n_odd = (int(v) for v in counters.tolist())       # tiny D2H; also orders the pack before reuse
-    if n_odd and not binarize:
-        raise ValueError(f"{n_odd} code entries are outside {{-1, 0, +1}}: pass sign()-binarised codes "
-                         "(train/base.py:141) - the reference's float dot product on raw activations is not "
-                         "a Hamming distance")
-    ps = PackedSet(sign, valid if n_zero else None, None, td.shape[0], td.shape[1], 0, n_zero)
-    if owner is not None:
-        _cache.put(owner, kind, device, ps)
-    return ps
+    return _PendingCodes(owner, kind, device, sign, valid, td.shape[0], td.shape[1], counters, binarize)
 
 
-def pack_labels(L, device=None) -> Tuple[torch.Tensor, int]:
-    """Multi-hot labels ``[n, nlab]`` -> (int64 masks [n, ceil(nlab/64)] on the device, nlab)."""
+def _pack_labels_enqueue(L, device, counters: torch.Tensor):
     t = _to_tensor(L)
-    device = _device_for(device, t)
     owner = L if isinstance(L, torch.Tensor) and _cache_enabled else None
     if owner is not None:
         hit = _cache.get(owner, "labels", device)
@@ -156,15 +175,42 @@ def pack_labels(L, device=None) -> Tuple[torch.Tensor, int]:
     if t.dim() != 2:
         raise ValueError(f"labels must be [n, nlab], got {tuple(t.shape)}")
     td = _on(t, device)
-    neg = torch.zeros(1, dtype=torch.int64, device=device)
-    masks = _e.pack_labels_device(td, neg)
-    if int(neg.item()):
-        raise ValueError("labels must be non-negative multi-hot (the reference's `dot > 0` relevance, "
-                         "utils/calc_utils.py:26, is a set intersection only then)")
-    out = (masks, td.shape[1])
-    if owner is not None:
-        _cache.put(owner, "labels", device, out)
+    masks = _e.pack_labels_device(td, counters)
+    return _PendingLabels(owner, device, masks, td.shape[1], counters)
+
+
+def _resolve(items, counters: torch.Tensor):
+    """ONE device-to-host read for everything that was enqueued: the counters decide whether a valid plane is needed
+    (exact zeros) and whether the inputs were legal."""
+    pending = [it for it in items if isinstance(it, (_PendingCodes, _PendingLabels))]
+    if not pending:
+        return items
+    host = counters.tolist()                         # the one sync of the pack stage
+    out = []
+    for i, it in enumerate(items):
+        if isinstance(it, (_PendingCodes, _PendingLabels)):
+            out.append(it.resolve(int(host[2 * i]), int(host[2 * i + 1])))
+        else:
+            out.append(it)
     return out
+
+
+def pack_codes(x, device=None, *, binarize: bool = False) -> PackedSet:
+    """Sign + bit-pack ``[n, bits]`` codes on the device (kernel K1).  Entries must be in {-1, 0, +1} (what
+    `torch.sign` / the argmax heads emit, train/base.py:141-158) unless ``binarize`` is set, in which case the
+    sign of any real value is taken (the duplicate API `utils/utils.py:77-78` does that)."""
+    if isinstance(x, PackedSet) or (hasattr(x, "packed") and hasattr(x, "put")):
+        return _pack_codes_enqueue(x, device, binarize, None)
+    device = _device_for(device, _to_tensor(x))
+    counters = torch.zeros(2, dtype=torch.int64, device=device)
+    return _resolve([_pack_codes_enqueue(x, device, binarize, counters)], counters)[0]
+
+
+def pack_labels(L, device=None) -> Tuple[torch.Tensor, int]:
+    """Multi-hot labels ``[n, nlab]`` -> (int64 masks [n, ceil(nlab/64)] on the device, nlab)."""
+    device = _device_for(device, _to_tensor(L))
+    counters = torch.zeros(2, dtype=torch.int64, device=device)
+    return _resolve([_pack_labels_enqueue(L, device, counters)], counters)[0]
 
 
 def _prepare(qB, rB, query_L, retrieval_L, rank, binarize=False) -> Tuple[PackedSet, PackedSet]:
@@ -174,13 +220,17 @@ def _prepare(qB, rB, query_L, retrieval_L, rank, binarize=False) -> Tuple[Packed
             dev = x.device
     if dev is None:
         dev = _device_for(rank, *(x for x in (qB, rB) if isinstance(x, torch.Tensor)))
-    q = pack_codes(qB, dev, binarize=binarize)
-    d = pack_codes(rB, dev, binarize=binarize)
+    # all four pack kernels are enqueued before their counters are read: one host sync instead of four
+    counters = torch.zeros(8, dtype=torch.int64, device=dev)
+    items = [_pack_codes_enqueue(qB, dev, binarize, counters[0:2]), _pack_codes_enqueue(rB, dev, binarize, counters[2:4])]
+    if query_L is not None:
+        items += [_pack_labels_enqueue(query_L, dev, counters[4:6]), _pack_labels_enqueue(retrieval_L, dev, counters[6:8])]
+    items = _resolve(items, counters)
+    q, d = items[0], items[1]
     if q.bits != d.bits:
         raise RuntimeError(f"code lengths differ: qB has {q.bits} columns, rB has {d.bits}")   # torch.mm would raise
     if query_L is not None:
-        ql, nlq = pack_labels(query_L, dev)
-        dl, nld = pack_labels(retrieval_L, dev)
+        (ql, nlq), (dl, nld) = items[2], items[3]
         if nlq != nld:
             raise RuntimeError(f"label widths differ: {nlq} vs {nld}")
         if ql.shape[0] != q.n or dl.shape[0] != d.n:

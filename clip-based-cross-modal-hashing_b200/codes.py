@@ -81,6 +81,35 @@ class CodeBuffer:
         """DCHMT head: ``argmax(logits [n, bits, 2], -1)`` with class 0 -> -1 (`train/base.py:150-158`)."""
         self._put(index, logits, 1)
 
+    def put_head(self, index, hidden: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                 relu: bool = False) -> None:
+        """The whole DCHMT head on the way in (`cmh_hash_head_pack`): ``hidden`` [n, h] are the activations after
+        `HashLayer.fc` (`relu=True` applies the reference's `torch.relu`, model/DCHMT.py:22), ``weight`` [bits, 2, h] /
+        ``bias`` [bits, 2] the `bits` stacked `nn.Linear(h, 2)` layers; bit j = argmax over the two logits (a tie is
+        class 0 = -1, train/base.py:150-158).  The [n, bits, 2] logits and the float codes never exist."""
+        x = hidden.detach()
+        if x.device != self.device:
+            x = x.to(self.device)
+        if x.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            x = x.float()
+        if x.dim() != 2:
+            raise ValueError(f"expected hidden activations [n, h], got {tuple(x.shape)}")
+        x = x.contiguous()
+        n, h = x.shape
+        w = weight.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        if tuple(w.shape) != (self.bits, 2, h):
+            raise ValueError(f"weight must be [{self.bits}, 2, {h}], got {tuple(w.shape)}")
+        b = None
+        if bias is not None:
+            b = bias.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            if tuple(b.shape) != (self.bits, 2):
+                raise ValueError(f"bias must be [{self.bits}, 2], got {tuple(b.shape)}")
+        idx = self._index(index, n)
+        with torch.cuda.device(self.device):
+            check(_cabi.lib().cmh_hash_head_pack(_ptr(x), _TORCH_DTYPE[x.dtype], n, h, h, 1 if relu else 0, _ptr(w), _ptr(b),
+                                                 self.bits, _ptr(idx), self.n, _ptr(self.sign), _ptr(self.valid),
+                                                 _ptr(self._counters), _stream(self.device)), "cmh_hash_head_pack")
+
     def reset(self) -> None:
         """Forget everything written so far (all rows read as -1 again, zero / bad-index counters cleared): a buffer
         reused across epochs returns to the +-1 fast path even if an earlier epoch stored exact zeros."""

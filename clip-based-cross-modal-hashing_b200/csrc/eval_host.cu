@@ -31,9 +31,7 @@ int launch_rank_lane(const EvalArgs& a, const uint2* base, const uint32_t* total
 constexpr int LANE_Q_TILE = 8;
 
 constexpr size_t MAX_DYN_SMEM = 227 * 1024;
-#ifndef CMH_AUTO_LANE
-#define CMH_AUTO_LANE 0       // the lane design is opt-in (CMH_EVAL_DESIGN=2 / cmh_eval_plan_design) until measured
-#endif
+
 constexpr int MAX_CHUNK_ROWS = 65520;  // pass-1 counters are 16 bit; multiple of 16 keeps bulk copies aligned
 constexpr int MIN_CHUNK_ROWS = 1024;   // amortises the per-CTA counter prologue / epilogue
 
@@ -388,9 +386,13 @@ using namespace cmh;
 // =====================================================================================================================
 // Which design ranks an (nq, nd, nb) problem when the caller does not say: thread-per-query tile kernels (0), generic
 // warp-per-query kernels (1: any bucket count, ternary codes), lane kernels (2: binary codes <= 128 bits).
-static int auto_design(int64_t nq, int64_t nd, int nb, bool tile_ok, bool lane_ok) {
-    (void)nq; (void)nd; (void)nb;
-    if (lane_ok && CMH_AUTO_LANE) return 2;
+static int auto_design(int64_t nq, int64_t nd, int nb, int nlab, bool tile_ok, bool lane_ok) {
+    (void)nq; (void)nd;
+    // Measured at the BASELINE.json shapes (profiles/r02c_map_designs.txt; hist + rank, ms): 64-bit codes tile 0.55 + 1.59
+    // / lane 0.48 + 1.39 (NUS-WIDE), 128-bit tile 2.29 + 6.71 / lane 0.91 + 2.46 (MS-COCO) - the tile design's per-thread
+    // counter columns leave one to three CTAs per SM there; 16 / 32-bit codes tile 0.31 + 0.68 / lane 0.59 + 0.89 (few
+    // buckets: the lanes of a step collide on the same counters).  Top-K (no labels) keeps the tile select kernel.
+    if (lane_ok && nlab > 0 && nb >= 65) return 2;
     return tile_ok ? 0 : 1;
 }
 
@@ -416,7 +418,7 @@ static int make_plan(int64_t nq, int64_t nd, int bits, int nlab, int ternary, in
         if (forced == 2 && lane_ok) design = 2;
         else if (forced == 1) design = 1;
         else if (forced == 0 && tile_ok) design = 0;
-        else design = auto_design(nq, nd, plan->nb, tile_ok, lane_ok);
+        else design = auto_design(nq, nd, plan->nb, nlab, tile_ok, lane_ok);
     }
     CMH_REQUIRE(design != 0 || tile_ok, CMH_ERR_UNSUPPORTED, "cmh_eval_plan: tile design cannot hold %d buckets", plan->nb);
     CMH_REQUIRE(design != 2 || lane_ok, CMH_ERR_UNSUPPORTED, "cmh_eval_plan: lane design needs binary codes of <= 128 bits");

@@ -17,6 +17,8 @@
 // Database rows stream through shared memory in LANE_ROWS-row stages filled by the bulk-copy engine (cp.async.bulk +
 // mbarrier) while the previous stage is consumed; the 8 warps (= 8 queries) of a CTA share the stage.  Layout of the
 // per-chunk histograms / bases: "W" ([chunk][query][bucket], eval_common.cuh), shared with the generic warp kernels.
+#include <cstdlib>
+
 #include "eval_common.cuh"
 
 namespace cmh {
@@ -27,8 +29,11 @@ constexpr int LANE_ROWS = 512;    // database rows per stage
 __host__ __device__ inline size_t lane_stage_bytes(int cws, int lws) { return (size_t)LANE_ROWS * (cws + lws) * 4; }
 __host__ __device__ inline int lane_nbp(int nb) { return (nb + 1 + 3) & ~3; }   // + the parking bucket of idle lanes
 
+constexpr int LANE_MODE_DEFAULT = 3;   // peers by shared-memory OR, four sub-histograms (see lane_mode())
+
 size_t lane_smem_bytes(const EvalArgs& a, int kind /*0 hist, 1 rank*/) {
-    return 128 + 2 * lane_stage_bytes(a.cw_stride, a.lw_stride) + (size_t)LANE_WARPS * lane_nbp(a.nb) * (kind ? 8 : 4) +
+    // pass 1: up to four uint32 sub-histograms per warp; pass 2: 16-byte counter entries + the precision@N bins
+    return 128 + 2 * lane_stage_bytes(a.cw_stride, a.lw_stride) + (size_t)LANE_WARPS * lane_nbp(a.nb) * 16 +
            (kind ? (size_t)LANE_WARPS * CMH_MAX_TOPN * 4 : 0);
 }
 
@@ -78,6 +83,31 @@ __device__ __forceinline__ void lane_load_stage(const EvalArgs& a, const LaneSme
     }
 }
 
+// ---- shared memory by 32-bit address (no generic-pointer window arithmetic in the loops: the r02d capture showed 14 % of
+// the stall samples on the S2UR / ULEA pair that rebuilds the shared window base every iteration) ----------------------
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint2 v) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void red_add_shared(uint32_t a, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_or_shared(uint32_t a, uint32_t v) {
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
 // the query of a warp: the same words in every lane
 template <int CWS, int LWS>
 struct LaneQuery {
@@ -93,36 +123,40 @@ struct LaneQuery {
             for (int w = 0; w < LWS; ++w) l[w] = live ? a.ql[q * LWS + w] : 0u;
         }
     }
-    // Hamming distance to the row at `rc` (padding words are zero on both sides)
-    __device__ __forceinline__ int bucket(const uint32_t* __restrict__ rc) const {
+    // Hamming distance to the staged row at shared address `rc` (padding words are zero on both sides)
+    __device__ __forceinline__ int bucket(uint32_t rc) const {
         if (CWS == 2) {
-            const uint2 r = *reinterpret_cast<const uint2*>(rc);
+            const uint2 r = lds64(rc);
             return __popc(s[0] ^ r.x) + __popc(s[1] ^ r.y);
         }
-        const uint4 r = *reinterpret_cast<const uint4*>(rc);
+        const uint4 r = lds128(rc);
         return __popc(s[0] ^ r.x) + __popc(s[1] ^ r.y) + __popc(s[2 % CWS] ^ r.z) + __popc(s[3 % CWS] ^ r.w);
     }
-    __device__ __forceinline__ bool relevant(const uint32_t* __restrict__ rl) const {
+    __device__ __forceinline__ bool relevant(uint32_t rl) const {
+        constexpr int N = LWS ? LWS : 1;
         if (LWS == 0) return false;
         if (LWS == 2) {
-            const uint2 r = *reinterpret_cast<const uint2*>(rl);
-            return ((l[0] & r.x) | (l[1 % (LWS ? LWS : 1)] & r.y)) != 0u;
+            const uint2 r = lds64(rl);
+            return ((l[0] & r.x) | (l[1 % N] & r.y)) != 0u;
         }
-        const uint4 r = *reinterpret_cast<const uint4*>(rl);
-        return ((l[0] & r.x) | (l[1 % (LWS ? LWS : 1)] & r.y) | (l[2 % (LWS ? LWS : 1)] & r.z) | (l[3 % (LWS ? LWS : 1)] & r.w)) != 0u;
+        const uint4 r = lds128(rl);
+        return ((l[0] & r.x) | (l[1 % N] & r.y) | (l[2 % N] & r.z) | (l[3 % N] & r.w)) != 0u;
     }
 };
 
 // =================================================================================================================
 // pass 1
 // =================================================================================================================
-template <int CWS, int LWS>
+// COPIES sub-histograms per warp (lane % COPIES picks one): the lanes of a step collide on the few buckets around the
+// mean distance, and a collision costs a shared-memory wavefront each (r02d: 4.6 extra wavefronts per step with one copy)
+template <int CWS, int LWS, int COPIES>
 __global__ void __launch_bounds__(LANE_WARPS * 32) hist_lane_kernel(const EvalArgs a, uint32_t* __restrict__ chunk_hist) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const LaneSmem s = carve_lane_smem(smem_raw, CWS, LWS);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nbp = lane_nbp(a.nb);
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(s.rest()) + warp * nbp;
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(s.rest()) + warp * (COPIES * nbp);
+    const uint32_t cnt_u = smem_u32(cnt) + (uint32_t)(lane % COPIES) * (uint32_t)nbp * 4u;
     const int chunk = blockIdx.y;
     const int64_t q = (int64_t)blockIdx.x * LANE_WARPS + warp;
     const int64_t c_begin = (int64_t)chunk * a.chunk_rows;
@@ -136,7 +170,7 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) hist_lane_kernel(const EvalAr
     }
     LaneQuery<CWS, LWS> qu;
     qu.load(a, q);
-    for (int b = lane; b < nbp; b += 32) cnt[b] = 0u;
+    for (int b = lane; b < COPIES * nbp; b += 32) cnt[b] = 0u;
     __syncthreads();
     lane_load_stage<CWS, LWS>(a, s, 0, c_begin, min(LANE_ROWS, c_rows));
     if (n_tiles > 1) lane_load_stage<CWS, LWS>(a, s, 1, c_begin + LANE_ROWS, min(LANE_ROWS, c_rows - LANE_ROWS));
@@ -145,19 +179,17 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) hist_lane_kernel(const EvalAr
         const int st = t & 1;
         mbar_wait(s.bar(st), (t >> 1) & 1);
         const int rows = min(LANE_ROWS, c_rows - t * LANE_ROWS);
-        const uint32_t* __restrict__ tc = s.codes(st);
-        const uint32_t* __restrict__ tl = s.labels(st);
+        const uint32_t tc = smem_u32(s.codes(st)) + (uint32_t)lane * (CWS * 4u);
+        const uint32_t tl = smem_u32(s.labels(st)) + (uint32_t)lane * (LWS * 4u);
         const int full = rows & ~31;
 #pragma unroll 4
         for (int g = 0; g < full; g += 32) {
-            const int r = g + lane;
-            const int d = qu.bucket(tc + r * CWS);
-            atomicAdd(&cnt[d], qu.relevant(tl + r * LWS) ? 0x10001u : 1u);   // shared-memory atomic; order is irrelevant here
+            const int d = qu.bucket(tc + (uint32_t)g * (CWS * 4u));
+            red_add_shared(cnt_u + 4u * (uint32_t)d, qu.relevant(tl + (uint32_t)g * (LWS * 4u)) ? 0x10001u : 1u);   // order is irrelevant here
         }
         if (full + lane < rows) {
-            const int r = full + lane;
-            const int d = qu.bucket(tc + r * CWS);
-            atomicAdd(&cnt[d], qu.relevant(tl + r * LWS) ? 0x10001u : 1u);
+            const int d = qu.bucket(tc + (uint32_t)full * (CWS * 4u));
+            red_add_shared(cnt_u + 4u * (uint32_t)d, qu.relevant(tl + (uint32_t)full * (LWS * 4u)) ? 0x10001u : 1u);
         }
         __syncthreads();  // everyone is done with stage st
         if (t + 2 < n_tiles)
@@ -165,7 +197,12 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) hist_lane_kernel(const EvalAr
     }
     __syncwarp();
     if (q < a.nq_pad)
-        for (int b = lane; b < a.nb; b += 32) chunk_hist[hist_index_W(a, chunk, b, q)] = cnt[b];
+        for (int b = lane; b < a.nb; b += 32) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int c = 0; c < COPIES; ++c) v += cnt[c * nbp + b];     // (all | rel << 16): no carry between the halves, counts <= 65520
+            chunk_hist[hist_index_W(a, chunk, b, q)] = v;
+        }
 }
 
 // =================================================================================================================
@@ -177,7 +214,6 @@ __device__ __forceinline__ float lane_u2f(uint32_t x) {
     if (BIG) return (float)x;
     return __uint_as_float(0x4B000000u | x) - 8388608.0f;
 }
-
 // 1 / y for y >= 1: one MUFU.RCP, without the denormal rescaling __fdividef / __frcp_rn carry around
 __device__ __forceinline__ float lane_rcp(float y) {
     float r;
@@ -185,7 +221,12 @@ __device__ __forceinline__ float lane_rcp(float y) {
     return r;
 }
 
-template <int CWS, int LWS, bool BIG>
+// A counter entry is 16 bytes: (rows ranked so far in the bucket, relevant rows among them, peer mask of the even lanes,
+// peer mask of the odd lanes).  PEERS = 0: the lanes that share a bucket in a step are found with __match_any_sync;
+// PEERS = 1: every lane ORs its bit into the entry of its bucket (a shared-memory reduction; even and odd lanes use
+// different words, i.e. different banks) and reads the mask back with the counters - MATCH.ANY carries ~half of the stall
+// samples of the r02d capture.  Either way the last lane of a group writes the group's final ranks and clears the masks.
+template <int CWS, int LWS, bool BIG, int PEERS>
 __global__ void __launch_bounds__(LANE_WARPS * 32) rank_lane_kernel(const EvalArgs a, const uint2* __restrict__ base,
                                                                     const uint32_t* __restrict__ total_arr, const TopnList topn,
                                                                     double* __restrict__ ap_part,
@@ -194,8 +235,9 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) rank_lane_kernel(const EvalAr
     const LaneSmem s = carve_lane_smem(smem_raw, CWS, LWS);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nbp = lane_nbp(a.nb);
-    uint2* cnt = reinterpret_cast<uint2*>(s.rest()) + warp * nbp;
-    uint32_t* hits = reinterpret_cast<uint32_t*>(s.rest() + (size_t)LANE_WARPS * nbp * 8) + warp * CMH_MAX_TOPN;
+    uint4* cnt = reinterpret_cast<uint4*>(s.rest()) + warp * nbp;
+    const uint32_t cnt_u = smem_u32(cnt);
+    uint32_t* hits = reinterpret_cast<uint32_t*>(s.rest() + (size_t)LANE_WARPS * nbp * 16) + warp * CMH_MAX_TOPN;
     const int chunk = blockIdx.y;
     const int64_t q = (int64_t)blockIdx.x * LANE_WARPS + warp;
     const bool qlive = q < a.nq_pad;
@@ -203,6 +245,7 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) rank_lane_kernel(const EvalAr
     const int c_rows = (int)min((int64_t)a.chunk_rows, a.nd - c_begin);
     const int n_tiles = (c_rows + LANE_ROWS - 1) / LANE_ROWS;
     const uint32_t lt = lanemask_lt();
+    const uint32_t my_bit = 1u << lane, my_mask_off = 8u + 4u * (uint32_t)(lane & 1);
 
     if (threadIdx.x == 0) {
         mbar_init(s.bar(0), 1);
@@ -212,8 +255,10 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) rank_lane_kernel(const EvalAr
     LaneQuery<CWS, LWS> qu;
     qu.load(a, q);
     const uint32_t total = qlive ? total_arr[q] : 0u;
-    for (int b = lane; b < nbp; b += 32)
-        cnt[b] = (qlive && b < a.nb) ? base[hist_index_W(a, chunk, b, q)] : make_uint2(0u, 0u);
+    for (int b = lane; b < nbp; b += 32) {
+        const uint2 v = (qlive && b < a.nb) ? base[hist_index_W(a, chunk, b, q)] : make_uint2(0u, 0u);
+        cnt[b] = make_uint4(v.x, v.y, 0u, 0u);
+    }
     for (int i = lane; i < a.ntopn; i += 32) hits[i] = 0u;
     __syncthreads();
     lane_load_stage<CWS, LWS>(a, s, 0, c_begin, min(LANE_ROWS, c_rows));
@@ -225,17 +270,26 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) rank_lane_kernel(const EvalAr
         const int st = t & 1;
         mbar_wait(s.bar(st), (t >> 1) & 1);
         const int rows = min(LANE_ROWS, c_rows - t * LANE_ROWS);
-        const uint32_t* __restrict__ tc = s.codes(st);
-        const uint32_t* __restrict__ tl = s.labels(st);
+        const uint32_t tc = smem_u32(s.codes(st)) + (uint32_t)lane * (CWS * 4u);
+        const uint32_t tl = smem_u32(s.labels(st)) + (uint32_t)lane * (LWS * 4u);
         float acc_t = 0.f;      // <= 16 terms <= 1 per lane and stage: float32 rounding stays below 16 * 2^-24 relative
         // one step = 32 rows, lane = row.  `in`: false only for the idle lanes of a chunk's ragged last step.
         auto step = [&](int g, bool in) {
-            const int r = g + lane;
-            const int d = in ? qu.bucket(tc + r * CWS) : a.nb;       // idle lanes park in bucket nb
-            const bool rel = in && qu.relevant(tl + r * LWS);
-            const uint32_t grp = __match_any_sync(0xffffffffu, d);   // the lanes (rows) of this step in my bucket
+            const int d = in ? qu.bucket(tc + (uint32_t)g * (CWS * 4u)) : a.nb;      // idle lanes park in bucket nb
+            const bool rel = in && qu.relevant(tl + (uint32_t)g * (LWS * 4u));
+            const uint32_t ent = cnt_u + 16u * (uint32_t)d;
+            uint32_t grp;
+            uint4 c;
+            if (PEERS == 0) {
+                grp = __match_any_sync(0xffffffffu, d);              // the lanes (rows) of this step in my bucket
+                c = lds128(ent);
+            } else {
+                red_or_shared(ent + my_mask_off, my_bit);
+                __syncwarp();                                        // every lane of the step has announced itself
+                c = lds128(ent);
+                grp = c.z | c.w;
+            }
             const uint32_t relmask = __ballot_sync(0xffffffffu, rel);
-            const uint2 c = cnt[d];
             const uint32_t below = grp & lt;                         // ... of lower index
             const uint32_t rank = c.x + (uint32_t)__popc(below) + 1u;
             const uint32_t rr = c.y + (uint32_t)__popc(below & relmask) + (rel ? 1u : 0u);
@@ -247,8 +301,8 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) rank_lane_kernel(const EvalAr
                 while (rank > topn.n[i]) ++i;
                 atomicAdd(&hits[i], 1u);
             }
-            __syncwarp();                                            // every lane has read its counter
-            if ((grp >> lane) == 1u) cnt[d] = make_uint2(rank, rr);  // the last row of the group leaves its own ranks behind
+            __syncwarp();                                            // every lane has read its entry
+            if ((grp >> lane) == 1u) sts128(ent, make_uint4(rank, rr, 0u, 0u));   // the group's last row leaves its ranks behind
             __syncwarp();
         };
         const int full = rows & ~31;
@@ -279,15 +333,30 @@ static int prep_lane(Kern kern, size_t smem) {
     return CMH_OK;
 }
 
+// CMH_LANE_MODE (measurement aid): bit 0 = peers through shared-memory OR instead of MATCH.ANY (pass 2), bit 1 = four
+// sub-histograms per warp instead of one (pass 1)
+static int lane_mode() {
+    static const int mode = [] { const char* e = getenv("CMH_LANE_MODE"); return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : LANE_MODE_DEFAULT; }();
+    return mode;
+}
+
 int launch_hist_lane(const EvalArgs& a, uint32_t* chunk_hist, cudaStream_t st) {
     const dim3 grid((unsigned)(a.nq_pad / LANE_WARPS), (unsigned)a.n_chunks);
     const size_t smem = lane_smem_bytes(a, 0);
-#define CMH_GO(CWS_, LWS_)                                                  \
-    do {                                                                    \
-        auto k = hist_lane_kernel<CWS_, LWS_>;                              \
-        int rc = prep_lane(k, smem);                                        \
-        if (rc) return rc;                                                  \
-        k<<<grid, LANE_WARPS * 32, smem, st>>>(a, chunk_hist);              \
+    const bool four = (lane_mode() & 2) != 0;
+#define CMH_GO(CWS_, LWS_)                                                       \
+    do {                                                                         \
+        if (four) {                                                              \
+            auto k = hist_lane_kernel<CWS_, LWS_, 4>;                            \
+            int rc = prep_lane(k, smem);                                         \
+            if (rc) return rc;                                                   \
+            k<<<grid, LANE_WARPS * 32, smem, st>>>(a, chunk_hist);               \
+        } else {                                                                 \
+            auto k = hist_lane_kernel<CWS_, LWS_, 1>;                            \
+            int rc = prep_lane(k, smem);                                         \
+            if (rc) return rc;                                                   \
+            k<<<grid, LANE_WARPS * 32, smem, st>>>(a, chunk_hist);               \
+        }                                                                        \
     } while (0)
     if (a.cw_stride == 2) {
         if (a.lw_stride == 0) CMH_GO(2, 0); else if (a.lw_stride == 2) CMH_GO(2, 2); else CMH_GO(2, 4);
@@ -304,20 +373,22 @@ int launch_rank_lane(const EvalArgs& a, const uint2* base, const uint32_t* total
     const dim3 grid((unsigned)(a.nq_pad / LANE_WARPS), (unsigned)a.n_chunks);
     const size_t smem = lane_smem_bytes(a, 1);
     const bool big = a.big_ranks != 0;
-#define CMH_GO(CWS_, LWS_, BIG_)                                                        \
+    const bool peers_or = (lane_mode() & 1) != 0;
+#define CMH_GO(CWS_, LWS_, BIG_, P_)                                                    \
     do {                                                                                \
-        auto k = rank_lane_kernel<CWS_, LWS_, BIG_>;                                    \
+        auto k = rank_lane_kernel<CWS_, LWS_, BIG_, P_>;                                \
         int rc = prep_lane(k, smem);                                                    \
         if (rc) return rc;                                                              \
         k<<<grid, LANE_WARPS * 32, smem, st>>>(a, base, total, tl, ap_part, hits_part); \
     } while (0)
-#define CMH_ROW(CWS_)                                                                   \
+#define CMH_PICK(CWS_, LWS_)                                                            \
     do {                                                                                \
-        if (a.lw_stride == 2) { if (big) CMH_GO(CWS_, 2, true); else CMH_GO(CWS_, 2, false); } \
-        else                  { if (big) CMH_GO(CWS_, 4, true); else CMH_GO(CWS_, 4, false); } \
+        if (big) { if (peers_or) CMH_GO(CWS_, LWS_, true, 1); else CMH_GO(CWS_, LWS_, true, 0); }   \
+        else     { if (peers_or) CMH_GO(CWS_, LWS_, false, 1); else CMH_GO(CWS_, LWS_, false, 0); } \
     } while (0)
-    if (a.cw_stride == 2) CMH_ROW(2); else CMH_ROW(4);
-#undef CMH_ROW
+    if (a.cw_stride == 2) { if (a.lw_stride == 2) CMH_PICK(2, 2); else CMH_PICK(2, 4); }
+    else                  { if (a.lw_stride == 2) CMH_PICK(4, 2); else CMH_PICK(4, 4); }
+#undef CMH_PICK
 #undef CMH_GO
     CMH_LAUNCH_CHECK("rank_lane_kernel");
     return CMH_OK;

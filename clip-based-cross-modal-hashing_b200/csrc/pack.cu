@@ -61,7 +61,7 @@ __device__ __forceinline__ void warp_count_flush(unsigned long long a, unsigned 
 // are in flight before the first is used; lane u keeps word u and lanes 0..7 store 32 contiguous bytes per plane.
 // ~0.3 warp instructions per float (r02a capture of the float4 / shuffle version this replaces: 0.9, ALU pipe 75 %
 // busy at 54 % of the HBM rate - the per-element 64-bit counters and a 64-bit division per stored word).
-constexpr int PACK_UNROLL = 8;
+constexpr int PACK_UNROLL = 16;
 
 template <bool SAME_STRIDE>   // words per row in == words per row out (bits % 64 == 0): the flat word index is the output index
 __global__ void __launch_bounds__(256) pack_codes_f32_fast(const float* __restrict__ x, int64_t n_elems,
@@ -126,15 +126,15 @@ __global__ void __launch_bounds__(256) pack_labels_f32_fast(const float* __restr
     for (int64_t r0 = warp * 32; r0 < n; r0 += n_warps * 32) {
         const int64_t e0 = r0 * ncols;
         uint32_t mine = 0;
-        for (int w = 0; w < ncols; w += 4) {          // 4 independent loads in flight
-            float v[4];
+        for (int w = 0; w < ncols; w += 16) {         // up to 16 independent 128-byte loads per lane in flight
+            float v[16];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 16; ++u) {
                 const int64_t e = e0 + (int64_t)(w + u) * 32 + lane;
                 v[u] = (w + u < ncols && e < n_elems) ? __ldcs(x + e) : 0.f;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 16; ++u) {
                 const uint32_t word = __ballot_sync(0xffffffffu, v[u] != 0.f);
                 n_neg += v[u] < 0.f ? 1u : 0u;
                 if (lane == w + u) mine = word;
@@ -324,7 +324,7 @@ extern "C" int cmh_pack_codes(const void* x, int dtype, int64_t n, int bits, int
         const int64_t n_elems = n * bits;
         const int block = 256;
         // 8 resident CTAs per SM (2048 threads): 8 x 128-byte loads per lane keep ~64 KB per SM in flight
-        int grid = (int)std::min<int64_t>(ceil_div(n_elems / 32, (int64_t)(block / 32) * PACK_UNROLL), (int64_t)sm_count() * 8);
+        int grid = (int)std::min<int64_t>(ceil_div(n_elems / 32, (int64_t)(block / 32) * PACK_UNROLL), (int64_t)sm_count() * 6);
         if (grid < 1) grid = 1;
         if (bits % 64 == 0)
             pack_codes_f32_fast<true><<<grid, block, 0, st>>>((const float*)x, n_elems, bits / 32, words * 2,

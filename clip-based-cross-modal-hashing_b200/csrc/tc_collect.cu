@@ -1233,7 +1233,8 @@ static void tc_geometry(int64_t nq, int64_t nd, int words, int64_t* n_qgroups, i
     *n_qgroups = std::max<int64_t>(1, ceil_div(nq, (int64_t)tc_T(words) * TC_M));
     // CTAs = query groups x chunks: as many as fit 4 full waves of one CTA per SM (rounding UP would add a fifth,
     // nearly empty wave: +25 % time)
-    int64_t want = std::max<int64_t>(1, ((int64_t)sm_count() * 4) / *n_qgroups);
+    static const int waves = [] { const char* e = getenv("CMH_TC_WAVES"); return (e && e[0] >= '1' && e[0] <= '8') ? e[0] - '0' : 4; }();
+    int64_t want = std::max<int64_t>(1, ((int64_t)sm_count() * waves) / *n_qgroups);
     want = std::min<int64_t>(want, TC_MAX_CHUNKS / (TC_BUFS / tc_T(words)));
     int64_t rows = round_up(std::max<int64_t>(1, ceil_div(nd, want)), TC_N);
     rows = std::max<int64_t>(rows, 16 * TC_N);

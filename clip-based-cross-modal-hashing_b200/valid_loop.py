@@ -1,0 +1,237 @@
+"""Config 5 - the end-to-end validation loop: encoder -> hash head -> packed codes -> mAP.
+
+The reference's `valid()` (`train/base.py:242-262`) runs `get_code_DCHMT` (`:160-178`) over the query and the retrieval
+loader - CLIP ViT-B/32 (`model/base/model.py:210-372`) + the DCHMT hash head (`model/DCHMT.py:8-26`) per batch, in
+float32 with autograd on and `nn.MultiheadAttention`, then argmax + float code buffers (`:150-158`) - and hands the
+buffers to `calc_map_k` four times.  Here:
+
+  * the encoder is the same architecture (same parameter names, so a reference state dict loads as it is) run under
+    `torch.no_grad()` in bfloat16 with fused scaled-dot-product attention - library GEMMs / attention, not part of the
+    hand-written path;
+  * the head is ONE kernel, `cmh_hash_head_pack` (`CodeBuffer.put_head`): `bits` x Linear(128, 2) + softmax + argmax +
+    pack + scatter by dataset index - logits, float codes and the float `[N, bits]` buffers never exist;
+  * batches are double-buffered: the next batch's pinned-host -> device copy runs on a copy stream under the current
+    batch's encoder;
+  * the four evaluation calls take the packed buffers as they are (`calc_map_k_matrix` accepts `CodeBuffer`s).
+
+`/root/reference` holds no checkpoint (and there is no network): weights are random-init with the reference's own
+initialisers; parity of the architecture is pinned by `tests/golden/clip_tiny.npz` (a small configuration of the
+reference's `CLIP` class run by `tests/golden/make_golden_clip.py`).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Iterable, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+@dataclass(frozen=True)
+class ClipConfig:
+    """`build_model`'s shape parameters (`model/base/model.py:415-447`); the defaults are ViT-B/32."""
+    embed_dim: int = 512
+    image_resolution: int = 224
+    vision_layers: int = 12
+    vision_width: int = 768
+    vision_patch_size: int = 32
+    context_length: int = 77
+    vocab_size: int = 49408
+    transformer_width: int = 512
+    transformer_heads: int = 8
+    transformer_layers: int = 12
+
+
+class _Attention(nn.Module):
+    """Parameter layout of `nn.MultiheadAttention` (`in_proj_weight`, `in_proj_bias`, `out_proj`), fused SDPA inside."""
+
+    def __init__(self, width: int, heads: int):
+        super().__init__()
+        self.heads = heads
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * width, width))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * width))
+        self.out_proj = nn.Linear(width, width)
+
+    def forward(self, x: torch.Tensor, causal: bool) -> torch.Tensor:          # x [N, L, D]
+        n, l, d = x.shape
+        qkv = F.linear(x, self.in_proj_weight, self.in_proj_bias).view(n, l, 3, self.heads, d // self.heads)
+        q, k, v = qkv.permute(2, 0, 3, 1, 4)                                   # [N, H, L, hd] each
+        o = F.scaled_dot_product_attention(q, k, v, is_causal=causal)
+        return self.out_proj(o.transpose(1, 2).reshape(n, l, d))
+
+
+class _Block(nn.Module):
+    """`ResidualAttentionBlock` (`model/base/model.py:167-196`): pre-LN attention + pre-LN MLP with QuickGELU."""
+
+    def __init__(self, width: int, heads: int):
+        super().__init__()
+        self.attn = _Attention(width, heads)
+        self.ln_1 = nn.LayerNorm(width)
+        self.mlp = nn.Sequential()
+        self.mlp.add_module("c_fc", nn.Linear(width, width * 4))
+        self.mlp.add_module("c_proj", nn.Linear(width * 4, width))
+        self.ln_2 = nn.LayerNorm(width)
+
+    def forward(self, x: torch.Tensor, causal: bool) -> torch.Tensor:
+        x = x + self.attn(self.ln_1(x), causal)
+        h = self.mlp.c_fc(self.ln_2(x))
+        return x + self.mlp.c_proj(h * torch.sigmoid(1.702 * h))              # QuickGELU (:162-164)
+
+
+class _Transformer(nn.Module):
+    def __init__(self, width: int, layers: int, heads: int):
+        super().__init__()
+        self.width, self.layers = width, layers
+        self.resblocks = nn.ModuleList([_Block(width, heads) for _ in range(layers)])
+
+    def forward(self, x: torch.Tensor, causal: bool) -> torch.Tensor:
+        for blk in self.resblocks:
+            x = blk(x, causal)
+        return x
+
+
+class _Visual(nn.Module):
+    """`VisionTransformer` (`model/base/model.py:210-252`)."""
+
+    def __init__(self, cfg: ClipConfig):
+        super().__init__()
+        w, p = cfg.vision_width, cfg.vision_patch_size
+        self.conv1 = nn.Conv2d(3, w, kernel_size=p, stride=p, bias=False)
+        scale = w ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(w))
+        self.positional_embedding = nn.Parameter(scale * torch.randn((cfg.image_resolution // p) ** 2 + 1, w))
+        self.ln_pre = nn.LayerNorm(w)
+        self.transformer = _Transformer(w, cfg.vision_layers, w // 64)
+        self.ln_post = nn.LayerNorm(w)
+        self.proj = nn.Parameter(scale * torch.randn(w, cfg.embed_dim))
+
+    def forward(self, image: torch.Tensor) -> torch.Tensor:
+        x = self.conv1(image)                                                  # [N, w, g, g]
+        x = x.flatten(2).transpose(1, 2)                                       # [N, g*g, w]
+        cls = self.class_embedding.to(x.dtype).expand(x.shape[0], 1, -1)
+        x = torch.cat([cls, x], dim=1) + self.positional_embedding.to(x.dtype)
+        x = self.transformer(self.ln_pre(x), causal=False)
+        return self.ln_post(x[:, 0, :]) @ self.proj
+
+
+class Clip(nn.Module):
+    """`CLIP` (`model/base/model.py:255-372`), ViT image tower + causal text tower, same parameter names."""
+
+    def __init__(self, cfg: ClipConfig = ClipConfig()):
+        super().__init__()
+        self.cfg = cfg
+        self.visual = _Visual(cfg)
+        self.transformer = _Transformer(cfg.transformer_width, cfg.transformer_layers, cfg.transformer_heads)
+        self.token_embedding = nn.Embedding(cfg.vocab_size, cfg.transformer_width)
+        self.positional_embedding = nn.Parameter(torch.empty(cfg.context_length, cfg.transformer_width))
+        self.ln_final = nn.LayerNorm(cfg.transformer_width)
+        self.text_projection = nn.Parameter(torch.empty(cfg.transformer_width, cfg.embed_dim))
+        self.logit_scale = nn.Parameter(torch.ones([]) * 2.6592)
+        self.initialize_parameters()
+
+    def initialize_parameters(self) -> None:                                    # :311-338
+        nn.init.normal_(self.token_embedding.weight, std=0.02)
+        nn.init.normal_(self.positional_embedding, std=0.01)
+        for tower in (self.transformer, self.visual.transformer):
+            proj_std = (tower.width ** -0.5) * ((2 * tower.layers) ** -0.5)
+            for blk in tower.resblocks:
+                nn.init.normal_(blk.attn.in_proj_weight, std=tower.width ** -0.5)
+                nn.init.normal_(blk.attn.out_proj.weight, std=proj_std)
+                nn.init.normal_(blk.mlp.c_fc.weight, std=(2 * tower.width) ** -0.5)
+                nn.init.normal_(blk.mlp.c_proj.weight, std=proj_std)
+        nn.init.normal_(self.text_projection, std=self.transformer.width ** -0.5)
+
+    def encode_image(self, image: torch.Tensor) -> torch.Tensor:               # :356-357
+        return self.visual(image.to(self.visual.conv1.weight.dtype))
+
+    def encode_text(self, text: torch.Tensor) -> torch.Tensor:                 # :359-372
+        x = self.token_embedding(text)
+        x = x + self.positional_embedding[:x.size(1), :].to(x.dtype)
+        x = self.ln_final(self.transformer(x, causal=True))
+        # features of the end-of-text token (the highest token id in each sequence)
+        return x[torch.arange(x.shape[0], device=x.device), text.argmax(dim=-1)] @ self.text_projection
+
+
+class DchmtHead(nn.Module):
+    """`HashLayer` (`model/DCHMT.py:8-26`): fc(embed -> 128) + relu, then `bits` separate Linear(128, 2) - kept as ONE
+    stacked weight [bits, 2, 128] / bias [bits, 2] (row j = `hash_list[j]`)."""
+    LINEAR_EMBED = 128
+
+    def __init__(self, input_dim: int, bits: int):
+        super().__init__()
+        self.fc = nn.Linear(input_dim, self.LINEAR_EMBED)
+        self.weight = nn.Parameter(torch.empty(bits, 2, self.LINEAR_EMBED))
+        self.bias = nn.Parameter(torch.zeros(bits, 2))
+        nn.init.kaiming_uniform_(self.fc.weight, mode="fan_out")              # weights_init_kaiming (model/modelbase.py:10-14)
+        nn.init.zeros_(self.fc.bias)
+        with torch.no_grad():
+            for j in range(bits):                                             # every Linear(128, 2) on its own, as there
+                nn.init.kaiming_uniform_(self.weight[j], mode="fan_out")
+
+    def hidden(self, feat: torch.Tensor) -> torch.Tensor:
+        """fc only; relu, the 2 * bits logits, argmax, pack and scatter happen inside `CodeBuffer.put_head`."""
+        return self.fc(feat)
+
+
+class DchmtModel(nn.Module):
+    """`MDCMHT` (`model/DCHMT.py:29-45`) for evaluation: CLIP + one hash head per modality."""
+
+    def __init__(self, bits: int = 64, cfg: ClipConfig = ClipConfig()):
+        super().__init__()
+        self.bits = bits
+        self.clip = Clip(cfg)
+        self.image_hash = DchmtHead(cfg.embed_dim, bits)
+        self.text_hash = DchmtHead(cfg.embed_dim, bits)
+
+
+def get_code_dchmt(model: DchmtModel, batches: Iterable[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]], length: int,
+                   device: torch.device):
+    """`get_code_DCHMT` (`train/base.py:160-178`): ``batches`` yields (image [n, 3, R, R], text int64 [n, ctx], index int64
+    [n]) on the HOST (pinned memory makes the copies asynchronous); returns the image and text `CodeBuffer`s, rows placed by
+    dataset index.  The copy of batch i+1 overlaps the encoder of batch i (copy stream + one event per batch)."""
+    from .codes import CodeBuffer
+    img, txt = CodeBuffer(length, model.bits, device), CodeBuffer(length, model.bits, device)
+    copy_stream = torch.cuda.Stream(device)
+    compute = torch.cuda.current_stream(device)
+    dtype = model.clip.visual.conv1.weight.dtype
+
+    def stage(batch):
+        image, text, index = batch
+        with torch.cuda.stream(copy_stream):
+            d = (image.to(device, non_blocking=True).to(dtype), text.to(device, non_blocking=True),
+                 index.to(device, non_blocking=True))
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return d, ev
+
+    it = iter(batches)
+    nxt = next(it, None)
+    staged = stage(nxt) if nxt is not None else None
+    with torch.no_grad():
+        while staged is not None:
+            (image, text, index), ev = staged
+            nxt = next(it, None)
+            staged = stage(nxt) if nxt is not None else None       # the next batch travels while this one is encoded
+            compute.wait_event(ev)
+            for t in (image, text, index):
+                t.record_stream(compute)
+            img.put_head(index, model.image_hash.hidden(model.clip.encode_image(image)), model.image_hash.weight,
+                         model.image_hash.bias, relu=True)
+            txt.put_head(index, model.text_hash.hidden(model.clip.encode_text(text)), model.text_hash.weight,
+                         model.text_hash.bias, relu=True)
+    return img, txt
+
+
+def valid(model: DchmtModel, query_batches, retrieval_batches, query_labels, retrieval_labels, n_query: int, n_retrieval: int,
+          device: torch.device, k: Optional[int] = None):
+    """`TrainBase.valid` (`train/base.py:242-262`): codes of both loaders, then the four directions of `calc_map_k`
+    (i->t, t->i, i->i, t->t) on the packed buffers.  Returns the four mAPs as 0-d float32 CPU tensors."""
+    from . import calc_utils as cu
+    q_img, q_txt = get_code_dchmt(model, query_batches, n_query, device)
+    r_img, r_txt = get_code_dchmt(model, retrieval_batches, n_retrieval, device)
+    rank = device.index if device.index is not None else 0
+    return (cu.calc_map_k_matrix(q_img, r_txt, query_labels, retrieval_labels, k, rank),
+            cu.calc_map_k_matrix(q_txt, r_img, query_labels, retrieval_labels, k, rank),
+            cu.calc_map_k_matrix(q_img, r_img, query_labels, retrieval_labels, k, rank),
+            cu.calc_map_k_matrix(q_txt, r_txt, query_labels, retrieval_labels, k, rank))

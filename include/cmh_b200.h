@@ -107,6 +107,16 @@ int cmh_unpack_codes(const uint64_t* sign, const uint64_t* valid, int64_t n, int
  * counters (device uint64 [2], may be NULL) += (#exact zeros, #rows whose index is outside [0, n_out): not written). */
 int cmh_pack_scatter(const void* x, int dtype, int64_t n, int bits, int64_t ld, int mode, const int64_t* index,
                      int64_t n_out, uint64_t* sign_out, uint64_t* valid_out, unsigned long long* counters, void* stream);
+/* The DCHMT hash head fused with binarise + pack + scatter (model/DCHMT.py:16-26 + train/base.py:150-158,176-177): `bits`
+ * separate Linear(hidden, 2) + softmax + argmax (class 0 -> -1) as ONE [hidden, 2 * bits] product whose epilogue emits
+ * packed bits, bit j = [logit(j, 1) > logit(j, 0)] (a tie is class 0), written at row index[i] (NULL: row i) of the
+ * packed planes.  x: device [n][ld] activations of `dtype` (F32 / F16 / BF16; the first `hidden` columns; relu != 0
+ * applies max(x, 0) first, model/DCHMT.py:22); weight: device float [bits][2][hidden] (the Linear weights stacked); bias:
+ * device float [bits][2] or NULL; valid_out (may be NULL) gets all real bits set; counters[1] += rows whose index is
+ * outside [0, n_out).  Logits are accumulated in float32 and never stored. */
+int cmh_hash_head_pack(const void* x, int dtype, int64_t n, int hidden, int64_t ld, int relu, const float* weight,
+                       const float* bias, int bits, const int64_t* index, int64_t n_out, uint64_t* sign_out,
+                       uint64_t* valid_out, unsigned long long* counters, void* stream);
 /* L: device [n][ld] multi-hot (non-negative).  out: device [n][lwords].  neg_counter: device uint64[1],
  * incremented by #entries < 0 (the reference's `dot > 0` predicate is only a set intersection for L >= 0). */
 int cmh_pack_labels(const void* L, int dtype, int64_t n, int nlab, int64_t ld,

@@ -119,7 +119,8 @@ def test_plan_geometry(cuda_lib):
         assert plan.chunk_rows % 16 == 0 and plan.chunk_rows <= 65520
         assert plan.n_chunks * plan.chunk_rows >= nd
         assert plan.nq_pad % plan.q_tile == 0 and plan.nq_pad >= nq
-        assert plan.design == (0 if plan.nb <= 200 else 1)
+        lane = (not tern) and nlab > 0 and 65 <= plan.nb <= 257 and nlab <= 128       # 64 .. 128-bit binary codes with labels
+        assert plan.design == (2 if lane else (0 if plan.nb <= 200 else 1))
         assert plan.workspace_bytes > 0
 
 

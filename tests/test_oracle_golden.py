@@ -130,3 +130,24 @@ def test_live_reference_agrees_with_oracle(name):
         assert abs(c_oracle.map_k(T["qB"][:n].numpy(), T["rB"].numpy(), T["qL"][:n].numpy(), T["rL"].numpy(), k)[0] - want) < TOL
     mod = ref.load()
     assert torch.equal(mod.calc_hammingDist(T["qB"][:4], T["rB"][:100]), orc.hamming_dist(T["qB"][:4], T["rB"][:100]))
+
+
+def test_valid_loop_encoder_matches_reference_clip():
+    """f2: `cmh_b200.valid_loop.Clip` (fused attention, same parameter names) loaded with the state dict of the
+    reference's own `CLIP` class reproduces its `encode_image` / `encode_text` (golden made by
+    tests/golden/make_golden_clip.py from /root/reference/model/base/model.py) in float32 within 2e-5."""
+    import os
+    import numpy as np
+    import torch
+    from cmh_b200.valid_loop import Clip, ClipConfig
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "clip_tiny.npz"))
+    cfg = ClipConfig(*[int(v) for v in z["cfg"]])
+    model = Clip(cfg).float().eval()
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    with torch.no_grad():
+        img = model.encode_image(torch.from_numpy(z["image"]))
+        txt = model.encode_text(torch.from_numpy(z["text"]))
+    np.testing.assert_allclose(img.numpy(), z["img_feat"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(txt.numpy(), z["txt_feat"], rtol=0, atol=2e-5)
