@@ -327,7 +327,7 @@ def bench_also(dev, local, hbm_peak, cpu=True):
     try:
         D128, Q128 = 50_000_000, 8192
         db = engine.synth_codes(SEED + 128, 0, D128, 128, dev)
-        idx = HammingIndex(db, 0, nd_total=D128, assume_binary=True)
+        idx = HammingIndex(db, 0, group=False, nd_total=D128, assume_binary=True)
         qs = [engine.synth_codes(SEED + 129, i * Q128, Q128, 128, dev) for i in range(4)]
         st = {}
         idx.search_packed(qs[0], TOPK)
@@ -343,7 +343,70 @@ def bench_also(dev, local, hbm_peak, cpu=True):
         del db, idx, qs
     except Exception as e:  # noqa: BLE001 - a secondary leg must not take the headline down
         also["bits128"] = {"error": repr(e)}
+    try:
+        also["c5_e2e"] = bench_c5(dev, local)
+    except Exception as e:  # noqa: BLE001
+        also["c5_e2e"] = {"error": repr(e)}
     return also
+
+
+def bench_c5(dev, local):
+    """BASELINE.json config 5 end to end: random-init CLIP ViT-B/32 + DCHMT hash head (bf16, no_grad, fused attention)
+    encodes a 5,000-query and a 100,000-row retrieval set from HOST batches (pinned, double-buffered H2D), the head +
+    argmax + pack + scatter is ONE kernel per modality and batch (cmh_hash_head_pack), then the reference's four
+    calc_map_k calls (train/base.py:259-262) on the packed buffers.  Synthetic images / tokens / labels."""
+    from cmh_b200 import calc_utils as cu
+    from cmh_b200.synth import CONFIGS, make_labels
+    from cmh_b200.valid_loop import DchmtModel, get_code_dchmt
+    shape = CONFIGS["c5"]
+    bits, batch, ctx = shape.bits, 500, 32
+    torch.manual_seed(5005)
+    model = DchmtModel(bits).to(dev).to(torch.bfloat16).eval()
+    rng = np.random.default_rng(shape.seed)
+    q_lab = torch.from_numpy(make_labels(rng, shape.n_query, shape.n_labels, shape.label_p, 0.01))
+    r_lab = torch.from_numpy(make_labels(rng, shape.n_db, shape.n_labels, shape.label_p, 0.0))
+    # a pool of distinct pinned host batches, cycled (synthetic data: the H2D traffic and the encoder work are real)
+    pool = []
+    g = torch.Generator().manual_seed(55)
+    for _ in range(4):
+        image = torch.randn(batch, 3, 224, 224, generator=g).to(torch.bfloat16).pin_memory()
+        text = torch.randint(1, 49000, (batch, ctx), generator=g)
+        text[:, 0] = 49406                                                     # start of text
+        eot = torch.randint(8, ctx, (batch,), generator=g)
+        text[torch.arange(batch), eot] = 49407                                 # end of text = the highest id
+        for i in range(batch):
+            text[i, int(eot[i]) + 1:] = 0
+        pool.append((image, text.pin_memory()))
+
+    def batches(n):
+        for b0 in range(0, n, batch):
+            m = min(batch, n - b0)
+            image, text = pool[(b0 // batch) % len(pool)]
+            yield image[:m], text[:m], torch.arange(b0, b0 + m).pin_memory()
+
+    def run():
+        t0 = time.perf_counter()
+        q_img, q_txt = get_code_dchmt(model, batches(shape.n_query), shape.n_query, dev)
+        r_img, r_txt = get_code_dchmt(model, batches(shape.n_db), shape.n_db, dev)
+        torch.cuda.synchronize(dev)
+        t1 = time.perf_counter()
+        maps = [cu.calc_map_k_matrix(a, b, q_lab, r_lab, shape.k, local)
+                for a, b in ((q_img, r_txt), (q_txt, r_img), (q_img, r_img), (q_txt, r_txt))]
+        torch.cuda.synchronize(dev)
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1, [float(m) for m in maps]
+
+    get_code_dchmt(model, batches(2 * batch), 2 * batch, dev)                  # warm-up: kernels, cuBLAS plans
+    torch.cuda.synchronize(dev)
+    enc_s, eval_s, maps = run()
+    n_items = shape.n_query + shape.n_db
+    flops = n_items * (4.37e9 + 2.9e9) * 1.0                                   # ~ViT-B/32 image (50 tokens) + text (32 tokens) forward
+    return {"shape": f"{shape.n_query} queries + {shape.n_db} database items, {bits}-bit DCHMT head, batches of {batch}",
+            "encode_s": enc_s, "eval_ms_four_directions": eval_s * 1e3, "total_s": enc_s + eval_s,
+            "items_per_s": n_items / enc_s, "approx_encoder_tflops": flops / enc_s / 1e12, "maps": maps,
+            "h2d_bytes": n_items * (3 * 224 * 224 * 2 + ctx * 8 + 8),
+            "note": "encoder: torch bf16 GEMMs + fused SDPA (library code) under no_grad; head + argmax + pack + scatter: "
+                    "cmh_hash_head_pack; evaluation: packed buffers straight into calc_map_k_matrix (4 calls)"}
 
 
 def bench_sharded_map(dev, rank, world, max_over_ranks, barrier):
@@ -581,8 +644,8 @@ def main_native(args):
     # ---- secondary legs, single GPU: the reference's own evaluation calls at the shapes of configs 1-3 (+ the eval
     # stage of config 5), K1 at HBM scale, the 128-bit tensor path -----------------------------------------------
     also = None
-    if not args.no_also:
-        also = bench_also(dev, local, hbm_peak, cpu=not args.no_cpu_baseline and world == 1)
+    if not args.no_also and world == 1:          # (the other ranks have left: nothing collective may follow)
+        also = bench_also(dev, local, hbm_peak, cpu=not args.no_cpu_baseline)
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -650,6 +713,9 @@ def main_native(args):
 
 
 def main():
+    # a hang must leave evidence: every 4 minutes without finishing, every thread's stack goes to stderr
+    import faulthandler
+    faulthandler.dump_traceback_later(240, repeat=True)
     args = parse_args()
     if args.impl == "reference":
         main_reference(args)

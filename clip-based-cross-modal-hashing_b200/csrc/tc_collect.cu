@@ -1002,18 +1002,21 @@ __global__ void __launch_bounds__(256) topk_verify_kernel(const uint64_t* __rest
 // true K-th distance; only candidates with dist <= T (between K and a few K of them) are sorted - by key, i.e. by
 // (distance, global index), which is the stable ranking.  A warp walks one (query, chunk) segment at a time.
 
-__global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64_t* __restrict__ cand,
+// THREADS x MAXK: 512 x 4096 for a whole database; 256 x 2048 for the short per-shard lists of a sharded search (twice the
+// resident CTAs, half the threads per barrier: the kernel is a chain of dependent small steps per query)
+template <int THREADS, int MAXK>
+__global__ void __launch_bounds__(THREADS) topk_finalize_kernel(const uint64_t* __restrict__ cand,
                                                                     const uint32_t* __restrict__ cnt,
                                                                     const int32_t* __restrict__ thr_limit, int64_t nq,
                                                                     int n_chunks, int seg_cap, int K, int64_t nd, int partial,
                                                                     int width, uint64_t* __restrict__ keys,
                                                                     uint32_t* __restrict__ fail_flags,
                                                                     uint32_t* __restrict__ fail_count) {
-    constexpr int BLOCK = FIN_THREADS * SEG_IT;
-    __shared__ uint64_t sk[FIN_MAX];
+    constexpr int BLOCK = THREADS * SEG_IT;
+    __shared__ uint64_t sk[MAXK];
     __shared__ uint32_t hist[FIN_BINS];
-    __shared__ uint32_t s_off[BLOCK + 1], s_warp[FIN_THREADS / 32];
-    __shared__ uint32_t s_wc[FIN_THREADS / 32][8], s_base[8];
+    __shared__ uint32_t s_off[BLOCK + 1], s_warp[THREADS / 32];
+    __shared__ uint32_t s_wc[THREADS / 32][8], s_base[8];
     __shared__ int s_T, s_keep;
     __shared__ uint32_t s_total, s_over;
     const int64_t q = blockIdx.x;
@@ -1025,9 +1028,9 @@ __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64
     // pass 1: the candidates' histogram (they sit in 3-4 buckets: one add per bucket per warp)
     uint32_t raw = 0, over = 0;
     for (int c0 = 0; c0 < n_chunks; c0 += BLOCK) {
-        const uint32_t total = seg_block_offsets<FIN_THREADS>(cnt, nq, q, c0, n_chunks, (uint32_t)seg_cap, s_off, s_warp, raw, over);
+        const uint32_t total = seg_block_offsets<THREADS>(cnt, nq, q, c0, n_chunks, (uint32_t)seg_cap, s_off, s_warp, raw, over);
         const uint64_t* base = mine + (uint64_t)c0 * seg_cap;
-        for (uint32_t i0 = threadIdx.x - lane; i0 < total; i0 += FIN_THREADS) {  // warp-uniform trip count
+        for (uint32_t i0 = threadIdx.x - lane; i0 < total; i0 += THREADS) {  // warp-uniform trip count
             const uint32_t i = i0 + lane;
             const uint32_t bkt = i < total ? min((uint32_t)(seg_flat_load(base, s_off, BLOCK, (uint32_t)seg_cap, i) >> 33),
                                                  (uint32_t)(FIN_BINS - 1)) : (uint32_t)FIN_BINS;
@@ -1039,8 +1042,8 @@ __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64
     if (lane == 0 && raw) atomicAdd(&s_total, raw);
     if (over) s_over = 1u;
     __syncthreads();
-    // partial (one shard of several): emit what there is, up to K; the K-th key is judged after the merge
-    const int64_t want = partial ? min(need, (int64_t)s_total) : need;
+    // partial (one shard of several): emit what there is, up to `width`; the K-th key is judged after the merge
+    const int64_t want = partial ? min(min(need, (int64_t)width), (int64_t)s_total) : need;
     bool fail = s_over != 0u || (int64_t)s_total < want;
     if (!fail) {
         if (threadIdx.x == 0) {
@@ -1050,7 +1053,7 @@ __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64
             s_T = T;
             // buckets above thr_limit may be incomplete (launches with different thresholds): the K-th distance must
             // not come from there
-            s_keep = (cum > FIN_MAX || (thr_limit != nullptr && T > thr_limit[q])) ? -1 : (int)cum;
+            s_keep = (cum > MAXK || (thr_limit != nullptr && T > thr_limit[q])) ? -1 : (int)cum;
         }
         __syncthreads();
         fail = s_keep < 0;
@@ -1081,14 +1084,14 @@ __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64
     for (int c0 = 0; c0 < n_chunks; c0 += BLOCK) {
         // (with a single block of segments - the usual case - the offsets of pass 1 are still in place)
         const uint32_t total = n_chunks <= BLOCK ? s_off[BLOCK]
-                                                 : seg_block_offsets<FIN_THREADS>(cnt, nq, q, c0, n_chunks, (uint32_t)seg_cap, s_off, s_warp, raw, over);
+                                                 : seg_block_offsets<THREADS>(cnt, nq, q, c0, n_chunks, (uint32_t)seg_cap, s_off, s_warp, raw, over);
         const uint64_t* base = mine + (uint64_t)c0 * seg_cap;
-        for (uint32_t i0 = 0; i0 < total; i0 += FIN_THREADS) {          // block-uniform trip count
+        for (uint32_t i0 = 0; i0 < total; i0 += THREADS) {          // block-uniform trip count
             const uint32_t i = i0 + threadIdx.x;
             const uint64_t key = i < total ? seg_flat_load(base, s_off, BLOCK, (uint32_t)seg_cap, i) : ~0ull;
             const int bkt = (int)(uint32_t)(key >> 33);
             const int cls = (i < total && bkt <= T) ? min(T - bkt, 7) : 8;
-            if (threadIdx.x < (FIN_THREADS / 32) * 8) s_wc[threadIdx.x >> 3][threadIdx.x & 7] = 0u;
+            if (threadIdx.x < (THREADS / 32) * 8) s_wc[threadIdx.x >> 3][threadIdx.x & 7] = 0u;
             __syncthreads();
             const uint32_t same = __match_any_sync(0xffffffffu, cls);
             if (cls < 8 && lane == __ffs(same) - 1) s_wc[warp][cls] = (uint32_t)__popc(same);
@@ -1096,13 +1099,13 @@ __global__ void __launch_bounds__(FIN_THREADS) topk_finalize_kernel(const uint64
             if (cls < 8) {
                 uint32_t pos = s_base[cls] + (uint32_t)__popc(same & lanemask_lt());
                 for (int w = 0; w < warp; ++w) pos += s_wc[w][cls];
-                if (pos < (uint32_t)FIN_MAX) sk[pos] = key;
+                if (pos < (uint32_t)MAXK) sk[pos] = key;
             }
             __syncthreads();
             if (threadIdx.x < 8) {
                 uint32_t tot = 0;
 #pragma unroll
-                for (int w = 0; w < FIN_THREADS / 32; ++w) tot += s_wc[w][threadIdx.x];
+                for (int w = 0; w < THREADS / 32; ++w) tot += s_wc[w][threadIdx.x];
                 s_base[threadIdx.x] += tot;
             }
             __syncthreads();                     // s_wc is zeroed again by the next trip
@@ -1376,8 +1379,15 @@ int tc_finalize(const uint64_t* cand, const uint32_t* cnt, const int32_t* thr_li
                 int64_t nd, int partial, int width, uint64_t* keys, uint32_t* fail_flags, uint32_t* fail_count, cudaStream_t st) {
     if (nq == 0) return CMH_OK;
     CMH_CUDA(cudaMemsetAsync(fail_count, 0, 4, st));
-    topk_finalize_kernel<<<(unsigned)nq, FIN_THREADS, 0, st>>>(cand, cnt, partial ? nullptr : thr_limit, nq, n_chunks, seg_cap, K, nd,
-                                                              partial, width, keys, fail_flags, fail_count);
+    // the short variant holds at most 2048 candidates at or below the list's last bucket: for lists of a few hundred keys
+    // (6+ shards at K = 1000); a query that holds more is flagged and redone exactly, so the choice only costs time
+    if (partial && width <= 512)
+        topk_finalize_kernel<256, 2048><<<(unsigned)nq, 256, 0, st>>>(cand, cnt, nullptr, nq, n_chunks, seg_cap, K, nd, partial, width,
+                                                                     keys, fail_flags, fail_count);
+    else
+        topk_finalize_kernel<FIN_THREADS, FIN_MAX><<<(unsigned)nq, FIN_THREADS, 0, st>>>(cand, cnt, partial ? nullptr : thr_limit, nq, n_chunks,
+                                                                                        seg_cap, K, nd, partial, width, keys, fail_flags,
+                                                                                        fail_count);
     CMH_LAUNCH_CHECK("topk_finalize_kernel");
     return CMH_OK;
 }

@@ -67,8 +67,10 @@ class HammingIndex:
         self.db = db
         self.index_base = int(index_base)
         self.group = group
-        distributed = group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                            and torch.distributed.get_world_size() > 1)
+        # group: a process group; None = the default group when torch.distributed is initialised; False = this process
+        # alone (a local index inside a distributed job)
+        distributed = group is not False and (group is not None or (
+            torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1))
         if nd_total is None:
             nd_total = db.n
             if distributed:
@@ -133,9 +135,7 @@ class HammingIndex:
         total = n if nd_total is None else int(nd_total)
         copy_stream = torch.cuda.Stream(dev)
         copy_stream.wait_stream(torch.cuda.current_stream(dev))      # `out` may still be read by earlier work
-        world = 1
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            world = torch.distributed.get_world_size(group)
+        world = _sh._world(group)[1]
         stages = _e.tc_pilot_stages(n, total, world)
         n_pilot = stages[-1] if stages else 0
         first = n_pilot if n_pilot else min(n, max(4096, n // 64) // 256 * 256 or n)

@@ -56,7 +56,9 @@ def lockstep_stripes(n_rows: int, world: int, rank: int, fractions=LOCKSTEP_FRAC
 
 
 def _world(group) -> Tuple[int, int]:
-    if not dist.is_available() or not dist.is_initialized():
+    """(rank, world) of ``group`` (None = the default process group when one is initialised; False = this process alone,
+    whatever is initialised)."""
+    if group is False or not dist.is_available() or not dist.is_initialized():
         return 0, 1
     return dist.get_rank(group), dist.get_world_size(group)
 
