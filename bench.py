@@ -59,7 +59,7 @@ def config_dict(args, world):
     return {"workload": "c4: 64-bit exact stable top-1000 Hamming retrieval, 100M-row database, one query chunk per step",
             "bits": BITS, "topk": TOPK, "db_rows": args.db_rows, "queries_per_step": args.queries,
             "queries": "a different chunk of the config's 1M queries every step (chunk i = query rows i*Q..(i+1)*Q)",
-            "pipelining": "none: one query chunk at a time, resolved and verified before the next is enqueued",
+            "pipelining": "searches run one after the other on one stream (same scratch); the host enqueues chunk i+1 before it reads the verdict of chunk i, so the GPU does not wait for Python between chunks",
             "sharding": f"database rows over {world} GPUs in lockstep stripes (3 global stripes x {world} contiguous pieces, rank r holds piece r of each); queries replicated; all-reduced threshold / prefix-rule histograms, NCCL all-to-all by query slice + merge + verify; results stay sharded by query slice (rank r keeps slice r)"
                         if world > 1 else "single GPU holds the whole database",
             "l2": "per-step working set (packed shard + candidate segments, >1 GB) exceeds the 126 MB L2; no explicit flush",
@@ -517,23 +517,27 @@ def main_native(args):
     if rank == 0:
         sampler.start()
 
-    # One query chunk at a time, each resolved (verdict read, failed queries redone) before the next is enqueued.  With N
-    # GPUs the result stays SHARDED BY QUERY SLICE: rank r merges, verifies and keeps the keys of its slice of the chunk
-    # (`gather=False`; an all-gather of the merged keys is one flag away and is what `search_packed` does by default).
-    def run_steps(first, n, stats):
-        keys = None
+    # Query chunks are searched one after the other on one stream.  The host stays one chunk ahead: chunk i+1 is enqueued
+    # before the verdict of chunk i is read (`defer=True`), so the GPU does not idle while Python prepares the next call -
+    # the searches themselves do not overlap (same stream, same scratch).  With N GPUs the result stays SHARDED BY QUERY
+    # SLICE: rank r merges, verifies and keeps the keys of its slice of the chunk (`gather=False`; an all-gather of the
+    # merged keys is one flag away and is what `search_packed` does by default).
+    def run_steps(first, n, stats=None):
+        pending, keys = None, None
         for i in range(first, first + n):
-            keys = index.search_packed(chunks[i], K, stats=stats, gather=False)
-        return keys
+            h = index.search_packed(chunks[i], K, stats=stats, gather=False, defer=True)
+            if pending is not None:
+                keys = pending()
+            pending = h
+        return pending() if pending is not None else keys
 
-    run_steps(0, args.warmup, {"time_collect": True, "time_phases": True})
+    run_steps(0, args.warmup)
     barrier()
     t_region0 = time.perf_counter()
     launches0 = lib.cmh_launch_count()
-    stats = {"time_collect": True, "time_phases": True}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    keys = run_steps(args.warmup, args.steps, stats)
+    keys = run_steps(args.warmup, args.steps)
     e1.record()
     barrier()
     launches = lib.cmh_launch_count() - launches0
@@ -542,7 +546,13 @@ def main_native(args):
     clocks = sampler.stop() if rank == 0 else None
     step_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     value = Q * D / (step_ms * 1e-3)
-    n_fail_total = stats.get("n_fail", 0)
+    # per-phase device times (the library's own CUDA events, cmh_tc_timing) in a separate pass over the timed chunks, each
+    # search resolved before the next: reading the events is a host sync that the timed region above does without
+    stats = {"time_collect": True, "time_phases": True}
+    n_fail_total = 0
+    for i in range(args.warmup, args.warmup + min(args.steps, 5)):
+        index.search_packed(chunks[i], K, stats=stats, gather=False)
+        n_fail_total += stats.get("n_fail", 0)
 
     # ---- parity of what was just timed: a subsample of the LAST timed chunk re-ranked by the exact (popc, two-pass)
     # sharded path - every rank's slice contributes queries - must give the same keys bit for bit ------------------

@@ -13,6 +13,7 @@
 // Exactness never depends on a threshold: a too-low one shows up as a short candidate list or as a K-th key from an
 // incomplete bucket and the query is flagged for the exact path.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <set>
 #include <vector>
@@ -185,7 +186,11 @@ extern "C" int cmh_tc_search_plan(const cmh_comm* comm, int64_t nq, int64_t nd, 
     p->thr_final_slot = p->n_thr - 1;
     // ---- the exchange: rank r merges query slice r; a shard sends the `exch_width` smallest keys it holds per query ---
     p->per_rank = (nq + world - 1) / world;
-    p->exch_width = world == 1 ? K : (int)std::min<int64_t>(K, ((int64_t)2 * K / world + 128 + 63) / 64 * 64);
+    // Lockstep stripes spread every stretch of the index order over all shards, so a shard's share of the K results stays
+    // near K / world even when a whole tie bucket is decided by the row index: twice the mean + 64, in 64s.  Contiguous
+    // shards send full lists (the lowest-index shard may own every winner of a tie bucket).  Any width is exact - a list
+    // that arrives full and ends below the merged K-th key flags the query (cmh_topk_merge_verify).
+    p->exch_width = (world > 1 && p->lockstep) ? (int)std::min<int64_t>(K, ((int64_t)2 * K / world + 64 + 63) / 64 * 64) : K;
     o.gather = o.gather ? 1 : 0;
     p->opts = o;
     // ---- global counts behind the statistics (sample rows, rows per stage over all shards) --------------------------
@@ -220,7 +225,9 @@ extern "C" int cmh_tc_search_plan(const cmh_comm* comm, int64_t nq, int64_t nd, 
         for (int i = 0; i < p->n_stages; ++i) p->stage_rows_all[i] = (int64_t)host[2 + 2 * i] + ((int64_t)host[3 + 2 * i] << 32);
     }
     // ---- workspace ---------------------------------------------------------------------------------------------------
-    const int nb = bits + 1;
+    // candidate histograms are exchanged up to the highest bucket a threshold can name: the kernel clamps thresholds to
+    // (bits - 1) / 2 (a query beyond that takes the exact path), so nothing above it is ever consulted
+    const int nb = std::min(bits + 1, (bits - 1) / 2 + 2);
     const int64_t nq_all = p->per_rank * world;
     uint64_t off = 0;
     auto take = [&](uint64_t bytes) { const uint64_t r = off; off += align256(bytes); return r; };
@@ -231,7 +238,7 @@ extern "C" int cmh_tc_search_plan(const cmh_comm* comm, int64_t nq, int64_t nd, 
     // candidate histogram [nq][nb] followed by the overflow flags [nq] (one all-reduce), twice (lower / seen) + gathered
     p->off_hist = take((uint64_t)nq * (nb + 1) * 4 * 2);
     p->off_gather = (world > 1 && !p->lockstep && p->n_prefix_cuts) ? take((uint64_t)world * nq * (nb + 1) * 4) : off;
-    p->off_sample_hist = take((uint64_t)nq * nb * 4);
+    p->off_sample_hist = take((uint64_t)nq * (bits + 1) * 4);
     p->off_part = world > 1 ? take((uint64_t)nq_all * p->exch_width * 8) : off;
     p->off_recv = world > 1 ? take((uint64_t)nq_all * p->exch_width * 8) : off;
     p->off_flags = take((uint64_t)nq_all * 4 * 2);
@@ -440,8 +447,8 @@ extern "C" int cmh_topk_tc(const cmh_tc_search* plan, const cmh_comm* comm, cons
     CMH_REQUIRE(p.opts.n_ready == 0 || ready_events, CMH_ERR_ARG, "cmh_topk_tc: the plan expects %d ready events", p.opts.n_ready);
     CMH_REQUIRE(p.opts.exact_thresholds || p.n_sample == 0 || sample_sign, CMH_ERR_ARG, "cmh_topk_tc: NULL sample");
     cudaStream_t st = (cudaStream_t)stream;
-    Search s{p, comm, reinterpret_cast<unsigned char*>(workspace), st, timing, p.bits + 1};
-    const int nb = s.nb, K = p.K, words = p.bits / 64;
+    Search s{p, comm, reinterpret_cast<unsigned char*>(workspace), st, timing, std::min(p.bits + 1, (p.bits - 1) / 2 + 2)};
+    const int nb = p.bits + 1, K = p.K, words = p.bits / 64;      // (s.nb: buckets of the exchanged candidate histograms)
     const int64_t nq = p.nq, nq_all = p.per_rank * world;
     int rc;
     if (timing) { timing->n_phase = 0; timing->n_collect = 0; }

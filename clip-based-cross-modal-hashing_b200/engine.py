@@ -493,6 +493,15 @@ class TcSearchPlan:
         self.device = device
         self.workspace = torch.empty(max(1, int(plan.workspace_bytes)), dtype=torch.uint8, device=device)
         self._timing = None
+        # verdicts travel to pinned host memory behind their own search and are waited for by EVENT: a stream-ordered
+        # read (`.item()`) would queue behind whatever was enqueued after the search - e.g. the next query chunk
+        self._slots = [(torch.empty(1, dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+        self._turn = 0
+
+    def verdict_slot(self):
+        slot = self._slots[self._turn % len(self._slots)]
+        self._turn += 1
+        return slot
 
     def timing(self):
         if self._timing is None:
@@ -661,6 +670,9 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     if rc and getattr(keep, "error", None) is not None:
         raise keep.error
     check(rc, "cmh_topk_tc")
+    fail_host, fail_event = sp.verdict_slot()
+    fail_host.copy_(fail_count, non_blocking=True)
+    fail_event.record(torch.cuda.current_stream(dev))
     if stats is not None:
         stats["candidates"] = sp.cnt.sum(0)
         stats["thr"] = sp.thr(p.thr_limit_slot).clone()
@@ -670,7 +682,8 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
         stats["exch_width"] = int(p.exch_width)
 
     def finish() -> torch.Tensor:
-        n_fail = int(fail_count.item())              # the one host sync of a search
+        fail_event.synchronize()                     # the one host sync of a search: this search's verdict, nothing later
+        n_fail = int(fail_host[0])
         if stats is not None:
             stats["n_fail"] = n_fail
             if timed:

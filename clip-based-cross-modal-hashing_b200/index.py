@@ -176,15 +176,19 @@ class HammingIndex:
         lo = min(int(nq), rank * per_rank)
         return lo, max(0, min(per_rank, int(nq) - lo))
 
-    def search_packed(self, q: PackedSet, K: int, stats: Optional[dict] = None, gather: bool = True) -> torch.Tensor:
+    def search_packed(self, q: PackedSet, K: int, stats: Optional[dict] = None, gather: bool = True, defer: bool = False):
         """int64 [Q, K] ascending keys ``(2*dist << 32) | global_row`` (-1 pads rows beyond the database).
         Sharded database, ``gather=False``: the result stays sharded by query slice - rank r returns
-        int64 [ceil(Q / world), K], the keys of the queries `query_slice` names (no all-gather of the merged keys)."""
+        int64 [ceil(Q / world), K], the keys of the queries `query_slice` names (no all-gather of the merged keys).
+        ``defer=True``: everything is enqueued on the current stream and a callable comes back; calling it reads the
+        verdict (the one host sync of a search), redoes failed queries and returns the keys.  Enqueuing the next chunk
+        before resolving the previous one keeps the GPU busy while the host prepares the next call (same stream, same
+        scratch: the searches still run one after the other)."""
         if self.sample is not None and q.valid is None and q.bits == self.db.bits and 1 <= int(K) <= _e.TC_MAX_K:
             ready, self._ready = self._ready, None       # only the first search can overlap the upload
             return _sh.topk_tc_sharded(q, self.db, int(K), self.index_base, self.nd_total, sample=self.sample,
                                        group=self.group, stats=stats, buffers=self._tc_buffers, ready=ready,
-                                       stripes=self.stripes, gather=gather)
+                                       stripes=self.stripes, gather=gather, defer=defer)
         self._upload_done()
         keys = _sh.topk_sharded(q, self.db, int(K), self.index_base, self.group, ternary=None, stripes=self.stripes)
         if not gather:
@@ -194,8 +198,8 @@ class HammingIndex:
                 out = torch.full((per_rank, int(K)), -1, dtype=torch.int64, device=keys.device)
                 lo, n = self.query_slice(q.n)
                 out[:n] = keys[lo:lo + n]
-                return out
-        return keys
+                keys = out
+        return (lambda: keys) if defer else keys
 
     def search_packed_async(self, q: PackedSet, K: int, stats: Optional[dict] = None) -> "PendingSearch":
         """`search_packed` without waiting: the search is enqueued on one of two alternating side streams (each with

@@ -185,41 +185,91 @@ class DchmtModel(nn.Module):
         self.text_hash = DchmtHead(cfg.embed_dim, bits)
 
 
+def _encode_batch(model: "DchmtModel", img, txt, image, text, index, w_img, b_img, w_txt, b_txt) -> None:
+    """One batch of `get_code_DCHMT` (`train/base.py:165-177`): both towers, both heads, codes stored by dataset index."""
+    img.put_head(index, model.image_hash.hidden(model.clip.encode_image(image)), w_img, b_img, relu=True)
+    txt.put_head(index, model.text_hash.hidden(model.clip.encode_text(text)), w_txt, b_txt, relu=True)
+
+
 def get_code_dchmt(model: DchmtModel, batches: Iterable[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]], length: int,
-                   device: torch.device):
+                   device: torch.device, graphs: bool = True):
     """`get_code_DCHMT` (`train/base.py:160-178`): ``batches`` yields (image [n, 3, R, R], text int64 [n, ctx], index int64
     [n]) on the HOST (pinned memory makes the copies asynchronous); returns the image and text `CodeBuffer`s, rows placed by
-    dataset index.  The copy of batch i+1 overlaps the encoder of batch i (copy stream + one event per batch)."""
+    dataset index.
+
+    Batches are double-buffered - the host -> device copy of batch i+1 runs on a copy stream under the encoder of batch i -
+    and, with ``graphs``, every full-size batch replays ONE captured CUDA graph per buffer set (encoder of both towers +
+    the two head kernels: ~800 launches per batch otherwise, which is what bounds a batch of a few hundred items)."""
     from .codes import CodeBuffer
     img, txt = CodeBuffer(length, model.bits, device), CodeBuffer(length, model.bits, device)
     copy_stream = torch.cuda.Stream(device)
     compute = torch.cuda.current_stream(device)
     dtype = model.clip.visual.conv1.weight.dtype
+    w_img, b_img = model.image_hash.weight.detach().float().contiguous(), model.image_hash.bias.detach().float().contiguous()
+    w_txt, b_txt = model.text_hash.weight.detach().float().contiguous(), model.text_hash.bias.detach().float().contiguous()
+    sets = []          # per buffer set: static inputs, the graph over them, the event of its last replay
 
-    def stage(batch):
-        image, text, index = batch
+    def new_set(image, text, index):
+        st = {"image": torch.empty(image.shape, dtype=dtype, device=device),
+              "text": torch.empty(text.shape, dtype=torch.int64, device=device),
+              "index": torch.empty(index.shape, dtype=torch.int64, device=device), "graph": None, "done": None}
+        return st
+
+    def upload(st, image, text, index):
         with torch.cuda.stream(copy_stream):
-            d = (image.to(device, non_blocking=True).to(dtype), text.to(device, non_blocking=True),
-                 index.to(device, non_blocking=True))
+            if st["done"] is not None:
+                copy_stream.wait_event(st["done"])            # the set's previous batch has been encoded
+            st["image"].copy_(image, non_blocking=True)       # (bf16 host batches copy as they are; others convert on the way)
+            st["text"].copy_(text, non_blocking=True)
+            st["index"].copy_(index, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return d, ev
+        return ev
 
-    it = iter(batches)
-    nxt = next(it, None)
-    staged = stage(nxt) if nxt is not None else None
+    def run(st):
+        st["uses"] = st.get("uses", 0) + 1
+        eager = lambda: _encode_batch(model, img, txt, st["image"], st["text"], st["index"], w_img, b_img, w_txt, b_txt)
+        if not graphs or st["graph"] is False or st["uses"] == 1:
+            eager()                                           # the first batch of a set also warms up the library plans
+            return
+        if st["graph"] is None:                               # second use of the set: capture over its static buffers
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    eager()
+                st["graph"] = g
+            except Exception:  # noqa: BLE001 - capture unsupported for some op: stay eager
+                st["graph"] = False
+                eager()
+                return
+        st["graph"].replay()
+
     with torch.no_grad():
-        while staged is not None:
-            (image, text, index), ev = staged
-            nxt = next(it, None)
-            staged = stage(nxt) if nxt is not None else None       # the next batch travels while this one is encoded
-            compute.wait_event(ev)
-            for t in (image, text, index):
-                t.record_stream(compute)
-            img.put_head(index, model.image_hash.hidden(model.clip.encode_image(image)), model.image_hash.weight,
-                         model.image_hash.bias, relu=True)
-            txt.put_head(index, model.text_hash.hidden(model.clip.encode_text(text)), model.text_hash.weight,
-                         model.text_hash.bias, relu=True)
+        turn, pending = 0, None
+        for batch in batches:
+            image, text, index = batch
+            st = None
+            for cand in sets:
+                if cand["image"].shape == image.shape and cand is not (pending[0] if pending else None):
+                    st = cand
+                    break
+            if st is None:
+                st = new_set(image, text, index)
+                if len([c for c in sets if c["image"].shape == image.shape]) < 2:
+                    sets.append(st)
+            ev = upload(st, image, text, index)               # travels while the previous batch is encoded
+            if pending is not None:
+                pst, pev = pending
+                compute.wait_event(pev)
+                run(pst)
+                pst["done"] = torch.cuda.Event()
+                pst["done"].record(compute)
+            pending = (st, ev)
+            turn += 1
+        if pending is not None:
+            pst, pev = pending
+            compute.wait_event(pev)
+            run(pst)
     return img, txt
 
 

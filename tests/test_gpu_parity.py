@@ -1056,6 +1056,8 @@ def test_valid_loop_codes_match_reference_sequence(dev):
     from cmh_b200 import _cabi, engine, calc_utils as cu
     from cmh_b200.codes import CodeBuffer
     from cmh_b200.valid_loop import Clip, ClipConfig, DchmtModel, valid
+    torch.backends.cudnn.allow_tf32 = False                      # float32 means float32 here (the patch convolution)
+    torch.backends.cuda.matmul.allow_tf32 = False
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "clip_tiny.npz"))
     cfg = ClipConfig(*[int(v) for v in z["cfg"]])
     clip = Clip(cfg).float().eval()
