@@ -23,7 +23,8 @@
 
 namespace cmh {
 
-constexpr int LANE_WARPS = 8;     // queries per CTA
+constexpr int LANE_WARPS = 8;     // queries (consumer warps) per CTA; one more warp feeds the stages
+constexpr int LANE_THREADS = (LANE_WARPS + 1) * 32;
 constexpr int LANE_ROWS = 512;    // database rows per stage
 
 __host__ __device__ inline size_t lane_stage_bytes(int cws, int lws) { return (size_t)LANE_ROWS * (cws + lws) * 4; }
@@ -47,7 +48,8 @@ bool lane_supported(const EvalArgs& a, bool tern) {
 struct LaneSmem {
     unsigned char* raw;
     uint32_t code_b, stage_b;
-    __device__ __forceinline__ uint64_t* bar(int st) const { return reinterpret_cast<uint64_t*>(raw) + st; }
+    __device__ __forceinline__ uint64_t* bar(int st) const { return reinterpret_cast<uint64_t*>(raw) + st; }         // stage full
+    __device__ __forceinline__ uint64_t* empty(int st) const { return reinterpret_cast<uint64_t*>(raw) + 2 + st; }  // stage consumed
     __device__ __forceinline__ uint32_t* codes(int st) const { return reinterpret_cast<uint32_t*>(raw + 128 + (size_t)st * stage_b); }
     __device__ __forceinline__ uint32_t* labels(int st) const {
         return reinterpret_cast<uint32_t*>(raw + 128 + (size_t)st * stage_b + code_b);
@@ -63,23 +65,35 @@ __device__ __forceinline__ LaneSmem carve_lane_smem(unsigned char* raw, int cws,
     return s;
 }
 
-// Fill one stage with database rows [row0, row0 + rows): whole stages through the bulk-copy engine, the ragged last
-// stage of a chunk (and every stage of a shard view that is not 16-byte aligned) by the CTA.  Called by all threads.
+// The producer warp: fills stage t % 2 with the rows of tile t as soon as the eight consumer warps have released it -
+// whole stages through the bulk-copy engine (one lane), the ragged last stage of a chunk (and every stage of a shard
+// view that is not 16-byte aligned) with the warp's own loads.  No CTA-wide barrier in the loop: a consumer warp moves
+// on to the next stage as soon as that stage is full, whatever the other queries are doing (the r02p captures had 2-3
+// of ~20 stall cycles per issue on __syncthreads).
 template <int CWS, int LWS>
-__device__ __forceinline__ void lane_load_stage(const EvalArgs& a, const LaneSmem& s, int st, int64_t row0, int rows) {
-    const uint32_t code_b = (uint32_t)rows * CWS * 4, lab_b = (uint32_t)rows * LWS * 4;
-    if (rows == LANE_ROWS && a.bulk_ok) {
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(s.bar(st), code_b + lab_b);
-            bulk_g2s(s.codes(st), a.ds + row0 * CWS, code_b, s.bar(st));
-            if (LWS) bulk_g2s(s.labels(st), a.dl + row0 * LWS, lab_b, s.bar(st));
+__device__ __forceinline__ void lane_producer(const EvalArgs& a, const LaneSmem& s, int64_t c_begin, int c_rows, int n_tiles) {
+    const int lane = threadIdx.x & 31;
+    for (int t = 0; t < n_tiles; ++t) {
+        const int st = t & 1;
+        if (t >= 2) mbar_wait(s.empty(st), ((t >> 1) - 1) & 1);          // the consumers are done with tile t - 2
+        const int64_t row0 = c_begin + (int64_t)t * LANE_ROWS;
+        const int rows = min(LANE_ROWS, c_rows - t * LANE_ROWS);
+        const uint32_t code_b = (uint32_t)rows * CWS * 4, lab_b = (uint32_t)rows * LWS * 4;
+        if (rows == LANE_ROWS && a.bulk_ok) {
+            if (lane == 0) {
+                mbar_expect_tx(s.bar(st), code_b + lab_b);
+                bulk_g2s(s.codes(st), a.ds + row0 * CWS, code_b, s.bar(st));
+                if (LWS) bulk_g2s(s.labels(st), a.dl + row0 * LWS, lab_b, s.bar(st));
+            }
+        } else {
+            for (int i = lane; i < rows * CWS; i += 32) s.codes(st)[i] = a.ds[row0 * CWS + i];
+            if (LWS)
+                for (int i = lane; i < rows * LWS; i += 32) s.labels(st)[i] = a.dl[row0 * LWS + i];
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s.bar(st));                       // release: the stores above are visible to the waiters
         }
-    } else {
-        for (int i = threadIdx.x; i < rows * CWS; i += blockDim.x) s.codes(st)[i] = a.ds[row0 * CWS + i];
-        if (LWS)
-            for (int i = threadIdx.x; i < rows * LWS; i += blockDim.x) s.labels(st)[i] = a.dl[row0 * LWS + i];
-        __syncthreads();
-        if (threadIdx.x == 0) mbar_arrive(s.bar(st));
+        __syncwarp();
     }
 }
 
@@ -150,7 +164,7 @@ struct LaneQuery {
 // COPIES sub-histograms per warp (lane % COPIES picks one): the lanes of a step collide on the few buckets around the
 // mean distance, and a collision costs a shared-memory wavefront each (r02d: 4.6 extra wavefronts per step with one copy)
 template <int CWS, int LWS, int COPIES>
-__global__ void __launch_bounds__(LANE_WARPS * 32) hist_lane_kernel(const EvalArgs a, uint32_t* __restrict__ chunk_hist) {
+__global__ void __launch_bounds__(LANE_THREADS) hist_lane_kernel(const EvalArgs a, uint32_t* __restrict__ chunk_hist) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const LaneSmem s = carve_lane_smem(smem_raw, CWS, LWS);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -166,14 +180,19 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) hist_lane_kernel(const EvalAr
     if (threadIdx.x == 0) {
         mbar_init(s.bar(0), 1);
         mbar_init(s.bar(1), 1);
+        mbar_init(s.empty(0), LANE_WARPS);
+        mbar_init(s.empty(1), LANE_WARPS);
         mbar_fence_init();
+    }
+    if (warp == LANE_WARPS) {                         // (uniform per warp)
+        __syncthreads();
+        lane_producer<CWS, LWS>(a, s, c_begin, c_rows, n_tiles);
+        return;
     }
     LaneQuery<CWS, LWS> qu;
     qu.load(a, q);
     for (int b = lane; b < COPIES * nbp; b += 32) cnt[b] = 0u;
     __syncthreads();
-    lane_load_stage<CWS, LWS>(a, s, 0, c_begin, min(LANE_ROWS, c_rows));
-    if (n_tiles > 1) lane_load_stage<CWS, LWS>(a, s, 1, c_begin + LANE_ROWS, min(LANE_ROWS, c_rows - LANE_ROWS));
 
     for (int t = 0; t < n_tiles; ++t) {
         const int st = t & 1;
@@ -191,9 +210,8 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) hist_lane_kernel(const EvalAr
             const int d = qu.bucket(tc + (uint32_t)full * (CWS * 4u));
             red_add_shared(cnt_u + 4u * (uint32_t)d, qu.relevant(tl + (uint32_t)full * (LWS * 4u)) ? 0x10001u : 1u);
         }
-        __syncthreads();  // everyone is done with stage st
-        if (t + 2 < n_tiles)
-            lane_load_stage<CWS, LWS>(a, s, st, c_begin + (int64_t)(t + 2) * LANE_ROWS, min(LANE_ROWS, c_rows - (t + 2) * LANE_ROWS));
+        __syncwarp();                                 // every lane has read its rows
+        if (lane == 0) mbar_arrive(s.empty(st));      // this warp is done with stage st
     }
     __syncwarp();
     if (q < a.nq_pad)
@@ -227,7 +245,7 @@ __device__ __forceinline__ float lane_rcp(float y) {
 // different words, i.e. different banks) and reads the mask back with the counters - MATCH.ANY carries ~half of the stall
 // samples of the r02d capture.  Either way the last lane of a group writes the group's final ranks and clears the masks.
 template <int CWS, int LWS, bool BIG, int PEERS>
-__global__ void __launch_bounds__(LANE_WARPS * 32) rank_lane_kernel(const EvalArgs a, const uint2* __restrict__ base,
+__global__ void __launch_bounds__(LANE_THREADS) rank_lane_kernel(const EvalArgs a, const uint2* __restrict__ base,
                                                                     const uint32_t* __restrict__ total_arr, const TopnList topn,
                                                                     double* __restrict__ ap_part,
                                                                     uint32_t* __restrict__ hits_part) {
@@ -250,7 +268,14 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) rank_lane_kernel(const EvalAr
     if (threadIdx.x == 0) {
         mbar_init(s.bar(0), 1);
         mbar_init(s.bar(1), 1);
+        mbar_init(s.empty(0), LANE_WARPS);
+        mbar_init(s.empty(1), LANE_WARPS);
         mbar_fence_init();
+    }
+    if (warp == LANE_WARPS) {                         // (uniform per warp)
+        __syncthreads();
+        lane_producer<CWS, LWS>(a, s, c_begin, c_rows, n_tiles);
+        return;
     }
     LaneQuery<CWS, LWS> qu;
     qu.load(a, q);
@@ -261,8 +286,6 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) rank_lane_kernel(const EvalAr
     }
     for (int i = lane; i < a.ntopn; i += 32) hits[i] = 0u;
     __syncthreads();
-    lane_load_stage<CWS, LWS>(a, s, 0, c_begin, min(LANE_ROWS, c_rows));
-    if (n_tiles > 1) lane_load_stage<CWS, LWS>(a, s, 1, c_begin + LANE_ROWS, min(LANE_ROWS, c_rows - LANE_ROWS));
 
     const uint32_t nmax = a.nmax;
     double acc = 0.0;
@@ -310,9 +333,8 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) rank_lane_kernel(const EvalAr
         for (int g = 0; g < full; g += 32) step(g, true);
         if (full < rows) step(full, full + lane < rows);
         acc += (double)acc_t;
-        __syncthreads();
-        if (t + 2 < n_tiles)
-            lane_load_stage<CWS, LWS>(a, s, st, c_begin + (int64_t)(t + 2) * LANE_ROWS, min(LANE_ROWS, c_rows - (t + 2) * LANE_ROWS));
+        __syncwarp();                                 // every lane has read its rows
+        if (lane == 0) mbar_arrive(s.empty(st));      // this warp is done with stage st
     }
     // fixed-order reduction over the lanes: deterministic
 #pragma unroll
@@ -350,12 +372,12 @@ int launch_hist_lane(const EvalArgs& a, uint32_t* chunk_hist, cudaStream_t st) {
             auto k = hist_lane_kernel<CWS_, LWS_, 4>;                            \
             int rc = prep_lane(k, smem);                                         \
             if (rc) return rc;                                                   \
-            k<<<grid, LANE_WARPS * 32, smem, st>>>(a, chunk_hist);               \
+            k<<<grid, LANE_THREADS, smem, st>>>(a, chunk_hist);               \
         } else {                                                                 \
             auto k = hist_lane_kernel<CWS_, LWS_, 1>;                            \
             int rc = prep_lane(k, smem);                                         \
             if (rc) return rc;                                                   \
-            k<<<grid, LANE_WARPS * 32, smem, st>>>(a, chunk_hist);               \
+            k<<<grid, LANE_THREADS, smem, st>>>(a, chunk_hist);               \
         }                                                                        \
     } while (0)
     if (a.cw_stride == 2) {
@@ -379,7 +401,7 @@ int launch_rank_lane(const EvalArgs& a, const uint2* base, const uint32_t* total
         auto k = rank_lane_kernel<CWS_, LWS_, BIG_, P_>;                                \
         int rc = prep_lane(k, smem);                                                    \
         if (rc) return rc;                                                              \
-        k<<<grid, LANE_WARPS * 32, smem, st>>>(a, base, total, tl, ap_part, hits_part); \
+        k<<<grid, LANE_THREADS, smem, st>>>(a, base, total, tl, ap_part, hits_part); \
     } while (0)
 #define CMH_PICK(CWS_, LWS_)                                                            \
     do {                                                                                \

@@ -1113,3 +1113,88 @@ def test_valid_loop_codes_match_reference_sequence(dev):
     for m, w in zip(maps, want):
         assert abs(float(m) - float(w)) < 0.05        # borderline logits may flip single bits of a random-init head
     assert all(0.0 <= float(m) <= 1.0 for m in maps)
+
+
+@pytest.mark.parametrize("world,K,ternary", [(2, 50, False), (3, 200, True), (4, 1000, False)])
+def test_topk_sharded_c_entry(dev, world, K, ternary):
+    """`cmh_topk_sharded` (exact popc path: local `cmh_topk`, all-gather, K-way merge in one C call per shard) over a
+    callback transport, shards of one GPU driven by threads: every rank returns the single-database stable ranking."""
+    import ctypes
+    import threading
+    from cmh_b200 import _cabi, engine, sharded
+    L = _cabi.lib()
+    case = BY_NAME["small_b64_ternary" if ternary else "small_b64_l24"]
+    T = _T(case)
+    cu = _cu()
+    q, d = cu._prepare(T["qB"].to(dev), T["rB"].to(dev), None, None, 0)
+    tern = q.valid is not None or d.valid is not None
+    assert tern == ternary
+    want = engine.RankPass(q, d, need_labels=False).topk(K, 5)
+    if tern:
+        q = engine.PackedSet(q.sign, q.valid if q.valid is not None else engine._full_valid(q), None, q.n, q.bits)
+        d = engine.PackedSet(d.sign, d.valid if d.valid is not None else engine._full_valid(d), None, d.n, d.bits)
+    comm = _ThreadComm(world)
+    out, errs = [None] * world, []
+
+    def run(rank):
+        try:
+            comm.bind(rank)
+            torch.cuda.set_device(dev)
+            lo, hi = sharded.shard_bounds(d.n, world, rank)
+            shard = d.rows(lo, hi)
+            cb = engine.CallbackComm(comm, dev)
+            plan = _cabi.Plan()
+            engine.check(L.cmh_eval_plan(q.n, shard.n, q.bits, 0, 1 if tern else 0, 0, ctypes.byref(plan)), "cmh_eval_plan")
+            ws = torch.empty(max(1, plan.workspace_bytes), dtype=torch.uint8, device=dev)
+            gathered = torch.empty((world, q.n, K), dtype=torch.int64, device=dev)
+            keys = torch.empty((q.n, K), dtype=torch.int64, device=dev)
+            qs, ds = q.struct(use_labels=False), shard.struct(use_labels=False)
+            rc = L.cmh_topk_sharded(cb.handle(), ctypes.byref(plan), ctypes.byref(qs), ctypes.byref(ds), K, 5 + lo,
+                                    engine._ptr(gathered), engine._ptr(keys), engine._ptr(ws), engine._stream(dev))
+            if rc and cb.error is not None:
+                raise cb.error
+            engine.check(rc, "cmh_topk_sharded")
+            torch.cuda.synchronize()
+            out[rank] = keys
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+            comm.barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errs, errs
+    for keys in out:
+        assert torch.equal(keys, want)
+
+
+def test_code_buffer_reset_and_cache_switch(dev):
+    """a CodeBuffer that once stored exact zeros can return to the +-1 fast path (`recount` after the rows
+    were overwritten, `reset` between epochs), tensors of ANOTHER device are moved instead of read through a raw
+    pointer, and the pack cache can be switched off for buffers written behind torch's version counter."""
+    from cmh_b200.codes import CodeBuffer
+    cu = _cu()
+    buf = CodeBuffer(10, 64, dev)
+    x = torch.ones(4, 64); x[1, 7] = 0.0
+    buf.put(torch.tensor([0, 1, 2, 3]), x)
+    assert buf.packed().valid is not None and buf.packed().n_zero == 1
+    buf.put(torch.tensor([1]), -torch.ones(1, 64))              # the row with the zero is overwritten
+    assert buf.packed().valid is not None                       # the counter is cumulative ...
+    assert buf.recount() == 0 and buf.packed().valid is None    # ... until it is recounted
+    buf.put(torch.tensor([5]), torch.zeros(1, 64))
+    assert buf.packed().n_zero == 64
+    buf.reset()
+    assert buf.packed().valid is None and bool((buf.sign == 0).all())
+    # cache switch: a write through .data is invisible to the version counter
+    a = torch.ones(3, 16, device=dev); b = -torch.ones(5, 16, device=dev)
+    qL = torch.ones(3, 2); rL = torch.ones(5, 2)
+    cu.clear_cache()
+    d0 = cu.calc_hammingDist(a, b)
+    a.data[0, :] = -1.0
+    assert torch.equal(cu.calc_hammingDist(a, b), d0)           # stale: same object, same version
+    cu.set_cache(False)
+    try:
+        d1 = cu.calc_hammingDist(a, b)
+        assert float(d1[0, 0]) == 0.0 and float(d1[1, 0]) == 16.0
+    finally:
+        cu.set_cache(True)
