@@ -616,7 +616,7 @@ def main_native(args):
     def e2e_step(i):
         # the queries go first (H2D copies share one engine: behind the shard they would wait for all of it)
         qp = cu.pack_codes(q_hosts[i].to(dev, non_blocking=True), dev)
-        idx = HammingIndex.from_packed_host(db_host, BITS, lo, nd_total=D, out=db_dev, pieces=3, stripes=stripes)
+        idx = HammingIndex.from_packed_host(db_host, BITS, lo, nd_total=D, out=db_dev, stripes=stripes)
         k = idx.search_packed(qp, K, gather=False)
         keys_host.copy_(k, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()

@@ -485,6 +485,23 @@ def _comm_handle(comm, device):
     return cb.handle(), cb
 
 
+# Verdicts travel to pinned host memory behind their own search and are waited for by EVENT: a stream-ordered read
+# (`.item()`) would queue behind whatever was enqueued after the search - e.g. the next query chunk.  One process-wide
+# ring (pinning memory costs a driver call; an index rebuilt every step must not pay it again).
+_VERDICTS: list = []
+_verdict_turn = 0
+
+
+def _verdict_slot():
+    global _verdict_turn
+    if not _VERDICTS:
+        host = torch.empty(16, dtype=torch.int32).pin_memory()
+        _VERDICTS.extend((host[i:i + 1], torch.cuda.Event()) for i in range(16))
+    slot = _VERDICTS[_verdict_turn % len(_VERDICTS)]
+    _verdict_turn += 1
+    return slot
+
+
 class TcSearchPlan:
     """`cmh_tc_search` + its device scratch (+ optional timing handle) for one (queries per call, shard) geometry."""
 
@@ -493,15 +510,9 @@ class TcSearchPlan:
         self.device = device
         self.workspace = torch.empty(max(1, int(plan.workspace_bytes)), dtype=torch.uint8, device=device)
         self._timing = None
-        # verdicts travel to pinned host memory behind their own search and are waited for by EVENT: a stream-ordered
-        # read (`.item()`) would queue behind whatever was enqueued after the search - e.g. the next query chunk
-        self._slots = [(torch.empty(1, dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(4)]
-        self._turn = 0
 
     def verdict_slot(self):
-        slot = self._slots[self._turn % len(self._slots)]
-        self._turn += 1
-        return slot
+        return _verdict_slot()
 
     def timing(self):
         if self._timing is None:
@@ -642,7 +653,8 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     key = (nq, d.n, nd_total, q.bits, K, tuple(stripes), n_sample, exact_thr,
            None if pilot is None else tuple(pilot) if isinstance(pilot, (list, tuple)) else int(pilot), bool(prefix),
            None if prefix_fractions is None else tuple(prefix_fractions), prefix_min_rows, bool(tighten), int(cap), seg_cap,
-           bool(gather), tuple(int(e) for e, _ in ready), world, rank, str(dev))
+           bool(gather), tuple(int(e) for e, _ in ready), world, rank, str(dev),
+           torch.cuda.current_stream(dev).cuda_stream)       # (scratch is only ever shared by searches of ONE stream)
     sp = buffers.get(key) if buffers is not None else None
     if sp is None:
         plan = tc_search_plan(handle, nq, d.n, nd_total, q.bits, K, stripes, n_sample, pilot=pilot, prefix=prefix,
@@ -650,7 +662,8 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
                               seg_cap=seg_cap, exact_thresholds=exact_thr, gather=gather,
                               ready_rows=[e for e, _ in ready], device=dev)
         if buffers is not None:
-            buffers.clear()                          # one geometry at a time: the scratch is large
+            while len(buffers) >= 2:                 # at most two geometries at a time: the scratch is large
+                buffers.pop(next(iter(buffers)))
         sp = TcSearchPlan(plan, dev)
         if buffers is not None:
             buffers[key] = sp

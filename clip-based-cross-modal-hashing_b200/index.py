@@ -51,6 +51,7 @@ class HammingIndex:
     # counting passes, whose fixed costs are lower
     TC_MIN_ROWS = 1_000_000
     SAMPLE_ROWS = 65_536
+    _shared_buffers: dict = {}
 
     def __init__(self, db: PackedSet, index_base: int = 0, group=None, nd_total: Optional[int] = None,
                  sample: Optional[PackedSet] = None, ready=None, stripes=None, assume_binary: bool = False):
@@ -84,7 +85,9 @@ class HammingIndex:
             t = torch.tensor([1 if tc_ok else 0], dtype=torch.int64, device=db.device)
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=group)
             tc_ok = bool(int(t.item()))
-        self._tc_buffers: dict = {}
+        # plans + candidate scratch are shared by the indices of a device (keyed by geometry, two at most): an index that
+        # is rebuilt for every upload of the same shard plans once and reuses the scratch
+        self._tc_buffers: dict = HammingIndex._shared_buffers.setdefault(str(db.device), {})
         # a strided sample of the shard: first guess of the per-query thresholds of the tensor-core search
         self.sample = None
         if sample is not None:
@@ -115,10 +118,11 @@ class HammingIndex:
 
     @classmethod
     def from_packed_host(cls, words: torch.Tensor, bits: int, index_base: int = 0, group=None,
-                         nd_total: Optional[int] = None, pieces: int = 4, out: Optional[torch.Tensor] = None,
+                         nd_total: Optional[int] = None, pieces: Optional[int] = None, out: Optional[torch.Tensor] = None,
                          device=None, stripes=None) -> "HammingIndex":
         """Upload packed +-1 codes from (pinned) host memory WITHOUT waiting for the copy: the rows travel in
-        ``pieces`` ranges on a copy stream, and the first search scans each range as soon as it has landed (the
+        ranges on a copy stream (``pieces`` equal ranges after the pilot rows; None = ranges that follow the search's own
+        launches), and the first search scans each range as soon as it has landed (the
         pilot rows first), so the upload of a fresh database hides behind the search that needs it.
         ``out``: optional device tensor [D, words] to upload into (reused between calls)."""
         if words.is_cuda:
@@ -139,9 +143,20 @@ class HammingIndex:
         stages = _e.tc_pilot_stages(n, total, world)
         n_pilot = stages[-1] if stages else 0
         first = n_pilot if n_pilot else min(n, max(4096, n // 64) // 256 * 256 or n)
-        ends = sorted({e for e in [first] +
-                       [first + (n - first) * (i + 1) // pieces // 256 * 256 for i in range(pieces - 1)] + [n]
-                       if 0 < e <= n})
+        if pieces is None:
+            # Upload ranges that follow the search's own launches: the pilot rows, one SHORT range (the first main launch
+            # can start ~1 ms into the upload instead of waiting for a third of the database - the link delivers rows
+            # about twice as fast as the scan consumes them, so later ranges are never waited for), then the rows up to
+            # every cut the search makes anyway (stripe boundaries, or the prefix-rule fractions of one GPU)
+            if stripes and len(stripes) > 1:
+                later = [int(lo_) for lo_, _ in stripes[1:]]
+            else:
+                later = [int(n * f) // 256 * 256 for f in (0.3, 0.5, 0.7)]
+            early = first + max(256, int(n * 0.065) // 256 * 256)
+            cand = [first, early] + later + [n]
+        else:
+            cand = [first] + [first + (n - first) * (i + 1) // pieces // 256 * 256 for i in range(pieces - 1)] + [n]
+        ends = sorted({e for e in cand if 0 < e <= n})
         ready, lo = [], 0
         with torch.cuda.stream(copy_stream):
             for hi in ends:
