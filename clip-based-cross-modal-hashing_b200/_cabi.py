@@ -30,7 +30,7 @@ EXPORTS = (
     "cmh_abi_version", "cmh_last_error", "cmh_device_info", "cmh_launch_count", "cmh_measure_popc_peak",
     "cmh_pack_codes", "cmh_pack_scatter", "cmh_hash_head_pack", "cmh_unpack_codes", "cmh_pack_labels", "cmh_synth_codes",
     "cmh_hamming_dense", "cmh_neighbor_dense",
-    "cmh_eval_plan", "cmh_eval_plan_design", "cmh_eval_hist", "cmh_eval_rank",
+    "cmh_eval_plan", "cmh_eval_plan_design", "cmh_eval_plan_sets", "cmh_eval_hist", "cmh_eval_rank", "cmh_finalize_map_hits",
     "cmh_finalize_map", "cmh_finalize_topn", "cmh_finalize_pr_workspace_bytes", "cmh_finalize_pr",
     "cmh_map_k_workspace_bytes", "cmh_map_k",
     "cmh_topk", "cmh_topk_merge",
@@ -57,7 +57,8 @@ class Plan(ctypes.Structure):
                 ("nb", ctypes.c_int32), ("design", ctypes.c_int32), ("q_tile", ctypes.c_int32),
                 ("n_qtiles", ctypes.c_int32), ("chunk_rows", ctypes.c_int32), ("n_chunks", ctypes.c_int32),
                 ("nq", ctypes.c_int64), ("nd", ctypes.c_int64), ("nq_pad", ctypes.c_int64),
-                ("workspace_bytes", ctypes.c_uint64)]
+                ("workspace_bytes", ctypes.c_uint64), ("kq", ctypes.c_int32), ("kd", ctypes.c_int32),
+                ("ap_mode", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 TC_MAX_STRIPES, TC_MAX_STAGES, TC_MAX_CUTS, TC_MAX_SPANS, TC_MAX_READY, TC_PHASES = 8, 4, 8, 32, 16, 8
@@ -177,6 +178,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cmh_neighbor_dense.argtypes = [vp, i64, vp, i64, i32, vp, i64, vp]
     L.cmh_eval_plan.argtypes = [i64, i64, i32, i32, i32, i32, ppl]
     L.cmh_eval_plan_design.argtypes = [i64, i64, i32, i32, i32, i32, i32, ppl]
+    L.cmh_eval_plan_sets.argtypes = [i64, i64, i32, i32, i32, i32, i32, ppl]
+    L.cmh_finalize_map_hits.argtypes = [vp, vp, i32, i64, vp, vp, vp]
     L.cmh_eval_hist.argtypes = [ppl, pcs, pcs, vp, vp, vp, vp]
     L.cmh_eval_rank.argtypes = [ppl, pcs, pcs, i64, vp, vp, vp, vp, ctypes.POINTER(i64), i32, vp, vp, vp, vp, vp]
     L.cmh_finalize_map.argtypes = [vp, vp, i64, i64, vp, vp, vp]

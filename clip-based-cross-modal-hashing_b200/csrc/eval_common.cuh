@@ -50,6 +50,9 @@ struct EvalArgs {
     int ntopn, K;
     uint32_t nmax;                  // largest precision@N cutoff (0 = none)
     int big_ranks;                  // ranks may reach 2^23 and beyond (a long shard, or bases from other shards)
+    int kq, kd;                     // set-valued codes: sub-codes per query / database item (1 = plain; warp kernels only)
+    int ap_mode;                    // 1: textbook AP@k - a relevant row counts when its RANK is within kcut
+    uint32_t kcut;
 };
 
 // precision@N cutoffs, passed to kernels by value

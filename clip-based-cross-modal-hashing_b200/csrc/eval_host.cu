@@ -45,6 +45,7 @@ static EvalArgs geometry_args(int bits, int nlab, bool ternary) {
     a.lw = (nlab + 31) / 32;
     a.lw_stride = 2 * ((nlab + 63) / 64);
     a.ntopn = 0;
+    a.kq = a.kd = 1;
     return a;
 }
 
@@ -88,6 +89,7 @@ static int fill_args(const cmh_plan& p, const cmh_codeset* q, const cmh_codeset*
     if (!(q->labels && d->labels)) { a.lw = 0; a.lw_stride = 0; a.ql = a.dl = nullptr; }
     a.nq = p.nq; a.nd = p.nd; a.nq_pad = p.nq_pad;
     a.chunk_rows = p.chunk_rows; a.n_chunks = p.n_chunks;
+    a.kq = p.kq > 0 ? p.kq : 1; a.kd = p.kd > 0 ? p.kd : 1; a.ap_mode = p.ap_mode;
     const uintptr_t align = (uintptr_t)a.ds | (uintptr_t)a.dv | (uintptr_t)a.dl;
     a.bulk_ok = (align & 15) == 0;
     *out = a;
@@ -274,6 +276,22 @@ __global__ void __launch_bounds__(1024) finalize_map_kernel(const double* __rest
     if (threadIdx.x == 0) map[0] = nq > 0 ? (float)(s / (double)nq) : 0.f;
 }
 
+// textbook AP@k (train/DPSIH/_utils.py:22-29): AP = ap_sum / #relevant rows within the first k (0 when there is none)
+__global__ void __launch_bounds__(1024) finalize_map_hits_kernel(const double* __restrict__ ap_sum,
+                                                                 const uint32_t* __restrict__ hits, int ntopn, int64_t nq,
+                                                                 double* __restrict__ ap, float* __restrict__ map) {
+    __shared__ double sh[32];
+    double local = 0.0;
+    for (int64_t q = threadIdx.x; q < nq; q += blockDim.x) {
+        const uint32_t h = hits[q * ntopn];
+        const double v = h > 0 ? ap_sum[q] / (double)h : 0.0;
+        if (ap) ap[q] = v;
+        local += v;
+    }
+    const double s = block_sum_1024(local, sh);
+    if (threadIdx.x == 0) map[0] = nq > 0 ? (float)(s / (double)nq) : 0.f;
+}
+
 __global__ void __launch_bounds__(1024) finalize_topn_kernel(const uint32_t* __restrict__ hits,
                                                              const int64_t* __restrict__ n_rel, int64_t nq, int ntopn,
                                                              const TopnList topn_unsorted, int64_t nd_total,
@@ -396,7 +414,8 @@ static int auto_design(int64_t nq, int64_t nd, int nb, int nlab, bool tile_ok, b
     return tile_ok ? 0 : 1;
 }
 
-static int make_plan(int64_t nq, int64_t nd, int bits, int nlab, int ternary, int max_topn, int design, cmh_plan* plan) {
+static int make_plan(int64_t nq, int64_t nd, int bits, int nlab, int ternary, int max_topn, int design, cmh_plan* plan,
+                     int kq = 1, int kd = 1, int ap_mode = 0) {
     CMH_REQUIRE(plan, CMH_ERR_ARG, "cmh_eval_plan: NULL plan");
     CMH_REQUIRE(nq >= 0 && nd >= 0 && nlab >= 0 && max_topn >= 0 && max_topn <= CMH_MAX_TOPN, CMH_ERR_ARG,
                 "cmh_eval_plan: bad sizes nq=%lld nd=%lld nlab=%d max_topn=%d", (long long)nq, (long long)nd, nlab, max_topn);
@@ -407,8 +426,15 @@ static int make_plan(int64_t nq, int64_t nd, int bits, int nlab, int ternary, in
     plan->bits = bits; plan->words = (bits + 63) / 64; plan->nlab = nlab; plan->lwords = (nlab + 63) / 64;
     plan->ternary = ternary ? 1 : 0; plan->nb = ternary ? 2 * bits + 1 : bits + 1;
     plan->max_topn = max_topn; plan->nq = nq; plan->nd = nd;
+    plan->kq = kq; plan->kd = kd; plan->ap_mode = ap_mode;
     EvalArgs a = geometry_args(bits, nlab, ternary != 0);
     a.ntopn = max_topn;
+    a.kq = kq; a.kd = kd;
+    if (kq > 1 || kd > 1 || ap_mode) {                        // set-valued codes / textbook AP@k: the generic warp kernels
+        CMH_REQUIRE(!ternary, CMH_ERR_UNSUPPORTED, "cmh_eval_plan_sets: binary codes only");
+        CMH_REQUIRE(design < 0 || design == 1, CMH_ERR_UNSUPPORTED, "cmh_eval_plan_sets: the warp design walks set-valued codes");
+        design = 1;
+    }
     const bool tile_ok = a.cw <= MAX_CW && a.lw <= MAX_LW && plan->nb <= TILE_MAX_NB &&
                          tile_smem_bytes(a, ternary != 0, 1) <= MAX_DYN_SMEM;
     const bool lane_ok = lane_supported(a, ternary != 0);
@@ -450,6 +476,11 @@ static int make_plan(int64_t nq, int64_t nd, int bits, int nlab, int ternary, in
 
 extern "C" int cmh_eval_plan(int64_t nq, int64_t nd, int bits, int nlab, int ternary, int max_topn, cmh_plan* plan) {
     return make_plan(nq, nd, bits, nlab, ternary, max_topn, -1, plan);
+}
+extern "C" int cmh_eval_plan_sets(int64_t nq, int64_t nd, int bits, int nlab, int kq, int kd, int ap_mode, cmh_plan* plan) {
+    CMH_REQUIRE(kq >= 1 && kd >= 1 && kq <= 64 && kd <= 64 && (ap_mode == 0 || ap_mode == 1), CMH_ERR_ARG,
+                "cmh_eval_plan_sets: kq=%d kd=%d ap_mode=%d", kq, kd, ap_mode);
+    return make_plan(nq, nd, bits, nlab, 0, 1, -1, plan, kq, kd, ap_mode);
 }
 extern "C" int cmh_eval_plan_design(int64_t nq, int64_t nd, int bits, int nlab, int ternary, int max_topn, int design,
                                     cmh_plan* plan) {
@@ -550,6 +581,11 @@ extern "C" int cmh_eval_rank(const cmh_plan* plan, const cmh_codeset* q, const c
     a.ntopn = ntopn;
     a.nmax = ntopn ? tl.n[ntopn - 1] : 0u;
     a.big_ranks = (global_all != nullptr || plan->nd >= (1ll << 23)) ? 1 : 0;   // ranks may exceed 2^23: no float bit tricks
+    a.ap_mode = plan->ap_mode;
+    a.kcut = (uint32_t)((k < 0 || k > 0xfffffffell) ? 0xfffffffeu : k);
+    CMH_REQUIRE(plan->ap_mode == 0 || plan->design == 1, CMH_ERR_UNSUPPORTED, "cmh_eval_rank: ap_mode 1 needs a cmh_eval_plan_sets plan");
+    CMH_REQUIRE(plan->ap_mode == 0 || (ntopn == 1 && topn[0] == (k < 0 ? topn[0] : k)), CMH_ERR_ARG,
+                "cmh_eval_rank: ap_mode 1 takes topn = {k}");
 
     ScanArgs sa;
     sa.g_all = global_all ? global_all : w.shard_all;
@@ -578,6 +614,15 @@ extern "C" int cmh_finalize_map(const double* ap_sum, const int64_t* n_rel, int6
     CMH_REQUIRE(nq == 0 || (ap_sum && n_rel), CMH_ERR_ARG, "cmh_finalize_map: NULL inputs");
     finalize_map_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ap_sum, n_rel, nq, k, ap, map);
     CMH_LAUNCH_CHECK("finalize_map_kernel");
+    return CMH_OK;
+}
+
+extern "C" int cmh_finalize_map_hits(const double* ap_sum, const uint32_t* hits, int ntopn, int64_t nq, double* ap, float* map,
+                                     void* stream) {
+    CMH_REQUIRE(nq >= 0 && ntopn >= 1 && map, CMH_ERR_ARG, "cmh_finalize_map_hits: bad arguments");
+    CMH_REQUIRE(nq == 0 || (ap_sum && hits), CMH_ERR_ARG, "cmh_finalize_map_hits: NULL inputs");
+    finalize_map_hits_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ap_sum, hits, ntopn, nq, ap, map);
+    CMH_LAUNCH_CHECK("finalize_map_hits_kernel");
     return CMH_OK;
 }
 

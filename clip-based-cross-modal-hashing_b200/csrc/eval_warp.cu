@@ -24,10 +24,10 @@ static inline int odd(int x) { return x | 1; }
 // wpc_fixed > 0: use that many warps per CTA (the plan's q_tile) instead of the largest that fits
 WarpGeom warp_geom(const EvalArgs& a, bool tern, int kind /*0 hist, 1 rank, 2 select*/, int wpc_fixed = 0) {
     WarpGeom g;
-    g.cs = odd(a.cw);
+    g.cs = odd(a.cw * (a.kd > 0 ? a.kd : 1));      // an item = kd sub-codes of cw words (set-valued codes; 1 otherwise)
     g.ls = a.lw ? odd(a.lw) : 1;
     const size_t per_warp_cnt = (size_t)(a.nb + 1) * (kind == 1 ? 8 : 4);
-    const size_t per_warp_q = (size_t)a.cw * 4 * (tern ? 2 : 1) + (size_t)a.lw * 4 + (size_t)CMH_MAX_TOPN * 4;
+    const size_t per_warp_q = (size_t)a.cw * (a.kq > 0 ? a.kq : 1) * 4 * (tern ? 2 : 1) + (size_t)a.lw * 4 + (size_t)CMH_MAX_TOPN * 4;
     const size_t stage = (size_t)W_ROWS * (g.cs * (tern ? 2 : 1) + g.ls) * 4;
     int wpc = (int)((200 * 1024 - stage) / (per_warp_cnt + per_warp_q));
     g.wpc = wpc_fixed > 0 ? wpc_fixed : (wpc < 1 ? 1 : (wpc > 8 ? 8 : wpc));
@@ -51,8 +51,9 @@ __device__ __forceinline__ WarpSmem carve_warp_smem(unsigned char* raw, const Ev
     s.codes = p; p += W_ROWS * cs;
     s.valid = p; if (TERN) p += W_ROWS * cs;
     s.labels = p; p += W_ROWS * ls;
-    s.qs = p + warp * a.cw; p += wpc * a.cw;
-    s.qv = p + warp * a.cw; if (TERN) p += wpc * a.cw;
+    const int qw = a.cw * a.kq;                      // query words per item
+    s.qs = p + warp * qw; p += wpc * qw;
+    s.qv = p + warp * qw; if (TERN) p += wpc * qw;
     s.ql = p + warp * a.lw; p += wpc * a.lw;
     s.hits = p + warp * CMH_MAX_TOPN; p += wpc * CMH_MAX_TOPN;
     uintptr_t c = (reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15;
@@ -62,10 +63,12 @@ __device__ __forceinline__ WarpSmem carve_warp_smem(unsigned char* raw, const Ev
 
 template <bool TERN>
 __device__ __forceinline__ void stage_rows(const EvalArgs& a, const WarpSmem& s, int cs, int ls, int64_t row0, int rows) {
-    for (int i = threadIdx.x; i < rows * a.cw; i += blockDim.x) {
-        const int r = i / a.cw, w = i - r * a.cw;
-        s.codes[r * cs + w] = a.ds[(row0 + r) * a.cw_stride + w];
-        if (TERN) s.valid[r * cs + w] = a.dv[(row0 + r) * a.cw_stride + w];
+    const int iw = a.cw * a.kd;                      // used words per item; in memory an item is kd x cw_stride words
+    for (int i = threadIdx.x; i < rows * iw; i += blockDim.x) {
+        const int r = i / iw, w = i - r * iw;
+        const int64_t src = (row0 + r) * (int64_t)(a.kd * a.cw_stride) + (w / a.cw) * a.cw_stride + (w % a.cw);
+        s.codes[r * cs + w] = a.ds[src];
+        if (TERN) s.valid[r * cs + w] = a.dv[src];
     }
     for (int i = threadIdx.x; i < rows * a.lw; i += blockDim.x) {
         const int r = i / a.lw, w = i - r * a.lw;
@@ -77,9 +80,10 @@ template <bool TERN>
 __device__ __forceinline__ void load_query(const EvalArgs& a, const WarpSmem& s, int64_t q) {
     const int lane = threadIdx.x & 31;
     const bool live = q < a.nq;
-    for (int w = lane; w < a.cw; w += 32) {
-        s.qs[w] = live ? a.qs[q * a.cw_stride + w] : 0u;
-        if (TERN) s.qv[w] = live ? a.qv[q * a.cw_stride + w] : 0u;
+    for (int w = lane; w < a.cw * a.kq; w += 32) {
+        const int64_t src = q * (int64_t)(a.kq * a.cw_stride) + (w / a.cw) * a.cw_stride + (w % a.cw);
+        s.qs[w] = live ? a.qs[src] : 0u;
+        if (TERN) s.qv[w] = live ? a.qv[src] : 0u;
     }
     for (int w = lane; w < a.lw; w += 32) s.ql[w] = live ? a.ql[q * a.lw_stride + w] : 0u;
 }
@@ -88,6 +92,18 @@ template <bool TERN>
 __device__ __forceinline__ int row_bucket(const EvalArgs& a, const WarpSmem& s, int cs, int r) {
     const uint32_t* rc = s.codes + r * cs;
     if (!TERN) {
+        if (a.kq * a.kd > 1) {
+            // set-valued codes (train/DPSIH/_utils.py:15-21): similarity = max over the kq x kd pairs of sub-codes, i.e.
+            // the distance of two items is the MINIMUM of the pairwise sub-code distances
+            int best = a.bits;
+            for (int x = 0; x < a.kq; ++x)
+                for (int y = 0; y < a.kd; ++y) {
+                    int d = 0;
+                    for (int w = 0; w < a.cw; ++w) d += __popc(s.qs[x * a.cw + w] ^ rc[y * a.cw + w]);
+                    best = min(best, d);
+                }
+            return best;
+        }
         int d = 0;
         for (int w = 0; w < a.cw; ++w) d += __popc(s.qs[w] ^ rc[w]);
         return d;
@@ -180,7 +196,7 @@ __global__ void __launch_bounds__(256) rank_warp_kernel(const EvalArgs a, int cs
             const uint32_t rank = c.x + __popc(grp & lt) + 1u;
             const uint32_t rr = c.y + __popc(grp & relmask & lt) + 1u;
             if (rel) {
-                if (rr <= total) acc += (double)__fdiv_rn((float)rr, (float)rank);
+                if (a.ap_mode ? rank <= a.kcut : rr <= total) acc += (double)__fdiv_rn((float)rr, (float)rank);
                 if (rank <= a.nmax) {
                     int i = 0;
                     while (rank > topn.n[i]) ++i;

@@ -21,7 +21,7 @@ from typing import Dict, Optional, Tuple
 import numpy as np
 
 __all__ = [
-    "EvalShape", "CONFIGS", "make_labels", "make_codes_uniform", "make_codes_clustered", "make_case",
+    "EvalShape", "CONFIGS", "make_labels", "make_codes_uniform", "make_codes_clustered", "make_case", "make_set_case",
     "splitmix64", "splitmix_rows",
 ]
 
@@ -149,4 +149,23 @@ def splitmix_rows(seed: int, row0: int, n: int, words: int, bits: int) -> np.nda
     tail = bits - 64 * (words - 1)
     if tail < 64:
         out[:, words - 1] &= np.uint64((1 << tail) - 1)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# set-valued codes (K sub-codes per item: the input of DPSIH's evaluation, train/DPSIH/_utils.py:4-30)
+# ------------------------------------------------------------------------------------------------------------
+def make_set_case(n_query: int, n_db: int, k_sub: int, bits: int, n_labels: int, label_p: float, seed: int,
+                  zero_query_frac: float = 0.05) -> Dict[str, np.ndarray]:
+    """``qB [n_query, k_sub, bits]``, ``rB [n_db, k_sub, bits]`` (+-1 float32) and the two multi-hot label matrices.
+    Every sub-code of an item is a differently perturbed copy of the item's clustered code, so the best of the
+    ``k_sub x k_sub`` pairs really differs from any fixed pair."""
+    rng = np.random.default_rng(seed)
+    q_lab = make_labels(rng, n_query, n_labels, label_p, zero_query_frac)
+    r_lab = make_labels(rng, n_db, n_labels, label_p, 0.0)
+    proto = make_codes_uniform(rng, n_labels, bits)
+    out = {"qL": q_lab, "rL": r_lab}
+    for name, lab in (("qB", q_lab), ("rB", r_lab)):
+        subs = [make_codes_clustered(rng, lab, proto, 0.15 + 0.05 * j) for j in range(k_sub)]
+        out[name] = np.ascontiguousarray(np.stack(subs, axis=1))
     return out

@@ -76,6 +76,9 @@ typedef struct cmh_plan {
     int32_t n_chunks;
     int64_t nq, nd, nq_pad;
     uint64_t workspace_bytes;
+    int32_t kq, kd;        /* sub-codes per query item / database item (1 = plain codes); cmh_eval_plan_sets */
+    int32_t ap_mode;       /* 0: calc_map_k_matrix's AP; 1: textbook AP@k (cmh_eval_rank: hits within k, ranks <= k) */
+    int32_t reserved;
 } cmh_plan;
 
 int cmh_abi_version(void);
@@ -141,6 +144,16 @@ int cmh_eval_plan(int64_t nq, int64_t nd, int bits, int nlab, int ternary, int m
  * on small inputs. */
 int cmh_eval_plan_design(int64_t nq, int64_t nd, int bits, int nlab, int ternary, int max_topn, int design,
                          cmh_plan* plan);
+
+/* Set-valued codes (train/DPSIH/_utils.py:4-30: K embeddings per item, similarity = max over the K x K pairs, i.e.
+ * distance = MIN over the pairs of sub-code Hamming distances): a query item is kq consecutive packed sub-codes
+ * ([nq][kq][words]), a database item kd of them; buckets are that minimum distance (nb = bits + 1).  Binary codes only;
+ * the generic warp kernels walk the passes.  ap_mode 1 makes cmh_eval_rank accumulate the TEXTBOOK AP@k that function
+ * computes - relevant rows ranked within the first k, relrank / rank - with the number of such rows in hits[q][0] (the
+ * caller passes topn = {k}); cmh_finalize_map_hits divides. */
+int cmh_eval_plan_sets(int64_t nq, int64_t nd, int bits, int nlab, int kq, int kd, int ap_mode, cmh_plan* plan);
+/* ap[q] = ap_sum[q] / hits[q * ntopn] (0 when there is no hit), *map = float(sum_q ap[q] / nq)   (DPSIH _utils.py:22-29) */
+int cmh_finalize_map_hits(const double* ap_sum, const uint32_t* hits, int ntopn, int64_t nq, double* ap, float* map, void* stream);
 
 /* Pass 1.  Per-(query, chunk) bucket histograms into `workspace` and their sum over this shard into
  * hist_all / hist_rel: device uint32 [nq][nb] (hist_rel may be NULL when q->labels is NULL). */

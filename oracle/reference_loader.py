@@ -71,3 +71,48 @@ def reference_ap_per_query(qB, rB, qL, rL, k=None, stable=True) -> torch.Tensor:
         for i in range(qB.shape[0]):
             out[i] = float(mod.calc_map_k_matrix(qB[i:i + 1], rB, qL[i:i + 1], rL, k))
     return out
+
+
+# ---- DPSIH's set-based evaluation (`train/DPSIH/_utils.py`) ------------------------------
+_DPSIH_UTILS = os.path.join(REFERENCE_ROOT, "train", "DPSIH", "_utils.py")
+
+
+def load_dpsih():
+    """The reference module holding `mean_average_precision` (set-valued codes)."""
+    if not os.path.isfile(_DPSIH_UTILS):
+        raise FileNotFoundError(f"reference not mounted at {REFERENCE_ROOT}")
+    spec = importlib.util.spec_from_file_location("_cmh_reference_dpsih_utils", _DPSIH_UTILS)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@contextlib.contextmanager
+def stable_argsort_patch():
+    """Inside the block `torch.argsort(x)` behaves as `torch.argsort(x, stable=True)` (`_utils.py:22` ranks with it)."""
+    original = torch.argsort
+
+    def _stable(inp, *args, **kwargs):
+        kwargs["stable"] = True
+        return original(inp, *args, **kwargs)
+
+    torch.argsort = _stable
+    try:
+        yield
+    finally:
+        torch.argsort = original
+
+
+def reference_set_map(qB, rB, qL, rL, topk=None, stable=True):
+    mod = load_dpsih()
+    ctx = stable_argsort_patch() if stable else contextlib.nullcontext()
+    with ctx:
+        return mod.mean_average_precision(qB, rB, qL, rL, topk)
+
+
+def reference_set_ap_per_query(qB, rB, qL, rL, topk=None) -> torch.Tensor:
+    """Per-query AP from the reference itself: one single-query call per row."""
+    out = torch.zeros(qB.shape[0], dtype=torch.float32)
+    for i in range(qB.shape[0]):
+        out[i] = float(reference_set_map(qB[i:i + 1], rB, qL[i:i + 1], rL, topk))
+    return out

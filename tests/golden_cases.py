@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from cmh_b200.synth import CONFIGS, EvalShape, make_case  # noqa: E402
+from cmh_b200.synth import CONFIGS, EvalShape, make_case, make_set_case  # noqa: E402
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -84,7 +84,37 @@ BY_NAME = {c.name: c for c in CASES}
 SMALL = tuple(c for c in CASES if not c.slow)
 
 
-def load_golden(case: GoldenCase) -> Dict[str, np.ndarray]:
+@dataclass(frozen=True)
+class SetCase:
+    """Set-valued codes (K sub-codes per item) through DPSIH's `mean_average_precision` (train/DPSIH/_utils.py:4-30)."""
+    name: str
+    n_query: int
+    n_db: int
+    k_sub: int
+    bits: int
+    n_labels: int
+    label_p: float
+    seed: int
+    ks: Tuple[Optional[int], ...] = (None,)
+
+    def tensors(self) -> Dict[str, np.ndarray]:
+        return make_set_case(self.n_query, self.n_db, self.k_sub, self.bits, self.n_labels, self.label_p, self.seed)
+
+    @property
+    def path(self) -> str:
+        return os.path.join(GOLDEN_DIR, self.name + ".npz")
+
+
+SET_CASES: Tuple[SetCase, ...] = (
+    SetCase("sets_k2_b64", 40, 3000, 2, 64, 24, 0.15, 41, ks=(None, 100, 7)),
+    SetCase("sets_k4_b32", 33, 2111, 4, 32, 21, 0.10, 42, ks=(None, 50)),
+    SetCase("sets_k3_b128", 24, 1500, 3, 128, 80, 0.04, 43, ks=(None, 500, 1)),
+    SetCase("sets_k1_b16", 30, 4000, 1, 16, 21, 0.10, 44, ks=(None, 64)),
+    SetCase("sets_k2_b256", 10, 900, 2, 256, 24, 0.15, 45, ks=(None, 10_000)),
+)
+
+
+def load_golden(case) -> Dict[str, np.ndarray]:
     with np.load(case.path, allow_pickle=False) as z:
         return {k: z[k] for k in z.files}
 

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(cuda_lib):
 
 def test_structs_mirror_header():
     assert ctypes.sizeof(_cabi.CodeSet) == 32            # 3 pointers + int64
-    assert ctypes.sizeof(_cabi.Plan) == 12 * 4 + 3 * 8 + 8
+    assert ctypes.sizeof(_cabi.Plan) == 12 * 4 + 3 * 8 + 8 + 4 * 4
     src = open(HEADER).read()
     fields = re.search(r"typedef struct cmh_plan \{(.*?)\} cmh_plan;", src, re.S).group(1)
     fields = re.sub(r"/\*.*?\*/", "", fields, flags=re.S)

@@ -1198,3 +1198,63 @@ def test_code_buffer_reset_and_cache_switch(dev):
         assert float(d1[0, 0]) == 0.0 and float(d1[1, 0]) == 16.0
     finally:
         cu.set_cache(True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# f4: set-valued codes - DPSIH's `mean_average_precision` (train/DPSIH/_utils.py:4-30)
+# ---------------------------------------------------------------------------------------------------------------
+from golden_cases import SET_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("case", SET_CASES, ids=lambda c: c.name)
+def test_set_map_matches_reference_goldens(dev, case):
+    """The CUDA path behind the reference's signature against vectors generated by the reference's own function."""
+    from cmh_b200 import dpsih_utils as du
+    g = load_golden(case)
+    T = {k: torch.from_numpy(v) for k, v in case.tensors().items()}
+    for k in case.ks:
+        res = du.set_map_detail(T["qB"].to(dev), T["rB"].to(dev), T["qL"], T["rL"], k)
+        np.testing.assert_allclose(res["ap"].cpu().numpy(), g[f"ap_{k_tag(k)}"], rtol=0, atol=TOL)
+        _, hits = orc.set_ap_per_query_counting(T["qB"], T["rB"], T["qL"], T["rL"], k)
+        assert np.array_equal(res["hits"].cpu().numpy(), hits)                        # integer work: exact
+        got = du.mean_average_precision(T["qB"].to(dev), T["rB"].to(dev), T["qL"], T["rL"], k)
+        assert isinstance(got, torch.Tensor) and got.dtype == torch.float32 and got.dim() == 0 and not got.is_cuda
+        assert abs(float(got) - float(g[f"map_{k_tag(k)}"])) < TOL
+    # host inputs + rank, as a caller that never moved its buffers would pass them
+    got = du.mean_average_precision(T["qB"], T["rB"], T["qL"], T["rL"], case.ks[-1], 0)
+    assert abs(float(got) - float(g[f"map_{k_tag(case.ks[-1])}"])) < TOL
+
+
+def test_set_map_edge_cases(dev):
+    from cmh_b200 import dpsih_utils as du
+    from cmh_b200.synth import make_set_case
+    t = make_set_case(37, 5003, 3, 64, 24, 0.15, 91)
+    T = {k: torch.from_numpy(v) for k, v in t.items()}
+    # asymmetric sets: 3 sub-codes per query against 2 per database item (the max is over kq x kd pairs)
+    rB2 = T["rB"][:, :2].contiguous()
+    res = du.set_map_detail(T["qB"].to(dev), rB2.to(dev), T["qL"], T["rL"], 200)
+    qs, ds = t["qB"], t["rB"][:, :2]
+    best = None
+    for x in range(3):
+        for y in range(2):
+            d = 0.5 * (64 - qs[:, x] @ ds[:, y].T)
+            best = d if best is None else np.minimum(best, d)
+    order = np.argsort(best, axis=1, kind="stable")
+    rel = (t["qL"] @ t["rL"].T > 0)
+    for i in range(37):
+        r = rel[i][order[i]][:200]
+        pos = np.nonzero(r)[0] + 1.0
+        want = np.mean(np.arange(1, len(pos) + 1) / pos) if len(pos) else 0.0
+        assert abs(float(res["ap"][i]) - want) < TOL
+    # K = 1 with topk = None is the textbook AP over all relevant rows == calc_map_k_matrix's AP with k = None
+    one = du.set_map_detail(T["qB"][:, :1].to(dev), T["rB"][:, :1].to(dev), T["qL"], T["rL"], None)
+    plain = _cu().map_k_detail(T["qB"][:, 0].contiguous().to(dev), T["rB"][:, 0].contiguous().to(dev), T["qL"], T["rL"], None)
+    np.testing.assert_allclose(one["ap"].cpu().numpy(), plain["ap"].cpu().numpy(), rtol=0, atol=TOL)
+    # no hit at all -> python 0.0; topk = 0 likewise; no query -> the reference's ZeroDivisionError
+    zero_l = torch.zeros_like(T["qL"])
+    assert du.mean_average_precision(T["qB"].to(dev), T["rB"].to(dev), zero_l, T["rL"]) == 0.0
+    assert du.mean_average_precision(T["qB"].to(dev), T["rB"].to(dev), T["qL"], T["rL"], 0) == 0.0
+    with pytest.raises(ZeroDivisionError):
+        du.mean_average_precision(T["qB"][:0].to(dev), T["rB"].to(dev), T["qL"][:0], T["rL"])
+    with pytest.raises(ValueError, match=r"\[n, K, bits\]"):
+        du.mean_average_precision(T["qB"][:, 0].to(dev), T["rB"].to(dev), T["qL"], T["rL"])

@@ -151,3 +151,50 @@ def test_valid_loop_encoder_matches_reference_clip():
         txt = model.encode_text(torch.from_numpy(z["text"]))
     np.testing.assert_allclose(img.numpy(), z["img_feat"], rtol=0, atol=2e-5)
     np.testing.assert_allclose(txt.numpy(), z["txt_feat"], rtol=0, atol=2e-5)
+
+
+# ---- f4: DPSIH's set-based evaluation (train/DPSIH/_utils.py:4-30) -------------------------------------------------
+from golden_cases import SET_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("case", SET_CASES, ids=lambda c: c.name)
+def test_set_oracle_matches_reference_goldens(case):
+    """Both restatements of `mean_average_precision` against vectors generated by the reference's own function
+    (tests/golden/make_golden_sets.py, argsort forced stable)."""
+    g, T = load_golden(case), case.tensors()
+    for k in case.ks:
+        ap, hits = orc.set_ap_per_query_sorted(T["qB"], T["rB"], T["qL"], T["rL"], k)
+        np.testing.assert_allclose(ap.numpy(), g[f"ap_{k_tag(k)}"], rtol=0, atol=TOL)
+        assert abs(float(orc.set_map_sorted(T["qB"], T["rB"], T["qL"], T["rL"], k)) - float(g[f"map_{k_tag(k)}"])) < TOL
+        ap2, hits2 = orc.set_ap_per_query_counting(T["qB"], T["rB"], T["qL"], T["rL"], k)
+        np.testing.assert_allclose(ap2, g[f"ap_{k_tag(k)}"], rtol=0, atol=TOL)
+        assert np.array_equal(hits.numpy(), hits2)
+
+
+def test_set_oracle_known_answers():
+    """Hand-checkable: K = 2 sub-codes of 8 bits; only the BEST pair counts; textbook AP@topk."""
+    q = -np.ones((1, 2, 8), np.float32); q[0, 1] = 1.0                        # sub-codes: all -1, all +1
+    r = np.ones((4, 2, 8), np.float32)
+    r[0, :, :4] = -1                                                          # both sub-codes half/half: best dist 4
+    r[1, 0] = -1                                                              # holds an all -1 sub-code: dist 0
+    r[2, 1, :2] = -1                                                          # (+1 x8, six +1): best dist 0 via q's +1 code
+    r[3, :, :6] = -1                                                          # two -1 x6: best dist min(2, 6) = 2
+    qL = np.array([[1, 0]], np.float32)
+    rL = np.array([[1, 0], [0, 1], [1, 0], [1, 1]], np.float32)
+    # ranking: row1 (0), row2 (0), row3 (2), row0 (4); relevant: rows 0, 2, 3 at ranks 4, 2, 3
+    want_all = (1 / 2 + 2 / 3 + 3 / 4) / 3
+    assert abs(float(orc.set_map_sorted(q, r, qL, rL)) - want_all) < 1e-7
+    assert abs(float(orc.set_map_sorted(q, r, qL, rL, 3)) - (1 / 2 + 2 / 3) / 2) < 1e-7     # rank 4 is cut off
+    assert float(orc.set_map_sorted(q, r, qL, rL, 1)) == 0.0                                  # no relevant row in the top 1
+    ap, hits = orc.set_ap_per_query_counting(q, r, qL, rL, 3)
+    assert hits.tolist() == [2] and abs(ap[0] - (1 / 2 + 2 / 3) / 2) < 1e-12
+
+
+@pytest.mark.skipif(not ref.available(), reason="/root/reference not mounted (GPU box)")
+def test_live_reference_set_map_agrees_with_oracle():
+    case = SET_CASES[0]
+    T = {k: torch.from_numpy(v) for k, v in case.tensors().items()}
+    n = 10
+    for k in (None, 25):
+        want = float(ref.reference_set_map(T["qB"][:n], T["rB"], T["qL"][:n], T["rL"], k))
+        assert abs(float(orc.set_map_sorted(T["qB"][:n], T["rB"], T["qL"][:n], T["rL"], k)) - want) < TOL
