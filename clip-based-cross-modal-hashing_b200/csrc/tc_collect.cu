@@ -1228,7 +1228,7 @@ static size_t tc_smem_bytes(int words) {
 }
 
 extern "C" int cmh_tc_supported(int bits, int ternary) {
-    return (!ternary && (bits == 64 || bits == 128)) ? 1 : 0;
+    return (!ternary && bits >= 1 && bits <= 128) ? 1 : 0;
 }
 
 // launch geometry: query groups of T x 128 rows, database chunks of whole tiles, at most 4 CTAs per SM over the launch
@@ -1251,8 +1251,9 @@ extern "C" int cmh_tc_set_trace(void* device_buffer) { g_tc_trace = (long long*)
 #endif
 
 extern "C" int cmh_tc_plan(int64_t nq, int64_t nd, int bits, int* n_chunks) {
-    CMH_REQUIRE(cmh_tc_supported(bits, 0), CMH_ERR_UNSUPPORTED, "cmh_tc_plan: bits=%d (64 or 128, +-1 codes only)", bits);
+    CMH_REQUIRE(cmh_tc_supported(bits, 0), CMH_ERR_UNSUPPORTED, "cmh_tc_plan: bits=%d (1..128, +-1 codes only)", bits);
     CMH_REQUIRE(nq >= 0 && nd >= 0 && n_chunks, CMH_ERR_ARG, "cmh_tc_plan: bad arguments");
+    bits = tc_eff_bits(bits);
     int64_t g, c, r;
     tc_geometry(nq, nd, bits / 64, &g, &c, &r);
     *n_chunks = (int)c * (TC_BUFS / tc_T(bits / 64));     // candidate segments per query of one launch
@@ -1263,7 +1264,8 @@ namespace cmh {
 int tc_collect_launch(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign, int64_t nd, int bits, int64_t index_base,
                       const int32_t* thr, int K, int seg_base, int seg_total, int seg_cap, uint64_t* cand, uint32_t* cnt,
                       uint32_t* aux, int probe, bool skip_cnt_zero, cudaStream_t st) {
-    CMH_REQUIRE(cmh_tc_supported(bits, 0), CMH_ERR_UNSUPPORTED, "cmh_tc_collect: bits=%d (64 or 128, +-1 codes only)", bits);
+    CMH_REQUIRE(cmh_tc_supported(bits, 0), CMH_ERR_UNSUPPORTED, "cmh_tc_collect: bits=%d (1..128, +-1 codes only)", bits);
+    bits = tc_eff_bits(bits);
     CMH_REQUIRE(nq >= 0 && nd >= 0 && seg_cap >= 1 && K >= 0 && index_base >= 0 && index_base + nd <= (1ll << 32),
                 CMH_ERR_ARG, "cmh_tc_collect: bad sizes");
     if (nq == 0) return CMH_OK;
@@ -1392,6 +1394,7 @@ int tc_finalize(const uint64_t* cand, const uint32_t* cnt, const int32_t* thr_li
     return CMH_OK;
 }
 int tc_geometry_segs(int64_t nq, int64_t nd, int bits) {
+    bits = tc_eff_bits(bits);
     int64_t g, c, r;
     tc_geometry(nq, nd, bits / 64, &g, &c, &r);
     return (int)c * (TC_BUFS / tc_T(bits / 64));

@@ -6,6 +6,11 @@
 
 namespace cmh {
 
+// The width a code length runs at on the tensor path: the width of its packed words.  Padding bits are zero on both
+// sides by contract (cmh_pack_codes, cmh_synth_codes), i.e. equal, so they add nothing to a Hamming distance: a 16-bit
+// code IS a 64-bit code whose upper 48 bits agree everywhere, and every distance, threshold and key is the same number.
+inline int tc_eff_bits(int bits) { return bits <= 64 ? 64 : 128; }
+
 // candidate segments one cmh_tc_collect launch over nd rows fills per query (cmh_tc_plan)
 int tc_geometry_segs(int64_t nq, int64_t nd, int bits);
 // the launch itself; skip_zero: cnt / aux of the launch's segments have been zeroed by the caller (one memset per search)

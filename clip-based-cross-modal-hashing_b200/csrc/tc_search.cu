@@ -76,7 +76,8 @@ extern "C" int cmh_tc_search_plan(const cmh_comm* comm, int64_t nq, int64_t nd, 
                                   const int64_t* stripe_row, const int64_t* stripe_index, int64_t n_sample,
                                   const cmh_tc_opts* opts_in, cmh_tc_search* p) {
     CMH_REQUIRE(p, CMH_ERR_ARG, "cmh_tc_search_plan: NULL plan");
-    CMH_REQUIRE(cmh_tc_supported(bits, 0), CMH_ERR_UNSUPPORTED, "cmh_tc_search_plan: bits=%d (64 or 128, +-1 codes only)", bits);
+    CMH_REQUIRE(cmh_tc_supported(bits, 0), CMH_ERR_UNSUPPORTED, "cmh_tc_search_plan: bits=%d (1..128, +-1 codes only)", bits);
+    bits = tc_eff_bits(bits);       // the search runs at the width of the packed words (padding bits agree: same distances)
     CMH_REQUIRE(nq >= 1 && nd >= 0 && nd_total >= nd && K >= 1 && K <= MAX_K, CMH_ERR_ARG,
                 "cmh_tc_search_plan: bad sizes nq=%lld nd=%lld nd_total=%lld K=%d", (long long)nq, (long long)nd,
                 (long long)nd_total, K);

@@ -631,7 +631,7 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     buffers a dict the caller keeps between calls: plan + multi-GB candidate scratch are made once per geometry
     exact_fallback(sub_q) -> [n, K] global keys of the queries whose candidate lists came out short or overflowed"""
     if not tc_supported(q, d, K):
-        raise ValueError("tensor-core top-K needs +-1 codes of 64 or 128 bits and K <= 4096")
+        raise ValueError("tensor-core top-K needs +-1 codes of at most 128 bits and K <= 4096")
     K = int(K)
     dev = q.device
     nq = q.n

@@ -204,7 +204,9 @@ int cmh_topk_merge(const uint64_t* keys_in, int n_lists, int64_t nq, int K, uint
 
 /* ---- top-K retrieval on the tensor cores (tcgen05 / TMEM) ---------------------------------------------------- */
 /* The +-1 int8 GEMM form of calc_hammingDist (utils/calc_utils.py:12: dist = 0.5 * (bits - qB . rB^T)) with the
- * candidate filter fused as the epilogue.  Supported: +-1 codes (no valid plane) of 64 or 128 bits. */
+ * candidate filter fused as the epilogue.  Supported: +-1 codes (no valid plane) of 1..128 bits.  A code runs at the
+ * width of its packed words (64 or 128): padding bits are zero on both sides, i.e. equal, and add nothing to a distance -
+ * distances, thresholds and keys are those of the real code length (cmh_tc_search.bits holds the width the search runs at). */
 int cmh_tc_supported(int bits, int ternary);
 /* Launch geometry of cmh_tc_collect for an (nq, nd) problem on the current device: the database is cut into
  * contiguous chunks, one CTA per (group of 512 / 256 queries, chunk); *n_chunks = the number of private candidate

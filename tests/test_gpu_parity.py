@@ -281,6 +281,50 @@ def test_tc_topk_matches_popc_path(dev, bits, nq, nd, K):
         assert stats["n_fail"] == 0
 
 
+@pytest.mark.parametrize("bits,nq,nd,K", [(16, 40, 2_000_000, 1000), (32, 64, 1_500_000, 1000), (20, 33, 300_000, 100),
+                                          (48, 130, 1_000_003, 500), (96, 70, 400_000, 200), (100, 33, 1_000_000, 1000),
+                                          (1, 5, 100_000, 50), (16, 9, 70_000, 4096)])
+def test_tc_topk_any_code_length(dev, bits, nq, nd, K):
+    """NS1: every +-1 code length up to 128 bits runs on the tensor path at the width of its packed words (padding bits
+    agree on both sides and add nothing to a distance).  Short codes are the tie-heavy regime - 16-bit codes have 17
+    distinct distances, the K-th bucket holds thousands of rows and the row index decides: keys must still equal the popc
+    path and the oracle bit for bit."""
+    from cmh_b200 import engine
+    from cmh_b200.synth import splitmix_rows
+    words = (bits + 63) // 64
+    db = engine.synth_codes(300 + bits, 0, nd, bits, dev)
+    q = engine.synth_codes(400 + bits, 0, nq, bits, dev)
+    assert engine.tc_supported(q, db, K)
+    want = engine.RankPass(q, db, need_labels=False).topk(K, 3)
+    st = {}
+    stride = max(1, nd // 65_536)
+    smp = engine.PackedSet(db.sign[::stride].contiguous(), None, None, -(-nd // stride), bits)
+    got = engine.topk_tc(q, db, K, 3, sample=smp, stats=st)
+    assert torch.equal(got, want)
+    assert torch.equal(engine.topk_tc(q, db, K, 3), want)                      # exact thresholds (full histogram)
+    if bits in (16, 100):
+        ds, qs = splitmix_rows(300 + bits, 0, nd, words, bits), splitmix_rows(400 + bits, 0, nq, words, bits)
+        mask = np.zeros(words, np.uint64)
+        for c in range(bits):
+            mask[c // 64] |= np.uint64(1) << np.uint64(c % 64)
+        oracle = c_oracle.topk_packed(qs, np.broadcast_to(mask, qs.shape).copy(), ds, np.broadcast_to(mask, ds.shape).copy(),
+                                      bits, K, 3)
+        assert np.array_equal(got.cpu().numpy().view(np.uint64), oracle)
+    print(f"bits={bits} nd={nd} K={K}: n_fail={st['n_fail']} of {nq}, candidates/query={float(st['candidates'].sum()) / nq:.0f}")
+
+
+def test_topk_hamming_short_codes_through_the_api(dev):
+    """`topk_hamming` on float codes of 16 / 32 bits over a database large enough for the tensor path, against the sorted
+    oracle (calc_utils.py:30-31, stable)."""
+    rng = np.random.default_rng(77)
+    for bits in (16, 32):
+        rB = (rng.integers(0, 2, size=(1_100_000, bits), dtype=np.int8) * 2 - 1).astype(np.float32)
+        qB = (rng.integers(0, 2, size=(12, bits), dtype=np.int8) * 2 - 1).astype(np.float32)
+        dist, idx = _cu().topk_hamming(torch.from_numpy(qB).to(dev), torch.from_numpy(rB).to(dev), 300)
+        ref_d, ref_i = orc.topk_sorted(qB, rB, 300)
+        assert torch.equal(idx.cpu(), ref_i) and torch.equal(dist.cpu(), ref_d)
+
+
 def test_tc_topk_against_oracle_and_fallback(dev):
     from cmh_b200 import engine
     from cmh_b200.synth import splitmix_rows
