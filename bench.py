@@ -610,25 +610,87 @@ def main_native(args):
     q_hosts = [_host_float_codes(SEED + 1, i * Q, Q).pin_memory() for i in range(n_chunks)]
     db_host = torch.empty((hi - lo, 1), dtype=torch.int64).pin_memory()
     db_host.copy_(db.sign)
-    db_dev = torch.empty_like(db.sign)
-    keys_host = torch.empty((per_rank if world > 1 else Q, K), dtype=torch.int64).pin_memory()
+    # Software pipeline over the steps, all through public calls: DEPTH + 1 device buffers for the shard, the upload of
+    # step i + DEPTH (copy stream) is enqueued when step i is, so it runs under the scans in front of it; queries H2D + pack
+    # on a side stream (the pack's counter read then waits for 2 MB, not for the scan in front of it); keys D2H on a third
+    # stream as soon as the step's verdict is in.  Every step still moves ITS queries and ITS copy of the shard H2D and
+    # its keys D2H inside the timed region.
+    DEPTH = int(os.environ.get("CMH_E2E_DEPTH", "1"))
+    NB = DEPTH + 1
+    PIECES = int(os.environ.get("CMH_E2E_PIECES", "0")) or None
+    db_bufs = [torch.empty_like(db.sign) for _ in range(NB)]
+    keys_hosts = [torch.empty((per_rank if world > 1 else Q, K), dtype=torch.int64).pin_memory() for _ in range(2)]
+    main_stream = torch.cuda.current_stream(dev)
+    q_stream, d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    buf_free = [None] * NB                       # event behind the last search that read db_bufs[j]
+    upload_ms, search_ev = [], []
 
-    def e2e_step(i):
-        # the queries go first (H2D copies share one engine: behind the shard they would wait for all of it)
-        qp = cu.pack_codes(q_hosts[i].to(dev, non_blocking=True), dev)
-        idx = HammingIndex.from_packed_host(db_host, BITS, lo, nd_total=D, out=db_dev, stripes=stripes)
-        k = idx.search_packed(qp, K, gather=False)
-        keys_host.copy_(k, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+    def e2e_upload(i):
+        return HammingIndex.from_packed_host(db_host, BITS, lo, nd_total=D, out=db_bufs[i % NB], stripes=stripes,
+                                             out_free=buf_free[i % NB], pieces=PIECES)
 
-    for i in range(max(1, args.warmup - 1)):
-        e2e_step(i)
+    def e2e_search(i, idx):
+        with torch.cuda.stream(q_stream):
+            qp = cu.pack_codes(q_hosts[i].to(dev, non_blocking=True), dev)
+        qp.sign.record_stream(main_stream)
+        main_stream.wait_stream(q_stream)
+        e_a = torch.cuda.Event(enable_timing=True)
+        e_a.record(main_stream)
+        h = idx.search_packed(qp, K, gather=False, defer=True)
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(main_stream)
+        buf_free[i % NB] = ev
+        search_ev.append((e_a, ev))
+        return h
+
+    def e2e_resolve(i, h):
+        k = h()                                  # verdict of step i (its scan, exchange and merge are complete)
+        if getattr(h, "n_fail", 1):
+            d2h_stream.wait_stream(main_stream)  # redone queries were patched in on the main stream
+        with torch.cuda.stream(d2h_stream):
+            keys_hosts[i % 2].copy_(k, non_blocking=True)
+        k.record_stream(d2h_stream)
+
+    def e2e_run(first, n):
+        last = first + n - 1
+        idxs = {i: e2e_upload(i) for i in range(first, min(last, first + DEPTH - 1) + 1)}
+        h_prev = None
+        for i in range(first, last + 1):
+            idx = idxs.pop(i)
+            h = e2e_search(i, idx)
+            if i + DEPTH <= last:
+                # (after the search: the index's sample gather goes to the main stream and must not sit in front of it)
+                idxs[i + DEPTH] = e2e_upload(i + DEPTH)
+            if h_prev is not None:
+                e2e_resolve(i - 1, h_prev)
+            h_prev = h
+            upload_ms.append(idx.upload_events)
+        e2e_resolve(last, h_prev)
+        torch.cuda.synchronize(dev)
+
+    e2e_run(0, max(NB, args.warmup))
+    upload_ms.clear()
+    search_ev.clear()
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.warmup, args.warmup + args.steps):
-        e2e_step(i)
+    e2e_run(args.warmup, args.steps)
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) / args.steps * 1e3)
+    upload_avg = max_over_ranks(sum(a.elapsed_time(b) for a, b in upload_ms) / max(1, len(upload_ms)))
+    # device time of the searches alone inside the e2e region (main-stream events around each): what is left of a step is
+    # the pack, the waits for the link and the gaps between searches
+    e2e_search_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in search_ev) / max(1, len(search_ev)))
+    e2e_span_ms = max_over_ranks(search_ev[0][0].elapsed_time(search_ev[-1][1]) / max(1, len(search_ev)))
+    # the library's own phase events for searches issued the e2e way (fresh index over an uploaded buffer; un-pipelined pass)
+    st_e = {"time_collect": True, "time_phases": True}
+    for i in range(args.warmup, args.warmup + min(args.steps, 3)):
+        idx_e = e2e_upload(i)
+        qp_e = cu.pack_codes(q_hosts[i].to(dev, non_blocking=True), dev)
+        idx_e.search_packed(qp_e, K, stats=st_e, gather=False)
+    n_e = max(1, st_e.get("timed_searches", 1))
+    e2e_phases = {k_: v / n_e for k_, v in st_e.get("phase_ms_sum", {}).items()}
+    e2e_phases["launch_ms"] = st_e.get("launch_ms")
+    keys_host = keys_hosts[(args.warmup + args.steps - 1) % 2]
     assert torch.equal(keys_host, keys.cpu()), "e2e keys differ from the device-resident run"
     h2d = q_hosts[0].numel() * 4 + db_host.numel() * 8
     d2h = keys_host.numel() * 8
@@ -682,11 +744,13 @@ def main_native(args):
         "dtype": "s8 (+-1 int8 tcgen05 MMA, int32 accumulate; exact integer distances and ranks)", "data": "synthetic",
         "config": config_dict(args, world),
         "e2e": {"value": Q * D / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h,
-                "note": "per step and rank: pinned-host packed database shard (uploaded in row ranges on a copy stream, "
-                        "scanned as they land) + this step's float32 query codes H2D, index build (device-side sample of the "
-                        "first range), pack, one cmh_topk_tc call (scan, all-to-all by query slice, merge + verify), "
-                        "this rank's slice of the top-K keys D2H"},
+                "d2h_bytes_per_step": d2h, "shard_upload_ms": upload_avg, "pipeline_depth": DEPTH,
+                "search_ms_per_step": e2e_search_ms, "search_phase_ms": e2e_phases, "first_search_start_to_last_search_end_ms_per_step": e2e_span_ms,
+                "note": "per step and rank: pinned-host packed database shard (uploaded in row ranges on a copy stream into "
+                        "one of two alternating device buffers, so the upload of step i+1 runs under the scan of step i) + "
+                        "this step's float32 query codes H2D, index build (device-side sample of the first range), pack, "
+                        "one cmh_topk_tc call (scan, all-to-all by query slice, merge + verify), this rank's slice of the "
+                        "top-K keys D2H; steps are software-pipelined, all copies inside the timed region"},
         "gpu_launches": int(launches),
         "parity_check": parity,
         "phase_ms_per_step": phases,

@@ -697,6 +697,7 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
     def finish() -> torch.Tensor:
         fail_event.synchronize()                     # the one host sync of a search: this search's verdict, nothing later
         n_fail = int(fail_host[0])
+        finish.n_fail = n_fail                       # (a deferred caller can tell whether redo work was enqueued)
         if stats is not None:
             stats["n_fail"] = n_fail
             if timed:

@@ -119,12 +119,15 @@ class HammingIndex:
     @classmethod
     def from_packed_host(cls, words: torch.Tensor, bits: int, index_base: int = 0, group=None,
                          nd_total: Optional[int] = None, pieces: Optional[int] = None, out: Optional[torch.Tensor] = None,
-                         device=None, stripes=None) -> "HammingIndex":
+                         device=None, stripes=None, out_free: Optional["torch.cuda.Event"] = None) -> "HammingIndex":
         """Upload packed +-1 codes from (pinned) host memory WITHOUT waiting for the copy: the rows travel in
         ranges on a copy stream (``pieces`` equal ranges after the pilot rows; None = ranges that follow the search's own
         launches), and the first search scans each range as soon as it has landed (the
         pilot rows first), so the upload of a fresh database hides behind the search that needs it.
-        ``out``: optional device tensor [D, words] to upload into (reused between calls)."""
+        ``out``: optional device tensor [D, words] to upload into (reused between calls).  The upload starts once ``out``
+        is no longer read: by default after everything enqueued on the current stream so far; ``out_free`` (an event
+        recorded behind the last reader of ``out``) narrows that, so that with two alternating ``out`` buffers the upload
+        for the NEXT search runs while the current one is still scanning the other buffer."""
         if words.is_cuda:
             return cls.from_packed(words, bits, index_base, group, nd_total, stripes)
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -138,7 +141,10 @@ class HammingIndex:
         words = words.view(torch.int64)
         total = n if nd_total is None else int(nd_total)
         copy_stream = torch.cuda.Stream(dev)
-        copy_stream.wait_stream(torch.cuda.current_stream(dev))      # `out` may still be read by earlier work
+        if out_free is not None:
+            copy_stream.wait_event(out_free)                         # the last reader of `out`, named by the caller
+        else:
+            copy_stream.wait_stream(torch.cuda.current_stream(dev))  # `out` may still be read by earlier work
         world = _sh._world(group)[1]
         stages = _e.tc_pilot_stages(n, total, world)
         n_pilot = stages[-1] if stages else 0
@@ -159,12 +165,16 @@ class HammingIndex:
         ends = sorted({e for e in cand if 0 < e <= n})
         ready, lo = [], 0
         with torch.cuda.stream(copy_stream):
+            t_begin = torch.cuda.Event(enable_timing=True)
+            t_begin.record(copy_stream)
             for hi in ends:
                 dst[lo:hi].copy_(words[lo:hi], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
                 ready.append((hi, ev))
                 lo = hi
+            t_end = torch.cuda.Event(enable_timing=True)
+            t_end.record(copy_stream)
         # the threshold sample is a strided gather of the FIRST range once it has landed (no host-side pass over the
         # database): ~SAMPLE_ROWS rows of the whole database, this shard's share of them.  Any subset of the shard's rows
         # is a valid sample - thresholds are only statistical bounds, exactness never depends on them.
@@ -175,8 +185,10 @@ class HammingIndex:
             cur.wait_event(ready[0][1])
         smp_rows = dst[:head:max(1, head // share)].contiguous() if head else dst[:0]
         sample = PackedSet(smp_rows, None, None, smp_rows.shape[0], bits)
-        return cls(PackedSet(dst, None, None, n, bits), index_base, group, nd_total, sample=sample, ready=ready,
-                   stripes=stripes, assume_binary=nd_total is not None)
+        idx = cls(PackedSet(dst, None, None, n, bits), index_base, group, nd_total, sample=sample, ready=ready,
+                  stripes=stripes, assume_binary=nd_total is not None)
+        idx.upload_events = (t_begin, t_end)         # (measurement aid: how long the link took for this shard)
+        return idx
 
     def _upload_done(self) -> None:
         if self._ready:
