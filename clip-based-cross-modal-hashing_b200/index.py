@@ -5,8 +5,14 @@ The reference only ever ranks inside `calc_map_k_matrix` (`utils/calc_utils.py:3
 query); this class is that ranking, truncated to the first K entries, for databases far beyond what a per-query
 sort can touch.  The database stays packed in HBM (8 B per 64-bit row: 100M rows = 800 MB); queries stream
 through in chunks.  +-1 codes of 64 / 128 bits are searched on the tensor cores (`engine.topk_tc`: int8 GEMM with
-a fused candidate filter, global thresholds, all-gather + merge when sharded); anything else - ternary codes, other
-code lengths, small databases - by two counting passes over the shard (histogram -> threshold -> ordered select).
+a fused candidate filter, global thresholds, all-gather + merge when sharded); anything else - longer codes, small
+databases - by two counting passes over the shard (histogram -> threshold -> ordered select).
+
+Exact zeros (`torch.sign(0) == 0`, train/base.py:141) do not take a database off the tensor cores: a one-GPU index
+splits its rows once into the +-1 rows (searched on the tensor path in a compacted copy, row numbers mapped back -
+compaction keeps the index order, so ties still break by ascending global index) and the few rows holding a zero
+(ranked by the ternary counting kernels); the two key lists of a query are merged (`cmh_topk_merge`).  Queries that
+hold a zero themselves are ranked by the counting passes against the whole database.
 """
 from __future__ import annotations
 
@@ -98,6 +104,21 @@ class HammingIndex:
             stride = max(1, db.n // share)
             rows = db.sign[::stride].contiguous()
             self.sample = PackedSet(rows, None, None, rows.shape[0], db.bits)
+        # ---- a database with exact zeros on one GPU: +-1 rows on the tensor path, the rest by the ternary counting kernels
+        self._hybrid = None
+        if (db.valid is not None and not distributed and not self.stripes and self._ready is None
+                and self.nd_total >= self.TC_MIN_ROWS and _e.tc_supported(PackedSet(db.sign, None, None, db.n, db.bits),
+                                                                          PackedSet(db.sign, None, None, db.n, db.bits))):
+            full = _e._full_valid(PackedSet(db.sign[:1], None, None, 1, db.bits))          # [1, words]: all real bits set
+            pure_mask = (db.valid == full).all(dim=1)
+            pure_rows = torch.nonzero(pure_mask, as_tuple=False).squeeze(1)
+            if pure_rows.numel() * 4 >= db.n * 3:                                          # (mostly zeros: not worth a copy)
+                mixed_rows = torch.nonzero(~pure_mask, as_tuple=False).squeeze(1)
+                pure = PackedSet(db.sign.index_select(0, pure_rows), None, None, int(pure_rows.numel()), db.bits)
+                mixed = PackedSet(db.sign.index_select(0, mixed_rows), db.valid.index_select(0, mixed_rows), None,
+                                  int(mixed_rows.numel()), db.bits)
+                self._hybrid = (HammingIndex(pure, 0, group=False, assume_binary=True), pure_rows + self.index_base,
+                                mixed, mixed_rows + self.index_base)
 
     @classmethod
     def from_codes(cls, rB, device=None, index_base: int = 0, group=None) -> "HammingIndex":
@@ -211,6 +232,9 @@ class HammingIndex:
         verdict (the one host sync of a search), redoes failed queries and returns the keys.  Enqueuing the next chunk
         before resolving the previous one keeps the GPU busy while the host prepares the next call (same stream, same
         scratch: the searches still run one after the other)."""
+        if self._hybrid is not None and q.bits == self.db.bits and 1 <= int(K) <= _e.TC_MAX_K:
+            keys = self._search_hybrid(q, int(K))
+            return (lambda: keys) if defer else keys
         if self.sample is not None and q.valid is None and q.bits == self.db.bits and 1 <= int(K) <= _e.TC_MAX_K:
             ready, self._ready = self._ready, None       # only the first search can overlap the upload
             return _sh.topk_tc_sharded(q, self.db, int(K), self.index_base, self.nd_total, sample=self.sample,
@@ -227,6 +251,43 @@ class HammingIndex:
                 out[:n] = keys[lo:lo + n]
                 keys = out
         return (lambda: keys) if defer else keys
+
+    @staticmethod
+    def _remap(keys: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+        """Keys whose low word is a row number of a compacted subset -> the same keys with the global row index."""
+        if rows.numel() == 0:
+            return keys
+        pad = keys < 0
+        local = (keys & 0xFFFFFFFF).clamp_(max=rows.numel() - 1)
+        return torch.where(pad, keys, (keys & ~0xFFFFFFFF) | rows.index_select(0, local.reshape(-1)).reshape(keys.shape))
+
+    def _search_hybrid(self, q: PackedSet, K: int) -> torch.Tensor:
+        pure_index, pure_rows, mixed, mixed_rows = self._hybrid
+        dev = self.db.device
+        keys = torch.full((q.n, K), -1, dtype=torch.int64, device=dev)
+        if q.valid is None:
+            q_bin, bin_rows, tern_rows = q, None, None
+        else:
+            full = _e._full_valid(PackedSet(q.sign[:1], None, None, 1, q.bits))
+            is_bin = (q.valid == full).all(dim=1)
+            bin_rows = torch.nonzero(is_bin, as_tuple=False).squeeze(1)
+            tern_rows = torch.nonzero(~is_bin, as_tuple=False).squeeze(1)
+            q_bin = PackedSet(q.sign.index_select(0, bin_rows), None, None, int(bin_rows.numel()), q.bits)
+        if q_bin.n:
+            lists = [self._remap(pure_index.search_packed(q_bin, K), pure_rows)]
+            if mixed.n:
+                # the rows that hold a zero: half-integer distances, keys in the same units (bits - dot)
+                lists.append(self._remap(_e.RankPass(q_bin, mixed, need_labels=False, ternary=True).topk(K), mixed_rows))
+            part = lists[0] if len(lists) == 1 else _e.topk_merge(torch.stack(lists), K)
+            if bin_rows is None:
+                keys = part
+            else:
+                keys.index_copy_(0, bin_rows, part)
+        if tern_rows is not None and tern_rows.numel():
+            q_t = PackedSet(q.sign.index_select(0, tern_rows), q.valid.index_select(0, tern_rows), None,
+                            int(tern_rows.numel()), q.bits)
+            keys.index_copy_(0, tern_rows, _e.topk_exact(q_t, self.db, K, self.index_base))
+        return keys
 
     def search_packed_async(self, q: PackedSet, K: int, stats: Optional[dict] = None) -> "PendingSearch":
         """`search_packed` without waiting: the search is enqueued on one of two alternating side streams (each with

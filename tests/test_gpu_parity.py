@@ -1302,3 +1302,47 @@ def test_set_map_edge_cases(dev):
         du.mean_average_precision(T["qB"][:0].to(dev), T["rB"].to(dev), T["qL"][:0], T["rL"])
     with pytest.raises(ValueError, match=r"\[n, K, bits\]"):
         du.mean_average_precision(T["qB"][:, 0].to(dev), T["rB"].to(dev), T["qL"], T["rL"])
+
+
+def test_ternary_database_keeps_the_tensor_path(dev):
+    """Exact zeros in a few rows (`torch.sign(0)`, train/base.py:141) no longer drop a large database to the popc path:
+    the +-1 rows are searched on the tensor cores in a compacted copy, the rows holding a zero by the ternary counting
+    kernels, and the two lists are merged.  Planted near-duplicates with one zeroed entry (distance 0.5) must come out at
+    the top, ties by ascending GLOBAL index, queries holding a zero themselves included."""
+    from cmh_b200 import engine
+    from cmh_b200.index import HammingIndex
+    rng = np.random.default_rng(2024)
+    D, Q, K, bits = 1_200_000, 40, 500, 64
+    rB = (rng.integers(0, 2, size=(D, bits), dtype=np.int8) * 2 - 1).astype(np.float32)
+    qB = (rng.integers(0, 2, size=(Q, bits), dtype=np.int8) * 2 - 1).astype(np.float32)
+    zr, zc = rng.integers(0, D, 400), rng.integers(0, bits, 400)
+    rB[zr, zc] = 0.0                                                  # ~400 rows hold a zero
+    for j in range(10):                                               # planted: query j with one entry zeroed -> distance 0.5
+        row = 1000 + 97_003 * j
+        rB[row] = qB[j]
+        rB[row, j] = 0.0
+        rB[row + 1] = qB[j]                                           # and an exact duplicate right behind it -> distance 0
+    qB[37, 5] = 0.0; qB[38, :3] = 0.0                                 # two queries holding zeros
+    d = _cu().pack_codes(torch.from_numpy(rB).to(dev))
+    q = _cu().pack_codes(torch.from_numpy(qB).to(dev))
+    assert d.valid is not None and q.valid is not None
+    idx = HammingIndex(d, 0, group=False)
+    assert idx._hybrid is not None and idx._hybrid[0].sample is not None          # the +-1 rows are on the tensor path
+    assert idx._hybrid[2].n == len(set(zr.tolist()) | {1000 + 97_003 * j for j in range(10)})
+    n0 = _cabi_launches()
+    keys = idx.search_packed(q, K)
+    want = engine.topk_exact(q, d, K)
+    assert torch.equal(keys, want)
+    for j in range(10):
+        assert keys[j, 0].item() == (0 << 32) | (1001 + 97_003 * j) and keys[j, 1].item() == (1 << 32) | (1000 + 97_003 * j)
+    # through the drop-in API, against the sorted oracle (calc_utils.py:30-31 truncated; includes a query with zeros)
+    sel = [0, 1, 37, 38]
+    dist, ind = _cu().topk_hamming(torch.from_numpy(qB[sel]).to(dev), torch.from_numpy(rB).to(dev), 200)
+    ref_d, ref_i = orc.topk_sorted(qB[sel], rB, 200)
+    assert torch.equal(ind.cpu(), ref_i) and torch.equal(dist.cpu(), ref_d)
+    assert _cabi_launches() > n0
+
+
+def _cabi_launches():
+    from cmh_b200 import _cabi
+    return _cabi.lib().cmh_launch_count()
