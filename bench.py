@@ -167,6 +167,43 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's own per-query path on the host cores
 # ---------------------------------------------------------------------------------------------------------------
+class NumaLocal:
+    """Pinned host buffers of a rank should live on the NUMA node its GPU hangs off: pages of `cudaHostAlloc` are placed
+    where the allocating thread runs (first touch), and an upload that crosses the socket interconnect is bounded by it -
+    eight ranks streaming their shards at once notice.  Inside the block the process runs on the GPU's local CPUs; the
+    previous affinity is restored on exit (the pages stay where they are).  Silent no-op when sysfs does not say."""
+
+    def __init__(self, dev):
+        self.info = {"node": None}
+        self.cpus, self.prev = None, None
+        try:
+            pr = torch.cuda.get_device_properties(dev)
+            bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+            self.info = {"gpu": bdf, "node": node}
+            if node >= 0:
+                cpus = set()
+                for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+                allowed = os.sched_getaffinity(0)
+                self.cpus = (cpus & allowed) or None
+                self.info["local_cpus_allowed"] = len(cpus & allowed)
+        except Exception as e:  # noqa: BLE001
+            self.info["error"] = repr(e)[:80]
+
+    def __enter__(self):
+        if self.cpus:
+            self.prev = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, self.cpus)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            os.sched_setaffinity(0, self.prev)
+        return False
+
+
 def _host_float_codes(seed, row0, n):
     from cmh_b200.synth import splitmix_rows
     w = splitmix_rows(seed, row0, n, 1, BITS)
@@ -607,9 +644,11 @@ def main_native(args):
     # ---- end to end through the public API with host buffers ------------------------------------------------
     # per step: this step's float32 query codes (pinned host) H2D + pack; the packed shard (pinned host) uploaded in row
     # ranges on a copy stream and scanned range by range as it lands; search; this rank's slice of the keys D2H
-    q_hosts = [_host_float_codes(SEED + 1, i * Q, Q).pin_memory() for i in range(n_chunks)]
-    db_host = torch.empty((hi - lo, 1), dtype=torch.int64).pin_memory()
-    db_host.copy_(db.sign)
+    numa = NumaLocal(dev)
+    with numa:                                   # pinned pages on the GPU's NUMA node
+        q_hosts = [_host_float_codes(SEED + 1, i * Q, Q).pin_memory() for i in range(n_chunks)]
+        db_host = torch.empty((hi - lo, 1), dtype=torch.int64).pin_memory()
+        db_host.copy_(db.sign)
     # Software pipeline over the steps, all through public calls: DEPTH + 1 device buffers for the shard, the upload of
     # step i + DEPTH (copy stream) is enqueued when step i is, so it runs under the scans in front of it; queries H2D + pack
     # on a side stream (the pack's counter read then waits for 2 MB, not for the scan in front of it); keys D2H on a third
@@ -619,7 +658,8 @@ def main_native(args):
     NB = DEPTH + 1
     PIECES = int(os.environ.get("CMH_E2E_PIECES", "0")) or None
     db_bufs = [torch.empty_like(db.sign) for _ in range(NB)]
-    keys_hosts = [torch.empty((per_rank if world > 1 else Q, K), dtype=torch.int64).pin_memory() for _ in range(2)]
+    with numa:
+        keys_hosts = [torch.empty((per_rank if world > 1 else Q, K), dtype=torch.int64).pin_memory() for _ in range(2)]
     main_stream = torch.cuda.current_stream(dev)
     q_stream, d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     buf_free = [None] * NB                       # event behind the last search that read db_bufs[j]
@@ -744,7 +784,7 @@ def main_native(args):
         "dtype": "s8 (+-1 int8 tcgen05 MMA, int32 accumulate; exact integer distances and ranks)", "data": "synthetic",
         "config": config_dict(args, world),
         "e2e": {"value": Q * D / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "shard_upload_ms": upload_avg, "pipeline_depth": DEPTH,
+                "d2h_bytes_per_step": d2h, "shard_upload_ms": upload_avg, "pipeline_depth": DEPTH, "pinned_host_numa": numa.info,
                 "search_ms_per_step": e2e_search_ms, "search_phase_ms": e2e_phases, "first_search_start_to_last_search_end_ms_per_step": e2e_span_ms,
                 "note": "per step and rank: pinned-host packed database shard (uploaded in row ranges on a copy stream into "
                         "one of two alternating device buffers, so the upload of step i+1 runs under the scan of step i) + "
