@@ -159,7 +159,8 @@ class ClockSampler:
             inside = self.rows[-3:]
         sm = [r[1] for r in inside]
         reasons = sorted({x for r in inside for x in r[4]})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max((r[2] for r in inside), default=None),
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": max((r[2] for r in inside), default=None),
                 "power_w_max": max((r[3] for r in inside), default=None), "samples": len(inside), "how": self.how,
                 "reasons": reasons}
 
@@ -559,10 +560,16 @@ def main_native(args):
     # the searches themselves do not overlap (same stream, same scratch).  With N GPUs the result stays SHARDED BY QUERY
     # SLICE: rank r merges, verifies and keeps the keys of its slice of the chunk (`gather=False`; an all-gather of the
     # merged keys is one flag away and is what `search_packed` does by default).
-    def run_steps(first, n, stats=None):
+    step_marks = []                              # an event behind every timed search: one-off stalls show in the line
+
+    def run_steps(first, n, stats=None, marks=None):
         pending, keys = None, None
         for i in range(first, first + n):
             h = index.search_packed(chunks[i], K, stats=stats, gather=False, defer=True)
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append(ev)
             if pending is not None:
                 keys = pending()
             pending = h
@@ -574,7 +581,7 @@ def main_native(args):
     launches0 = lib.cmh_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    keys = run_steps(args.warmup, args.steps)
+    keys = run_steps(args.warmup, args.steps, marks=step_marks)
     e1.record()
     barrier()
     launches = lib.cmh_launch_count() - launches0
@@ -582,6 +589,7 @@ def main_native(args):
         sampler.window(t_region0, time.perf_counter())
     clocks = sampler.stop() if rank == 0 else None
     step_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    step_each = [round(a_.elapsed_time(b_), 3) for a_, b_ in zip([e0] + step_marks[:-1], step_marks)]
     value = Q * D / (step_ms * 1e-3)
     # per-phase device times (the library's own CUDA events, cmh_tc_timing) in a separate pass over the timed chunks, each
     # search resolved before the next: reading the events is a host sync that the timed region above does without
@@ -650,8 +658,9 @@ def main_native(args):
         db_host = torch.empty((hi - lo, 1), dtype=torch.int64).pin_memory()
         db_host.copy_(db.sign)
     # Software pipeline over the steps, all through public calls: DEPTH + 1 device buffers for the shard, the upload of
-    # step i + DEPTH (copy stream) is enqueued when step i is, so it runs under the scans in front of it; queries H2D + pack
-    # on a side stream (the pack's counter read then waits for 2 MB, not for the scan in front of it); keys D2H on a third
+    # step i + DEPTH (copy stream) is enqueued when step i is, so it runs under the scans in front of it; queries packed straight from
+    # pinned host memory on a side stream (the kernel reads the float codes over the link: nothing queues behind the shard
+    # on the copy engine, and the pack's counter read waits for 2 MB, not for the scan in front of it); keys D2H on a third
     # stream as soon as the step's verdict is in.  Every step still moves ITS queries and ITS copy of the shard H2D and
     # its keys D2H inside the timed region.
     DEPTH = int(os.environ.get("CMH_E2E_DEPTH", "1"))
@@ -670,8 +679,8 @@ def main_native(args):
                                              out_free=buf_free[i % NB], pieces=PIECES)
 
     def e2e_search(i, idx):
-        with torch.cuda.stream(q_stream):
-            qp = cu.pack_codes(q_hosts[i].to(dev, non_blocking=True), dev)
+        with torch.cuda.stream(q_stream):        # pinned host codes: the pack kernel reads them straight over the link
+            qp = cu.pack_codes(q_hosts[i], dev)
         qp.sign.record_stream(main_stream)
         main_stream.wait_stream(q_stream)
         e_a = torch.cuda.Event(enable_timing=True)
@@ -725,7 +734,7 @@ def main_native(args):
     st_e = {"time_collect": True, "time_phases": True}
     for i in range(args.warmup, args.warmup + min(args.steps, 3)):
         idx_e = e2e_upload(i)
-        qp_e = cu.pack_codes(q_hosts[i].to(dev, non_blocking=True), dev)
+        qp_e = cu.pack_codes(q_hosts[i], dev)
         idx_e.search_packed(qp_e, K, stats=st_e, gather=False)
     n_e = max(1, st_e.get("timed_searches", 1))
     e2e_phases = {k_: v / n_e for k_, v in st_e.get("phase_ms_sum", {}).items()}
@@ -780,7 +789,7 @@ def main_native(args):
     algo_bytes = (hi - lo) * 8 + Q * 8                       # packed shard + packed queries, read once
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": step_ms, "ms_each_step": step_each, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "s8 (+-1 int8 tcgen05 MMA, int32 accumulate; exact integer distances and ranks)", "data": "synthetic",
         "config": config_dict(args, world),
         "e2e": {"value": Q * D / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,

@@ -158,8 +158,9 @@ def _pack_codes_enqueue(x, device, binarize: bool, counters: torch.Tensor):
         t = t.unsqueeze(0)
     if t.dim() != 2:
         raise ValueError(f"codes must be [n, bits], got {tuple(t.shape)}")
-    td = _on(t, device)
-    sign, valid = _e.pack_codes_device(td, counters)
+    # pinned host codes are read by the pack kernel straight over the link (no staging copy of the floats in HBM)
+    td = t if (not t.is_cuda and t.is_pinned() and t.stride(-1) == 1) else _on(t, device)
+    sign, valid = _e.pack_codes_device(td, counters, device)
     return _PendingCodes(owner, kind, device, sign, valid, td.shape[0], td.shape[1], counters, binarize)
 
 

@@ -103,21 +103,35 @@ def _row_major(x: torch.Tensor) -> torch.Tensor:
     return x
 
 
-def pack_codes_device(x: torch.Tensor, counters: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Enqueue K1 on float / integer codes ``[n, bits]`` (CUDA).  Returns (sign, valid) int64 [n, words];
-    ``counters`` (int64 [2], CUDA) is incremented by (#zeros, #entries outside {-1, 0, +1})."""
-    _require_cuda(x, "codes")
+def pack_codes_device(x: torch.Tensor, counters: torch.Tensor, device: Optional[torch.device] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Enqueue K1 on float / integer codes ``[n, bits]``.  Returns (sign, valid) int64 [n, words] on the device;
+    ``counters`` (int64 [2], CUDA) is incremented by (#zeros, #entries outside {-1, 0, +1}).
+
+    ``x`` is a CUDA tensor - or a PINNED host tensor (``device`` then names the GPU): page-locked memory is mapped into the
+    device's address space, so the kernel reads the codes straight over the link and only the packed words (1/32 of the
+    bytes for float32) ever exist in HBM; no staging copy, nothing queued on the copy engines."""
+    if not x.is_cuda:
+        if not x.is_pinned() or device is None:
+            raise RuntimeError("codes must be a CUDA tensor or a pinned host tensor with a target device "
+                               "(cmh_b200 has no CPU path)")
+        dev = torch.device(device)
+    else:
+        dev = x.device
     x = _row_major(_as_2d(x, "codes"))
+    if not x.is_cuda and not x.is_pinned():      # (a layout fix-up made a pageable copy)
+        x = x.to(dev)
     n, bits = x.shape
     if bits < 1 or bits > _cabi.CMH_MAX_BITS:
         raise ValueError(f"code length {bits} outside [1, {_cabi.CMH_MAX_BITS}]")
     words = (bits + 63) // 64
-    sign = torch.empty((n, words), dtype=torch.int64, device=x.device)
-    valid = torch.empty((n, words), dtype=torch.int64, device=x.device)
-    with torch.cuda.device(x.device):
+    sign = torch.empty((n, words), dtype=torch.int64, device=dev)
+    valid = torch.empty((n, words), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
         check(_cabi.lib().cmh_pack_codes(_ptr(x), _TORCH_DTYPE[x.dtype], n, bits, x.stride(0) if n > 1 else bits,
-                                         _ptr(sign), _ptr(valid), _ptr(counters), _stream(x.device)),
+                                         _ptr(sign), _ptr(valid), _ptr(counters), _stream(dev)),
               "cmh_pack_codes")
+    if not x.is_cuda:
+        sign._cmh_keepalive = x                  # the kernel is still reading the host pages when this returns
     return sign, valid
 
 

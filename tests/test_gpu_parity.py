@@ -79,6 +79,26 @@ def test_pack_codes_strided_and_odd_values(dev):
         _cu().pack_codes(big)                                            # raw activations are rejected loudly
 
 
+def test_pack_codes_from_pinned_host_memory(dev):
+    """Pinned host codes are packed straight over the link (the kernel reads the mapped pages; no staging copy): same
+    words and counters as the device path, and the drop-in call accepts them like any other host tensor."""
+    from cmh_b200 import engine
+    rng = np.random.default_rng(5)
+    x = rng.integers(-1, 2, size=(5003, 64)).astype(np.float32)
+    host = torch.from_numpy(x).pin_memory()
+    counters = torch.zeros(2, dtype=torch.int64, device=dev)
+    sign, valid = engine.pack_codes_device(host, counters, dev)
+    ws, wv, nz, _ = orc.pack_codes(x)
+    assert sign.is_cuda and np.array_equal(sign.cpu().numpy().view(np.uint64), ws)
+    assert np.array_equal(valid.cpu().numpy().view(np.uint64), wv) and counters.tolist() == [nz, 0]
+    with pytest.raises(RuntimeError, match="pinned"):
+        engine.pack_codes_device(torch.from_numpy(x), counters, dev)              # pageable memory is not device-visible
+    case = BY_NAME["small_b64_l24"]
+    g, T = load_golden(case), _T(case)
+    got = _cu().calc_map_k_matrix(T["qB"].pin_memory(), T["rB"].pin_memory(), T["qL"], T["rL"], None, 0)
+    assert abs(float(got) - float(g["map_all"])) < TOL
+
+
 @pytest.mark.parametrize("nlab", [1, 21, 24, 64, 80, 291])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.int64, torch.uint8])
 def test_pack_labels_bit_exact(dev, nlab, dtype):
