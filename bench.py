@@ -694,7 +694,7 @@ def main_native(args):
 
     def e2e_resolve(i, h):
         k = h()                                  # verdict of step i (its scan, exchange and merge are complete)
-        if getattr(h, "n_fail", 1):
+        if getattr(h, "verdict", {}).get("n_fail", 1):
             d2h_stream.wait_stream(main_stream)  # redone queries were patched in on the main stream
         with torch.cuda.stream(d2h_stream):
             keys_hosts[i % 2].copy_(k, non_blocking=True)

@@ -708,10 +708,12 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
         stats["n_launches"] = sum(1 for i in range(p.n_spans) if p.span_hi[i] > p.span_lo[i])
         stats["exch_width"] = int(p.exch_width)
 
+    verdict: dict = {}
+
     def finish() -> torch.Tensor:
         fail_event.synchronize()                     # the one host sync of a search: this search's verdict, nothing later
         n_fail = int(fail_host[0])
-        finish.n_fail = n_fail                       # (a deferred caller can tell whether redo work was enqueued)
+        verdict["n_fail"] = n_fail                   # (a deferred caller can tell whether redo work was enqueued)
         if stats is not None:
             stats["n_fail"] = n_fail
             if timed:
@@ -739,4 +741,7 @@ def topk_tc(q: PackedSet, d: PackedSet, K: int, index_base: int = 0, sample: Opt
                 keys.index_copy_(0, rows, redo)
         return keys if sliced else keys[:nq]
 
+    # (the dict, not the function itself, is what the closure writes to: a function that names itself in its own body is a
+    # reference cycle, and cycles keep the 65 MB key tensors alive until the cyclic collector happens to run)
+    finish.verdict = verdict
     return finish if defer else finish()
