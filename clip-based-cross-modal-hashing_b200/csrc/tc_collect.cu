@@ -224,10 +224,13 @@ struct TcArgs {
 };
 
 // smem: [A: T tiles x {+-1, +-S, bias digits}][B: STAGES tiles][bias weights][packed ring][barriers][tmem slot][park]
-template <int WORDS, int T, int TC_STAGES, bool WK = false>
+// KBITS: the code length the operands are expanded to - 32 (codes of up to 32 bits: the low half of the packed word, one
+// K-step per field), 64 or 128
+template <int WORDS, int T, int TC_STAGES, bool WK = false, int KBITS = WORDS * 64>
 __global__ void __launch_bounds__(WK ? TC_THREADS_WK : TC_THREADS, 1) tc_collect_kernel(const TcArgs a) {
     constexpr int NTHREADS = WK ? TC_THREADS_WK : TC_THREADS;
-    constexpr int KBYTES = WORDS * 64;           // int8 elements (= bytes) per row
+    constexpr int KBYTES = KBITS;                // int8 elements (= bytes) per row
+    static_assert(KBITS == WORDS * 64 || (WORDS == 1 && KBITS == 32), "operand width");
     constexpr int KSTEPS = KBYTES / 32;          // tcgen05.mma kind::i8 has K = 32
     constexpr int CHUNKS = KBYTES / 16;          // 16-byte K chunks per row
     constexpr int FIELD = WORDS == 1 ? 8 : 10;   // bits per packed dot-product field
@@ -432,11 +435,9 @@ __global__ void __launch_bounds__(WK ? TC_THREADS_WK : TC_THREADS, 1) tc_collect
                     for (int x = 0; x < WORDS; ++x) cur[h][x] = row < c_end ? __ldg(a.d + row * WORDS + x) : 0ull;
                 }
             }
-            mbar_arrive(&r_empty[slot]);
-            if (pt == 0) {
-                mbar_wait(&r_empty[slot], (i / TC_RING) & 1);
-                issue(i + TC_RING);              // refill the slot everyone has just read
-            }
+            // (the slot is handed back BELOW, after the words have been used: an arrive right behind the loads can be
+            // performed while they are still queued - measured with dense hits: the refill for tile i + 8 then lands first
+            // and rows of this warp come out as the rows eight tiles further on)
             if (pt == 0) TC_TRACE(1, i, 2);
             mbar_wait(&b_empty[s], ((i / TC_STAGES) & 1) ^ 1);
             if (pt == 0) TC_TRACE(1, i, 3);
@@ -453,6 +454,13 @@ __global__ void __launch_bounds__(WK ? TC_THREADS_WK : TC_THREADS, 1) tc_collect
             fence_proxy_async_smem();            // generic-proxy stores -> visible to the tensor core (async proxy)
             if (pt == 0) TC_TRACE(1, i, 5);
             mbar_arrive(&b_full[s]);
+            // the ring slot goes back only now: the loaded words have been consumed by the stores above and the fence has
+            // drained this thread's memory operations, so no read of the slot can still be in flight when it is refilled
+            mbar_arrive(&r_empty[slot]);
+            if (pt == 0) {
+                mbar_wait(&r_empty[slot], (i / TC_RING) & 1);
+                issue(i + TC_RING);              // refill the slot everyone has read
+            }
             if (pt == 0) TC_TRACE(1, i, 6);
         }
     } else if (WK && warp >= TC_MMA_WARPS + TC_PROD_WARPS + TC_EPI_WARPS) {
@@ -1220,9 +1228,9 @@ extern "C" int cmh_tc_set_workers(int mode) {
     g_tc_workers_mode = mode;
     return CMH_OK;
 }
-static size_t tc_smem_bytes(int words) {
+static size_t tc_smem_bytes(int words, int kbytes) {
     const int st = tc_stages(words), T = tc_T(words);
-    return (size_t)T * (2 * TC_M * words * 64 + TC_M * 32) + (size_t)st * TC_N * words * 64 + TC_NM * 32 +
+    return (size_t)T * (2 * TC_M * kbytes + TC_M * 32) + (size_t)st * TC_N * kbytes + TC_NM * 32 +
            (size_t)TC_RING * TC_N * words * 8 + (2 * st + 2 * TC_BUFS + 2 * TC_RING) * 8 + 16 +
            (size_t)TC_EPI_WARPS * TC_BACKLOG * TC_PARK_WORDS * 4;
 }
@@ -1255,8 +1263,8 @@ extern "C" int cmh_tc_plan(int64_t nq, int64_t nd, int bits, int* n_chunks) {
     CMH_REQUIRE(nq >= 0 && nd >= 0 && n_chunks, CMH_ERR_ARG, "cmh_tc_plan: bad arguments");
     bits = tc_eff_bits(bits);
     int64_t g, c, r;
-    tc_geometry(nq, nd, bits / 64, &g, &c, &r);
-    *n_chunks = (int)c * (TC_BUFS / tc_T(bits / 64));     // candidate segments per query of one launch
+    tc_geometry(nq, nd, tc_words(bits), &g, &c, &r);
+    *n_chunks = (int)c * (TC_BUFS / tc_T(tc_words(bits)));     // candidate segments per query of one launch
     return CMH_OK;
 }
 
@@ -1270,8 +1278,8 @@ int tc_collect_launch(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign
                 CMH_ERR_ARG, "cmh_tc_collect: bad sizes");
     if (nq == 0) return CMH_OK;
     int64_t n_qgroups, n_chunks, chunk_rows;
-    tc_geometry(nq, nd, bits / 64, &n_qgroups, &n_chunks, &chunk_rows);
-    const int words = bits / 64;
+    const int words = tc_words(bits);
+    tc_geometry(nq, nd, words, &n_qgroups, &n_chunks, &chunk_rows);
     const int n_segs = (int)n_chunks * (TC_BUFS / tc_T(words));
     CMH_REQUIRE(seg_base >= 0 && seg_base + n_segs <= seg_total, CMH_ERR_ARG,
                 "cmh_tc_collect: segments [%d, %d) do not fit seg_total=%d (see cmh_tc_plan)", seg_base, seg_base + n_segs,
@@ -1296,9 +1304,15 @@ int tc_collect_launch(const uint64_t* q_sign, int64_t nq, const uint64_t* d_sign
     // (K = 0: loose thresholds, 20-30x the candidates) saturate the one worker per group and are faster with the warps
     // working their own queues off.  128-bit codes: the worker state does not fit next to 2 x 64 KB of operands.
     const bool workers = tc_workers_mode() == 1 || (tc_workers_mode() < 0 && words == 1 && K > 0 && !(probe & 128));
-    const size_t smem = tc_smem_bytes(words) + (workers ? (size_t)TC_WK_WORDS * 4 : 0);
+    const size_t smem = tc_smem_bytes(words, bits) + (workers ? (size_t)TC_WK_WORDS * 4 : 0);
     const dim3 grid((unsigned)n_qgroups, (unsigned)n_chunks);
-    if (workers && words == 1) {
+    if (workers && bits == 32) {
+        CMH_CUDA(cudaFuncSetAttribute(tc_collect_kernel<1, 4, 6, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_collect_kernel<1, 4, 6, true, 32><<<grid, TC_THREADS_WK, smem, st>>>(a);
+    } else if (bits == 32) {
+        CMH_CUDA(cudaFuncSetAttribute(tc_collect_kernel<1, 4, 6, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_collect_kernel<1, 4, 6, false, 32><<<grid, TC_THREADS, smem, st>>>(a);
+    } else if (workers && words == 1) {
         CMH_CUDA(cudaFuncSetAttribute(tc_collect_kernel<1, 4, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_collect_kernel<1, 4, 6, true><<<grid, TC_THREADS_WK, smem, st>>>(a);
     } else if (words == 1) {
@@ -1396,8 +1410,8 @@ int tc_finalize(const uint64_t* cand, const uint32_t* cnt, const int32_t* thr_li
 int tc_geometry_segs(int64_t nq, int64_t nd, int bits) {
     bits = tc_eff_bits(bits);
     int64_t g, c, r;
-    tc_geometry(nq, nd, bits / 64, &g, &c, &r);
-    return (int)c * (TC_BUFS / tc_T(bits / 64));
+    tc_geometry(nq, nd, tc_words(bits), &g, &c, &r);
+    return (int)c * (TC_BUFS / tc_T(tc_words(bits)));
 }
 }  // namespace cmh
 

@@ -9,7 +9,10 @@ namespace cmh {
 // The width a code length runs at on the tensor path: the width of its packed words.  Padding bits are zero on both
 // sides by contract (cmh_pack_codes, cmh_synth_codes), i.e. equal, so they add nothing to a Hamming distance: a 16-bit
 // code IS a 64-bit code whose upper 48 bits agree everywhere, and every distance, threshold and key is the same number.
-inline int tc_eff_bits(int bits) { return bits <= 64 ? 64 : 128; }
+// Codes of up to 32 bits use the low half of their word only: one K-step per field instead of two (K = 32 of tcgen05.mma
+// kind::i8 is exactly such a code), half the expansion work for the producers.
+inline int tc_eff_bits(int bits) { return bits <= 32 ? 32 : (bits <= 64 ? 64 : 128); }
+inline int tc_words(int eff_bits) { return (eff_bits + 63) / 64; }
 
 // candidate segments one cmh_tc_collect launch over nd rows fills per query (cmh_tc_plan)
 int tc_geometry_segs(int64_t nq, int64_t nd, int bits);

@@ -77,7 +77,7 @@ extern "C" int cmh_tc_search_plan(const cmh_comm* comm, int64_t nq, int64_t nd, 
                                   const cmh_tc_opts* opts_in, cmh_tc_search* p) {
     CMH_REQUIRE(p, CMH_ERR_ARG, "cmh_tc_search_plan: NULL plan");
     CMH_REQUIRE(cmh_tc_supported(bits, 0), CMH_ERR_UNSUPPORTED, "cmh_tc_search_plan: bits=%d (1..128, +-1 codes only)", bits);
-    bits = tc_eff_bits(bits);       // the search runs at the width of the packed words (padding bits agree: same distances)
+    bits = tc_eff_bits(bits);       // the search runs at 32 / 64 / 128 bits (padding bits agree: same distances)
     CMH_REQUIRE(nq >= 1 && nd >= 0 && nd_total >= nd && K >= 1 && K <= MAX_K, CMH_ERR_ARG,
                 "cmh_tc_search_plan: bad sizes nq=%lld nd=%lld nd_total=%lld K=%d", (long long)nq, (long long)nd,
                 (long long)nd_total, K);
@@ -449,7 +449,7 @@ extern "C" int cmh_topk_tc(const cmh_tc_search* plan, const cmh_comm* comm, cons
     CMH_REQUIRE(p.opts.exact_thresholds || p.n_sample == 0 || sample_sign, CMH_ERR_ARG, "cmh_topk_tc: NULL sample");
     cudaStream_t st = (cudaStream_t)stream;
     Search s{p, comm, reinterpret_cast<unsigned char*>(workspace), st, timing, std::min(p.bits + 1, (p.bits - 1) / 2 + 2)};
-    const int nb = p.bits + 1, K = p.K, words = p.bits / 64;      // (s.nb: buckets of the exchanged candidate histograms)
+    const int nb = p.bits + 1, K = p.K, words = tc_words(p.bits);      // (s.nb: buckets of the exchanged candidate histograms)
     const int64_t nq = p.nq, nq_all = p.per_rank * world;
     int rc;
     if (timing) { timing->n_phase = 0; timing->n_collect = 0; }

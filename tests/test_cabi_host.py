@@ -77,7 +77,8 @@ def test_search_plan_geometry(cuda_lib):
     assert small.n_stages == 0 and small.n_prefix_cuts == 0 and small.n_spans == 1 and small.span_index[0] == 7
     assert small.n_sample == 300_000
     short = engine.tc_search_plan(None, 100, 300_000, 300_000, 32, 50, [(0, 0)], 0, exact_thresholds=True)
-    assert short.bits == 64                       # a 32-bit code runs at the width of its packed word (NS1)
+    assert short.bits == 32                       # codes of up to 32 bits: one K-step per field (NS1)
+    assert engine.tc_search_plan(None, 100, 300_000, 300_000, 48, 50, [(0, 0)], 0, exact_thresholds=True).bits == 64
     assert engine.tc_search_plan(None, 100, 300_000, 300_000, 96, 50, [(0, 0)], 0, exact_thresholds=True).bits == 128
     with pytest.raises(ValueError):
         engine.tc_search_plan(None, 100, 1000, 1000, 129, 50, [(0, 0)], 0)           # beyond two packed words: no tensor path

@@ -1366,3 +1366,39 @@ def test_ternary_database_keeps_the_tensor_path(dev):
 def _cabi_launches():
     from cmh_b200 import _cabi
     return _cabi.lib().cmh_launch_count()
+
+
+@pytest.mark.parametrize("bits,thr_v,K,workers", [(32, 8, 0, -1), (32, 8, 0, 1), (32, 8, 1 << 30, 0), (16, 3, 0, -1),
+                                                  (64, 24, 0, -1), (64, 24, 1 << 30, -1), (48, 14, 0, 1), (128, 44, 0, -1)])
+def test_tc_collect_candidate_sets_under_dense_hits(dev, cuda_lib, bits, thr_v, K, workers):
+    """One bare `cmh_tc_collect` launch with thresholds far looser than any search uses (0.3 - 3 % of all pairs qualify: the
+    parking queues are full, shared memory is saturated) must still return EXACTLY the pairs at dist <= thr - brute force
+    on the host.  Regression test of a write-after-read race on the packed-word ring: a slot was handed back right behind
+    the loads that read it, and under this kind of pressure the refill for tile i + 8 could land before they were performed
+    (rows of one producer warp then came out as the rows eight tiles further on)."""
+    from cmh_b200 import _cabi, engine
+    nq, nd = 256, 256 * 600 + 77
+    words = (bits + 63) // 64
+    db = engine.synth_codes(300 + bits, 0, nd, bits, dev)
+    q = engine.synth_codes(400 + bits, 0, nq, bits, dev)
+    tb = engine.TcBuffers(nq, [nd], bits, 1 << 22, dev)
+    thr = torch.full((nq,), thr_v, dtype=torch.int32, device=dev)
+    cuda_lib.cmh_tc_set_workers(workers)
+    try:
+        _cabi.check(cuda_lib.cmh_tc_collect(engine._ptr(q.sign), nq, engine._ptr(db.sign), nd, bits, 0, engine._ptr(thr), K, 0,
+                                            tb.seg_total, tb.seg_cap, engine._ptr(tb.cand), engine._ptr(tb.cnt),
+                                            engine._ptr(tb.aux), engine._stream(dev)), "cmh_tc_collect")
+        torch.cuda.synchronize()
+    finally:
+        cuda_lib.cmh_tc_set_workers(-1)
+    cnt = tb.cnt.cpu().numpy().astype(np.int64)
+    cand = tb.cand.cpu().numpy().view(np.uint64)
+    assert cnt.max() <= tb.seg_cap, "a candidate segment overflowed: enlarge the test's capacity"
+    qs, ds = q.sign.cpu().numpy().view(np.uint64), db.sign.cpu().numpy().view(np.uint64)
+    for qi in range(nq):
+        dist = np.bitwise_count(qs[qi][None, :] ^ ds).sum(1)
+        want = np.nonzero(dist <= thr_v)[0]
+        keys = np.concatenate([cand[qi, s, :cnt[s, qi]] for s in range(tb.seg_total)])
+        got_rows = np.sort((keys & np.uint64(0xFFFFFFFF)).astype(np.int64))
+        assert np.array_equal(got_rows, want), f"query {qi}: {len(want)} pairs wanted, {len(got_rows)} collected"
+        assert np.array_equal((keys >> np.uint64(33)).astype(np.int64), dist[(keys & np.uint64(0xFFFFFFFF)).astype(np.int64)])
