@@ -336,8 +336,9 @@ def topk_hamming(qB, rB, K: int, rank=0):
         stride = max(1, d.n // 65_536)
         rows = d.sign[::stride].contiguous()
         keys = _e.topk_tc(q, d, kk, sample=_e.PackedSet(rows, None, None, rows.shape[0], d.bits))
-    elif d.n >= _TC_MIN_ROWS and d.valid is not None and bool(_e._cabi.lib().cmh_tc_supported(d.bits, 0)) and kk <= _e.TC_MAX_K:
-        # exact zeros in a large database: the +-1 rows still go to the tensor path (`index.HammingIndex`, hybrid split)
+    elif d.n >= _TC_MIN_ROWS and bool(_e._cabi.lib().cmh_tc_supported(d.bits, 0)) and kk <= _e.TC_MAX_K:
+        # exact zeros in a large database (or in some queries): the +-1 rows / queries still go to the tensor path
+        # (`index.HammingIndex`: hybrid split of the rows, split of the queries)
         from .index import HammingIndex
         keys = HammingIndex(d, 0, group=False).search_packed(q, kk)
     else:

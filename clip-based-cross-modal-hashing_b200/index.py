@@ -85,6 +85,7 @@ class HammingIndex:
                 torch.distributed.all_reduce(t, group=group)
                 nd_total = int(t.item())
         self.nd_total = int(nd_total)
+        self._distributed = bool(distributed)
         # every rank must take the same path: the tensor cores need +-1 codes (no valid plane) on ALL shards
         tc_ok = db.valid is None and _e.tc_supported(db, db)
         if distributed and not assume_binary:
@@ -232,7 +233,11 @@ class HammingIndex:
         verdict (the one host sync of a search), redoes failed queries and returns the keys.  Enqueuing the next chunk
         before resolving the previous one keeps the GPU busy while the host prepares the next call (same stream, same
         scratch: the searches still run one after the other)."""
-        if self._hybrid is not None and q.bits == self.db.bits and 1 <= int(K) <= _e.TC_MAX_K:
+        if (q.valid is not None and not self._distributed and q.bits == self.db.bits and 1 <= int(K) <= _e.TC_MAX_K
+                and (self._hybrid is not None or self.sample is not None)):
+            keys = self._split_queries(q, int(K), stats)       # zeros in some queries: the others keep the fast path
+            return (lambda: keys) if defer else keys
+        if self._hybrid is not None and q.valid is None and q.bits == self.db.bits and 1 <= int(K) <= _e.TC_MAX_K:
             keys = self._search_hybrid(q, int(K))
             return (lambda: keys) if defer else keys
         if self.sample is not None and q.valid is None and q.bits == self.db.bits and 1 <= int(K) <= _e.TC_MAX_K:
@@ -261,33 +266,33 @@ class HammingIndex:
         local = (keys & 0xFFFFFFFF).clamp_(max=rows.numel() - 1)
         return torch.where(pad, keys, (keys & ~0xFFFFFFFF) | rows.index_select(0, local.reshape(-1)).reshape(keys.shape))
 
-    def _search_hybrid(self, q: PackedSet, K: int) -> torch.Tensor:
-        pure_index, pure_rows, mixed, mixed_rows = self._hybrid
-        dev = self.db.device
-        keys = torch.full((q.n, K), -1, dtype=torch.int64, device=dev)
-        if q.valid is None:
-            q_bin, bin_rows, tern_rows = q, None, None
-        else:
-            full = _e._full_valid(PackedSet(q.sign[:1], None, None, 1, q.bits))
-            is_bin = (q.valid == full).all(dim=1)
-            bin_rows = torch.nonzero(is_bin, as_tuple=False).squeeze(1)
-            tern_rows = torch.nonzero(~is_bin, as_tuple=False).squeeze(1)
+    def _split_queries(self, q: PackedSet, K: int, stats) -> torch.Tensor:
+        """Queries that hold an exact zero are ranked by the counting passes against the whole database; the +-1 queries
+        of the same chunk take the index's fast path (one GPU)."""
+        full = _e._full_valid(PackedSet(q.sign[:1], None, None, 1, q.bits))
+        is_bin = (q.valid == full).all(dim=1)
+        bin_rows = torch.nonzero(is_bin, as_tuple=False).squeeze(1)
+        tern_rows = torch.nonzero(~is_bin, as_tuple=False).squeeze(1)
+        keys = torch.full((q.n, K), -1, dtype=torch.int64, device=self.db.device)
+        if bin_rows.numel():
             q_bin = PackedSet(q.sign.index_select(0, bin_rows), None, None, int(bin_rows.numel()), q.bits)
-        if q_bin.n:
-            lists = [self._remap(pure_index.search_packed(q_bin, K), pure_rows)]
-            if mixed.n:
-                # the rows that hold a zero: half-integer distances, keys in the same units (bits - dot)
-                lists.append(self._remap(_e.RankPass(q_bin, mixed, need_labels=False, ternary=True).topk(K), mixed_rows))
-            part = lists[0] if len(lists) == 1 else _e.topk_merge(torch.stack(lists), K)
-            if bin_rows is None:
-                keys = part
-            else:
-                keys.index_copy_(0, bin_rows, part)
-        if tern_rows is not None and tern_rows.numel():
+            keys.index_copy_(0, bin_rows, self.search_packed(q_bin, K, stats))
+        if tern_rows.numel():
             q_t = PackedSet(q.sign.index_select(0, tern_rows), q.valid.index_select(0, tern_rows), None,
                             int(tern_rows.numel()), q.bits)
-            keys.index_copy_(0, tern_rows, _e.topk_exact(q_t, self.db, K, self.index_base))
+            self._upload_done()
+            keys.index_copy_(0, tern_rows, _e.topk_exact(q_t, self.db, K, self.index_base, self.stripes))
         return keys
+
+    def _search_hybrid(self, q: PackedSet, K: int) -> torch.Tensor:
+        """+-1 queries against a database that holds exact zeros: tensor path over the +-1 rows, ternary counting kernels
+        over the rest, merge."""
+        pure_index, pure_rows, mixed, mixed_rows = self._hybrid
+        lists = [self._remap(pure_index.search_packed(q, K), pure_rows)]
+        if mixed.n:
+            # the rows that hold a zero: half-integer distances, keys in the same units (bits - dot)
+            lists.append(self._remap(_e.RankPass(q, mixed, need_labels=False, ternary=True).topk(K), mixed_rows))
+        return lists[0] if len(lists) == 1 else _e.topk_merge(torch.stack(lists), K)
 
     def search_packed_async(self, q: PackedSet, K: int, stats: Optional[dict] = None) -> "PendingSearch":
         """`search_packed` without waiting: the search is enqueued on one of two alternating side streams (each with

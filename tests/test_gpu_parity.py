@@ -1361,6 +1361,15 @@ def test_ternary_database_keeps_the_tensor_path(dev):
     ref_d, ref_i = orc.topk_sorted(qB[sel], rB, 200)
     assert torch.equal(ind.cpu(), ref_i) and torch.equal(dist.cpu(), ref_d)
     assert _cabi_launches() > n0
+    # a +-1 database with zeros only in some QUERIES: those go the exact way, the rest of the chunk stays on the tensor path
+    rB2 = np.where(rB == 0.0, 1.0, rB).astype(np.float32)
+    d2 = _cu().pack_codes(torch.from_numpy(rB2).to(dev))
+    assert d2.valid is None
+    idx2 = HammingIndex(d2, 0, group=False)
+    assert idx2._hybrid is None and idx2.sample is not None
+    st = {}
+    assert torch.equal(idx2.search_packed(q, K, stats=st), engine.topk_exact(q, d2, K))
+    assert st.get("n_launches", 0) >= 1                                # (stats come from the tensor-core search of the +-1 queries)
 
 
 def _cabi_launches():
