@@ -1017,7 +1017,7 @@ __global__ void __launch_bounds__(THREADS) topk_finalize_kernel(const uint64_t* 
                                                                     const uint32_t* __restrict__ cnt,
                                                                     const int32_t* __restrict__ thr_limit, int64_t nq,
                                                                     int n_chunks, int seg_cap, int K, int64_t nd, int partial,
-                                                                    int width, uint64_t* __restrict__ keys,
+                                                                    int width, int order_slack, uint64_t* __restrict__ keys,
                                                                     uint32_t* __restrict__ fail_flags,
                                                                     uint32_t* __restrict__ fail_count) {
     constexpr int BLOCK = THREADS * SEG_IT;
@@ -1061,7 +1061,15 @@ __global__ void __launch_bounds__(THREADS) topk_finalize_kernel(const uint64_t* 
             s_T = T;
             // buckets above thr_limit may be incomplete (launches with different thresholds): the K-th distance must
             // not come from there
-            s_keep = (cum > MAXK || (thr_limit != nullptr && T > thr_limit[q])) ? -1 : (int)cum;
+            // More candidates at or below the K-th bucket than the sort buffer holds (short codes: the K-th bucket of a
+            // 16-bit code holds thousands of rows and the index decides).  The buckets below T always fit (fewer than
+            // `want` rows); of bucket T only the first rows in STORED order are kept - exact when that order is the index
+            // order up to a bounded displacement: order_slack = 256 says a query's candidates are appended tile by tile
+            // (one segment per chunk: operand widths up to 64 bits), so the `want` lowest indices of the bucket are among
+            // its first want + 255 stored entries; -1 = no such bound (two interleaved segments per chunk at 128 bits,
+            // caller-built segments): the query is then flagged as before.
+            const bool fits = cum <= MAXK || (order_slack >= 0 && want + order_slack <= (int64_t)MAXK);
+            s_keep = (!fits || (thr_limit != nullptr && T > thr_limit[q])) ? -1 : (int)(cum < (int64_t)MAXK ? cum : (int64_t)MAXK);
         }
         __syncthreads();
         fail = s_keep < 0;
@@ -1392,18 +1400,19 @@ int tc_merge_verify(const uint64_t* lists, int n_lists, int64_t nq_lists, int64_
     return CMH_OK;
 }
 int tc_finalize(const uint64_t* cand, const uint32_t* cnt, const int32_t* thr_limit, int64_t nq, int n_chunks, int seg_cap, int K,
-                int64_t nd, int partial, int width, uint64_t* keys, uint32_t* fail_flags, uint32_t* fail_count, cudaStream_t st) {
+                int64_t nd, int partial, int width, int order_slack, uint64_t* keys, uint32_t* fail_flags, uint32_t* fail_count,
+                cudaStream_t st) {
     if (nq == 0) return CMH_OK;
     CMH_CUDA(cudaMemsetAsync(fail_count, 0, 4, st));
     // the short variant holds at most 2048 candidates at or below the list's last bucket: for lists of a few hundred keys
     // (6+ shards at K = 1000); a query that holds more is flagged and redone exactly, so the choice only costs time
     if (partial && width <= 512)
         topk_finalize_kernel<256, 2048><<<(unsigned)nq, 256, 0, st>>>(cand, cnt, nullptr, nq, n_chunks, seg_cap, K, nd, partial, width,
-                                                                     keys, fail_flags, fail_count);
+                                                                     order_slack, keys, fail_flags, fail_count);
     else
         topk_finalize_kernel<FIN_THREADS, FIN_MAX><<<(unsigned)nq, FIN_THREADS, 0, st>>>(cand, cnt, partial ? nullptr : thr_limit, nq, n_chunks,
-                                                                                        seg_cap, K, nd, partial, width, keys, fail_flags,
-                                                                                        fail_count);
+                                                                                        seg_cap, K, nd, partial, width, order_slack, keys,
+                                                                                        fail_flags, fail_count);
     CMH_LAUNCH_CHECK("topk_finalize_kernel");
     return CMH_OK;
 }
@@ -1500,7 +1509,7 @@ extern "C" int cmh_topk_finalize(const uint64_t* cand, const uint32_t* cnt, cons
     if (nq == 0) return CMH_OK;
     CMH_REQUIRE(cand && cnt && keys && fail_flags && fail_count, CMH_ERR_ARG, "cmh_topk_finalize: NULL pointer");
     CMH_REQUIRE(nq <= 0x7fffffffll, CMH_ERR_UNSUPPORTED, "cmh_topk_finalize: too many queries per call");
-    return tc_finalize(cand, cnt, thr_limit, nq, n_chunks, seg_cap, K, nd, partial, partial ? width : K, keys, fail_flags,
+    return tc_finalize(cand, cnt, thr_limit, nq, n_chunks, seg_cap, K, nd, partial, partial ? width : K, -1, keys, fail_flags,
                        fail_count, (cudaStream_t)stream);
 }
 

@@ -34,7 +34,10 @@ int tc_count_flags(const uint32_t* flags, int64_t n, uint32_t* count, cudaStream
 // lists [n_lists][nq_lists][W]; the first nq queries of every block are merged
 int tc_merge_verify(const uint64_t* lists, int n_lists, int64_t nq_lists, int64_t nq, int W, int K, int64_t nd_total,
                     const int32_t* thr_limit, uint64_t* keys_out, uint32_t* fail_flags, cudaStream_t st);
+// order_slack: >= 0 when a query's candidates are stored in index order up to a displacement of that many rows (256: one
+// segment per chunk, appended tile by tile); -1 when nothing is known about the stored order
 int tc_finalize(const uint64_t* cand, const uint32_t* cnt, const int32_t* thr_limit, int64_t nq, int n_chunks, int seg_cap, int K,
-                int64_t nd, int partial, int width, uint64_t* keys, uint32_t* fail_flags, uint32_t* fail_count, cudaStream_t st);
+                int64_t nd, int partial, int width, int order_slack, uint64_t* keys, uint32_t* fail_flags, uint32_t* fail_count,
+                cudaStream_t st);
 
 }  // namespace cmh

@@ -496,7 +496,7 @@ extern "C" int cmh_topk_tc(const cmh_tc_search* plan, const cmh_comm* comm, cons
     if ((rc = s.mark(PH_MAIN))) return rc;
     // ---- finalize -------------------------------------------------------------------------------------------------------
     if (world == 1) {
-        if ((rc = tc_finalize(s.cand(), s.cnt(), thr_limit, nq, p.seg_total, p.seg_cap, K, p.nd_total, 0, K, keys, fail_flags,
+        if ((rc = tc_finalize(s.cand(), s.cnt(), thr_limit, nq, p.seg_total, p.seg_cap, K, p.nd_total, 0, K, p.bits <= 64 ? 256 : -1, keys, fail_flags,
                               fail_count, st)))
             return rc;
         if ((rc = s.mark(PH_FINALIZE))) return rc;
@@ -508,7 +508,7 @@ extern "C" int cmh_topk_tc(const cmh_tc_search* plan, const cmh_comm* comm, cons
     uint32_t* flags_slice = reinterpret_cast<uint32_t*>(s.ws + p.off_flags);
     uint32_t* part_flags = flags_slice + nq_all;                           // finalize's own verdicts (the marker carries them)
     if (nq_all > nq) CMH_CUDA(cudaMemsetAsync(part + nq * W, 0xff, (size_t)(nq_all - nq) * W * 8, st));
-    if ((rc = tc_finalize(s.cand(), s.cnt(), nullptr, nq, p.seg_total, p.seg_cap, K, p.nd_total, 1, W, part, part_flags, fail_count,
+    if ((rc = tc_finalize(s.cand(), s.cnt(), nullptr, nq, p.seg_total, p.seg_cap, K, p.nd_total, 1, W, p.bits <= 64 ? 256 : -1, part, part_flags, fail_count,
                           st)))
         return rc;
     if ((rc = s.mark(PH_FINALIZE))) return rc;

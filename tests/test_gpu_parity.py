@@ -303,7 +303,7 @@ def test_tc_topk_matches_popc_path(dev, bits, nq, nd, K):
 
 @pytest.mark.parametrize("bits,nq,nd,K", [(16, 40, 2_000_000, 1000), (32, 64, 1_500_000, 1000), (20, 33, 300_000, 100),
                                           (48, 130, 1_000_003, 500), (96, 70, 400_000, 200), (100, 33, 1_000_000, 1000),
-                                          (1, 5, 100_000, 50), (16, 9, 70_000, 4096)])
+                                          (1, 5, 100_000, 50), (16, 9, 70_000, 4096), (16, 24, 6_000_000, 3000)])
 def test_tc_topk_any_code_length(dev, bits, nq, nd, K):
     """NS1: every +-1 code length up to 128 bits runs on the tensor path at the width of its packed words (padding bits
     agree on both sides and add nothing to a distance).  Short codes are the tie-heavy regime - 16-bit codes have 17
@@ -331,6 +331,10 @@ def test_tc_topk_any_code_length(dev, bits, nq, nd, K):
                                       bits, K, 3)
         assert np.array_equal(got.cpu().numpy().view(np.uint64), oracle)
     print(f"bits={bits} nd={nd} K={K}: n_fail={st['n_fail']} of {nq}, candidates/query={float(st['candidates'].sum()) / nq:.0f}")
+    if (bits, K) == (16, 3000):
+        # ~4.9K candidates at or below the K-th bucket - more than the 4096 keys finalize sorts: it keeps the first rows of
+        # that bucket in stored order (index order up to one 256-row tile) instead of sending the query to the exact path
+        assert float(st["candidates"].sum()) / nq > 4096 and st["n_fail"] == 0
 
 
 def test_topk_hamming_short_codes_through_the_api(dev):
