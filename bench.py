@@ -717,7 +717,7 @@ def main_native(args):
         e2e_resolve(last, h_prev)
         torch.cuda.synchronize(dev)
 
-    e2e_run(0, max(NB, args.warmup))
+    e2e_run(0, max(1, min(n_chunks, max(NB, args.warmup))))     # (never beyond the chunks that exist: --warmup 0 --steps 1)
     upload_ms.clear()
     search_ev.clear()
     barrier()
