@@ -81,13 +81,25 @@ __global__ void __launch_bounds__(256) pack_codes_f32_fast(const float* __restri
         for (int u = 0; u < PACK_UNROLL; ++u)
             v[u] = w0 + u < n_words ? __ldcs(x + ((w0 + u) << 5) + lane) : 1.f;
         uint32_t sw = 0, vw = 0xffffffffu;
+        // Fast trip: what `torch.sign` / the argmax heads emit is +-1 almost everywhere, so only the sign plane is voted
+        // (compare + vote + select per element) while one predicate per lane remembers whether everything it saw was
+        // +-1; a single vote afterwards sends the 16 words through the full classification (zeros, other values) only
+        // when something else turned up.  (r02p capture of the version that voted both planes: ALU pipe 89 % busy.)
+        bool plain = true;
 #pragma unroll
         for (int u = 0; u < PACK_UNROLL; ++u) {
-            const bool nz = v[u] != 0.f;
             const uint32_t s = __ballot_sync(0xffffffffu, v[u] > 0.f);
-            const uint32_t z = __ballot_sync(0xffffffffu, nz);
-            n_odd += (nz && fabsf(v[u]) != 1.f) ? 1u : 0u;
-            if (lane == u) { sw = s; vw = z; }
+            plain = plain && fabsf(v[u]) == 1.f;
+            if (lane == u) sw = s;
+        }
+        if (!__all_sync(0xffffffffu, plain)) {
+#pragma unroll
+            for (int u = 0; u < PACK_UNROLL; ++u) {
+                const bool nz = v[u] != 0.f;
+                const uint32_t z = __ballot_sync(0xffffffffu, nz);
+                n_odd += (nz && fabsf(v[u]) != 1.f) ? 1u : 0u;
+                if (lane == u) vw = z;
+            }
         }
         if (lane < PACK_UNROLL && w0 + lane < n_words) {
             n_zero += (uint32_t)__popc(~vw);
